@@ -1,0 +1,249 @@
+"""ctypes wrapper around the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / ``--impl reference`` leg.  The product package
+``sqmc_b200`` never imports this module.
+
+Determinants cross the boundary as arrays of shape (n, 2) uint64 = little-endian
+128-bit integers, the memory layout of the reference's ``integer(ik)``
+(src/types.f90:26).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "sqmc_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_longlong, C.c_double
+        L.orc_chem_new.restype = vp
+        L.orc_chem_new.argtypes = [C.c_char_p, i32, i32, i32, vp, i32, i32, i32]
+        L.orc_heg_new.restype = vp
+        L.orc_heg_new.argtypes = [i32, dbl, i32, i32, dbl]
+        L.orc_hubbardk_new.restype = vp
+        L.orc_hubbardk_new.argtypes = [i32, i32, dbl, dbl, i32, i32]
+        L.orc_free.argtypes = [vp]
+        L.orc_norb.argtypes = [vp]
+        L.orc_nint.restype = i64
+        L.orc_nint.argtypes = [vp]
+        L.orc_get_chem.argtypes = [vp] * 8
+        L.orc_get_heg.argtypes = [vp] * 4
+        L.orc_get_hubbardk.argtypes = [vp] * 4
+        L.orc_elements.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.orc_build_upper.restype = i64
+        L.orc_build_upper.argtypes = [vp, i64, vp, vp, i32]
+        L.orc_get_upper.argtypes = [vp, vp, vp, vp]
+        L.orc_matvec_upper.argtypes = [i64, vp, vp, vp, vp, vp]
+        L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
+        L.orc_hci.argtypes = [vp, vp, i32, i32, i32]
+        L.orc_hci_ndets.restype = i64
+        L.orc_hci_ndets.argtypes = [vp]
+        L.orc_hci_niter.argtypes = [vp]
+        L.orc_hci_get.argtypes = [vp] * 9
+        L.orc_hci_nritz.restype = i64
+        L.orc_hci_nritz.argtypes = [vp]
+        L.orc_hci_get_ritz.argtypes = [vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def dets_to_u64(dets):
+    """list/array of python ints -> (n,2) uint64 little-endian 128-bit."""
+    out = np.zeros((len(dets), 2), dtype=np.uint64)
+    for k, d in enumerate(dets):
+        d = int(d)
+        out[k, 0] = d & 0xFFFFFFFFFFFFFFFF
+        out[k, 1] = d >> 64
+    return out
+
+
+def u64_to_ints(a):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 2)
+    return [int(lo) | (int(hi) << 64) for lo, hi in a]
+
+
+class System:
+    """One model system (chem / heg / hubbardk) held by the oracle."""
+
+    def __init__(self, handle, model):
+        if not handle:
+            raise RuntimeError("oracle: system construction failed")
+        self.h = handle
+        self.model = model
+        self.norb = lib().orc_norb(handle)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- constructors -------------------------------------------------
+    @staticmethod
+    def chem(fcidump, norb, nelec, nup, orbsym, time_sym=False, z=1, hf_symmetry=999):
+        sym = np.ascontiguousarray(orbsym, dtype=np.int32)
+        h = lib().orc_chem_new(str(fcidump).encode(), norb, nelec, nup, _p(sym), int(time_sym), z, hf_symmetry)
+        s = System(h, "chem")
+        s.nelec, s.nup, s.ndn, s.time_sym, s.z = nelec, nup, nelec - nup, bool(time_sym), z
+        return s
+
+    @staticmethod
+    def heg(n_dim, r_s, nelec, nup, cutoff_radius):
+        s = System(lib().orc_heg_new(n_dim, r_s, nelec, nup, cutoff_radius), "heg")
+        s.nelec, s.nup, s.ndn, s.n_dim = nelec, nup, nelec - nup, n_dim
+        return s
+
+    @staticmethod
+    def hubbardk(l_x, l_y, t, U, nup, ndn):
+        s = System(lib().orc_hubbardk_new(l_x, l_y, t, U, nup, ndn), "hubbardk")
+        s.nelec, s.nup, s.ndn = nup + ndn, nup, ndn
+        return s
+
+    # ---- tables -------------------------------------------------------
+    def chem_tables(self):
+        n1 = self.norb + 1
+        nint = lib().orc_nint(self.h)
+        integrals = np.zeros(nint)
+        c2 = np.zeros(n1 * n1, dtype=np.int32)
+        order = np.zeros(n1, dtype=np.int32)
+        sym = np.zeros(self.norb, dtype=np.int32)
+        oe = np.zeros(self.norb)
+        enuc = C.c_double()
+        hf = np.zeros(4, dtype=np.uint64)
+        lib().orc_get_chem(self.h, _p(integrals), _p(c2), _p(order), _p(sym), _p(oe), C.addressof(enuc), _p(hf))
+        return dict(integrals=integrals, combine_2=c2, orb_order=order, orbital_symmetries=sym,
+                    orbital_energies=oe, enuc=enuc.value,
+                    hf_up=int(hf[0]) | (int(hf[1]) << 64), hf_dn=int(hf[2]) | (int(hf[3]) << 64))
+
+    def heg_tables(self):
+        kv = np.zeros(self.n_dim * self.norb)
+        L = C.c_double()
+        krel = np.zeros(self.norb * 3, dtype=np.int32)
+        lib().orc_get_heg(self.h, _p(kv), C.addressof(L), _p(krel))
+        return dict(k_vectors=kv.reshape(self.norb, self.n_dim), length_cell=L.value, k_rel=krel.reshape(self.norb, 3))
+
+    def hubbardk_tables(self):
+        kv = np.zeros(2 * self.norb, dtype=np.int32)
+        ke = np.zeros(self.norb)
+        u = C.c_double()
+        lib().orc_get_hubbardk(self.h, _p(kv), _p(ke), C.addressof(u))
+        return dict(k_vectors=kv.reshape(self.norb, 2), k_energies=ke, ubyn=u.value)
+
+    # ---- hot path -----------------------------------------------------
+    def elements(self, iu, id_, ju, jd):
+        iu, id_, ju, jd = (np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 2) for a in (iu, id_, ju, jd))
+        out = np.zeros(len(iu))
+        lib().orc_elements(self.h, len(iu), _p(iu), _p(id_), _p(ju), _p(jd), _p(out))
+        return out
+
+    def build_upper(self, up, dn, incremental=False):
+        """-> (counts int64[n], indices int64[nnz] 1-based, values f64[nnz]) : reference layout."""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        n = len(up)
+        nnz = lib().orc_build_upper(self.h, n, _p(up), _p(dn), int(incremental))
+        counts = np.zeros(n, dtype=np.int64)
+        idx = np.zeros(nnz, dtype=np.int64)
+        val = np.zeros(nnz)
+        lib().orc_get_upper(self.h, _p(counts), _p(idx), _p(val))
+        return counts, idx, val
+
+    def hci(self, eps_var, eps_var_sched=(), n_states=1, max_iters=50, max_dets=0):
+        sched = np.zeros(30)
+        for k, e in enumerate(eps_var_sched):
+            sched[k] = e
+        sched = np.maximum(sched, eps_var)  # do_walk.f90:425
+        lib().orc_hci(self.h, _p(sched), n_states, max_iters, max_dets)
+        n = lib().orc_hci_ndets(self.h)
+        nit = lib().orc_hci_niter(self.h)
+        up = np.zeros((n, 2), dtype=np.uint64)
+        dn = np.zeros((n, 2), dtype=np.uint64)
+        wts = np.zeros(n * n_states)
+        energy = np.zeros(n_states)
+        lnd = np.zeros(nit, dtype=np.int64)
+        lnz = np.zeros(nit, dtype=np.int64)
+        lnr = np.zeros(nit, dtype=np.int64)
+        le = np.zeros(nit * n_states)
+        lib().orc_hci_get(self.h, _p(up), _p(dn), _p(wts), _p(energy), _p(lnd), _p(lnz), _p(lnr), _p(le))
+        nr = lib().orc_hci_nritz(self.h)
+        ritz = np.zeros(nr)
+        lib().orc_hci_get_ritz(self.h, _p(ritz))
+        ritz_per_iter, o = [], 0
+        for k in range(nit):
+            ritz_per_iter.append(ritz[o:o + lnr[k]].reshape(-1, n_states))
+            o += lnr[k]
+        return dict(up=up, dn=dn, wts=wts.reshape(n_states, n).T, energy=energy, ndet=lnd, nnz=lnz,
+                    ritz=ritz_per_iter, iter_energy=le.reshape(nit, n_states))
+
+
+def matvec_upper(counts, idx, val, x):
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    lib().orc_matvec_upper(len(counts), _p(idx), _p(counts), _p(val), _p(x), _p(y))
+    return y
+
+
+def davidson(counts, idx, val, n_states=1, v0=None):
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(counts)
+    evecs = np.zeros(n * n_states)
+    evals = np.zeros(n_states)
+    ritz = np.zeros(4096)
+    nmv = C.c_int()
+    v0p = None
+    if v0 is not None:
+        v0 = np.ascontiguousarray(np.asarray(v0, dtype=np.float64).T.reshape(-1))  # (n,n_states) -> column-major
+        v0p = _p(v0)
+    nl = lib().orc_davidson(n, n_states, _p(idx), _p(counts), _p(val), v0p, _p(evecs), _p(evals), _p(ritz), len(ritz), C.addressof(nmv))
+    return dict(evals=evals, evecs=evecs.reshape(n_states, n).T, ritz=ritz[:min(nl, len(ritz))].reshape(-1, n_states), n_matvec=nmv.value)
+
+
+def projector_step(counts, idx, minus_tau_H, tau, e_trial, w):
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    vals = np.ascontiguousarray(minus_tau_H, dtype=np.float64)
+    w = np.array(w, dtype=np.float64)
+    dw = np.zeros_like(w)
+    lib().orc_projector_step(len(counts), _p(idx), _p(counts), _p(vals), tau, e_trial, _p(w), _p(dw))
+    return w, dw
+
+
+def upper_to_scipy(counts, idx, val):
+    """reference upper-tri layout -> full symmetric scipy CSR (test helper)."""
+    import scipy.sparse as sp
+    n = len(counts)
+    rows = np.repeat(np.arange(n), counts)
+    cols = np.asarray(idx) - 1
+    U = sp.coo_matrix((val, (rows, cols)), shape=(n, n)).tocsr()
+    D = sp.diags(U.diagonal())
+    return (U + U.T - D).tocsr()

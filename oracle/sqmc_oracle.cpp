@@ -1,0 +1,1321 @@
+// =============================================================================
+// sqmc_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// A plain C++ restatement of the reference algorithm (QMC-Cornell/sqmc, Fortran)
+// for the one hot path this repository accelerates: sparse Hamiltonian
+// construction over a determinant list and the repeated sparse H.v inside
+// Davidson / the deterministic projector.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference leg may load this library.
+// The product (sqmc_b200/) never links, imports or calls it.
+//
+// The reference itself (Fortran 90) cannot be compiled in the build container
+// (no Fortran compiler), so this restatement is pinned against the reference's
+// own golden log src/e2e_tests/heg/o_det_ref (orbital order, HF energy,
+// 277/3511 and 9475/165193 dets/nnz, per-iteration Davidson Ritz values and the
+// first 20 CI coefficients); see tests/test_oracle_golden.py.
+// The C2 cc-pVDZ path has no reference output shipped => chem energies are
+// "parity unpinned by the reference" and pinned by this oracle + dense checks.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference/src).  Arithmetic order is kept identical to the Fortran so
+// that the |H|>1e-12 pattern test sees the same floating-point values
+// (compile with -ffp-contract=off; the reference is gfortran -O3 on baseline
+// x86-64, i.e. no FMA contraction: Makefile:52-53).
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+typedef unsigned __int128 det_t;  // integer(ik)=integer(16), types.f90:26 (values < 2^127)
+typedef int64_t i8b;              // types.f90:18
+
+static inline int popcnt(det_t d) {
+  return __builtin_popcountll((uint64_t)d) + __builtin_popcountll((uint64_t)(d >> 64));
+}
+static inline int trailz(det_t d) {  // Fortran trailz; caller guarantees d != 0
+  uint64_t lo = (uint64_t)d;
+  if (lo) return __builtin_ctzll(lo);
+  return 64 + __builtin_ctzll((uint64_t)(d >> 64));
+}
+static inline det_t bit(int k) { return (det_t)1 << k; }
+static inline bool btest(det_t d, int k) { return (d >> k) & 1; }
+static inline det_t maskr(int k) { return k <= 0 ? (det_t)0 : ((k >= 128) ? ~(det_t)0 : (bit(k) - 1)); }
+
+// ---------------------------------------------------------------------------
+// tools.f90:1294-1337 permutation_factor (ik = 16-byte branch)
+// ---------------------------------------------------------------------------
+static inline int permutation_factor(det_t det1, det_t det2) {
+  det_t diff = (det1 > det2) ? (det1 & (det1 - det2)) : (det2 & (det2 - det1));
+  return (popcnt(diff) & 1) ? -1 : 1;
+}
+// tools.f90:1342-1396 permutation_factor2
+static inline void permutation_factor2(det_t det_i, det_t det_j, int &gamma, int &first_i_bit, int &second_i_bit,
+                                       int &first_j_bit, int &second_j_bit) {
+  det_t diff = det_i & ~det_j;
+  first_i_bit = trailz(diff);
+  second_i_bit = trailz(diff & ~bit(first_i_bit));
+  diff = det_j & ~det_i;
+  first_j_bit = trailz(diff);
+  second_j_bit = trailz(diff & ~bit(first_j_bit));
+  diff = det_i & (det_j & ((maskr(first_i_bit) ^ maskr(first_j_bit)) ^ (maskr(second_i_bit) ^ maskr(second_j_bit))));
+  gamma = (popcnt(diff) & 1) ? -1 : 1;
+}
+// chemistry.f90:7162-7227 / heg.f90:3987-4052 excitation_level
+static inline int excitation_level(det_t iu, det_t id, det_t ju, det_t jd) {
+  int lvl = 0;
+  det_t tmp = iu & ~ju;
+  while (tmp != 0) {
+    lvl++;
+    if (lvl > 2) return -1;
+    tmp &= tmp - 1;
+  }
+  tmp = id & ~jd;
+  while (tmp != 0) {
+    lvl++;
+    if (lvl > 2) return -1;
+    tmp &= tmp - 1;
+  }
+  return lvl;
+}
+
+// ---------------------------------------------------------------------------
+// Small symmetric eigensolver (cyclic Jacobi).  Replaces LAPACK dsyev called at
+// more_tools.f90:2204 on the <= (50*n_states)^2 Krylov matrix (third-party,
+// un-vendored, version unpinned: Makefile:13).  Eigenvalues ascending,
+// eigenvectors in columns (column-major, ld = n), like dsyev('V','U').
+// ---------------------------------------------------------------------------
+static void jacobi_eigh(int n, std::vector<double> a /*col-major copy*/, std::vector<double> &evals,
+                        std::vector<double> &evecs) {
+  evecs.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) evecs[(size_t)i * n + i] = 1.0;
+  auto A = [&](int i, int j) -> double & { return a[(size_t)j * n + i]; };
+  auto V = [&](int i, int j) -> double & { return evecs[(size_t)j * n + i]; };
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += A(p, q) * A(p, q);
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = A(p, q);
+        if (std::fabs(apq) < 1e-300) continue;
+        double app = A(p, p), aqq = A(q, q);
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = A(k, p), akq = A(k, q);
+          A(k, p) = c * akp - s * akq;
+          A(k, q) = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = A(p, k), aqk = A(q, k);
+          A(p, k) = c * apk - s * aqk;
+          A(q, k) = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double vkp = V(k, p), vkq = V(k, q);
+          V(k, p) = c * vkp - s * vkq;
+          V(k, q) = s * vkp + c * vkq;
+        }
+      }
+  }
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return A(x, x) < A(y, y); });
+  evals.resize(n);
+  std::vector<double> v2((size_t)n * n);
+  for (int j = 0; j < n; j++) {
+    evals[j] = A(order[j], order[j]);
+    for (int i = 0; i < n; i++) v2[(size_t)j * n + i] = V(i, order[j]);
+  }
+  evecs.swap(v2);
+}
+
+// ---------------------------------------------------------------------------
+// System description.  model: 0 = chem, 1 = heg, 2 = hubbardk
+// ---------------------------------------------------------------------------
+struct System {
+  int model = 0;
+  int norb = 0, nelec = 0, nup = 0, ndn = 0;
+  // --- chem (chemistry.f90 module variables :24-43,104)
+  bool time_sym = false;
+  int z = 1;
+  std::vector<double> integrals;  // 1-based in Fortran; stored 0-based here with index-1
+  std::vector<int> combine_2;     // (norb+1)x(norb+1), 1-based accessor below
+  std::vector<int> orbital_symmetries, orb_order, orb_order_inv;
+  std::vector<double> orbital_energies;
+  double nuclear_nuclear_energy = 0, sqrt2 = 0, sqrt2inv = 0;
+  det_t hf_up = 0, hf_dn = 0;
+  double max_double = 0;
+  // --- heg (heg.f90 module variables)
+  int n_dim = 3, n_max = 0;
+  double r_s = 0, length_cell = 0, cutoff_radius = 0;
+  std::vector<double> k_vectors;   // (n_dim, norb) column-major as in Fortran
+  std::vector<int> k_rel;          // (norb,3)
+  std::vector<int> orb_lut;        // (2n_max+1)^3
+  // --- hubbard k-space (hubbard.f90)
+  int l_x = 0, l_y = 0;
+  double hub_t = 1, hub_U = 0, ubyn = 0;
+  std::vector<int> hk_vectors;     // (2,nsites)
+  std::vector<double> k_energies;
+  // stored sparse H (sparse_mat, commons/common_selected_ci.f90:26-31)
+  std::vector<i8b> H_nonzero_elements, H_indices;
+  std::vector<double> H_values;
+  i8b sparse_ndet = 0;
+  // HCI log
+  std::vector<double> log_ritz;    // Davidson "Iteration, Eigenvalues=" values (all states), concatenated
+  std::vector<i8b> log_ndet, log_nnz, log_nritz;
+  std::vector<double> log_energy;
+  std::vector<det_t> hci_up, hci_dn;
+  std::vector<double> hci_wts, hci_energy;
+
+  int &c2(int i, int j) { return combine_2[(size_t)(j - 1) * (norb + 1) + (i - 1)]; }
+};
+
+// chemistry.f90:9106-9134 integral_index
+static inline i8b integral_index(System &S, int i, int j, int k, int l) {
+  i8b a = S.c2(i, j), b = S.c2(k, l);
+  return (a > b) ? (a * (a - 1)) / 2 + b : (b * (b - 1)) / 2 + a;
+}
+// chemistry.f90:1234-1256 integral_value
+static inline double integral_value(System &S, int p, int q, int r, int s) {
+  return S.integrals[integral_index(S, p, q, r, s) - 1];
+}
+
+// chemistry.f90:1382-1435 one_body
+static double one_body(System &S, det_t up, det_t dn) {
+  double energy = 0.0;
+  int n1 = S.norb + 1;
+  det_t det = up;
+  while (det != 0) {
+    int i = trailz(det) + 1;
+    energy = energy + integral_value(S, i, i, n1, n1);
+    det &= ~bit(i - 1);
+  }
+  if (dn == up) {
+    energy = energy * 2.0;
+  } else if (dn != 0) {
+    det = dn;
+    while (det != 0) {
+      int i = trailz(det) + 1;
+      energy = energy + integral_value(S, i, i, n1, n1);
+      det &= ~bit(i - 1);
+    }
+  }
+  return energy;
+}
+// chemistry.f90:1775-1839 two_body, "usual way" branch (counter_two_body=-10 in
+// HCI runs, :133,1645; the one-entry last_det cache returns the same bits)
+static double two_body(System &S, det_t up, det_t dn) {
+  double exchange = 0.0, direct = 0.0;
+  int norb = S.norb;
+  for (int i = 1; i <= norb; i++)
+    if (btest(up, i - 1))
+      for (int j = i + 1; j <= norb; j++)
+        if (btest(up, j - 1)) exchange = exchange - integral_value(S, i, j, j, i);
+  if (dn == up) {
+    exchange = exchange * 2.0;
+  } else if (dn != 0) {
+    for (int i = 1; i <= norb; i++)
+      if (btest(dn, i - 1))
+        for (int j = i + 1; j <= norb; j++)
+          if (btest(dn, j - 1)) exchange = exchange - integral_value(S, i, j, j, i);
+  }
+  for (int i = 1; i <= norb; i++) {
+    if (btest(up, i - 1)) {
+      for (int j = i + 1; j <= norb; j++)
+        if (btest(up, j - 1)) direct = direct + integral_value(S, i, i, j, j);
+      for (int j = 1; j <= norb; j++)
+        if (btest(dn, j - 1)) direct = direct + integral_value(S, i, i, j, j);
+    }
+    if (btest(dn, i - 1)) {
+      for (int j = i + 1; j <= norb; j++)
+        if (btest(dn, j - 1)) direct = direct + integral_value(S, i, i, j, j);
+    }
+  }
+  return exchange + direct;
+}
+// chemistry.f90:1439-1480 one_body_single
+static double one_body_single(System &S, det_t iu, det_t id, det_t ju, det_t jd) {
+  int n1 = S.norb + 1;
+  if (iu != ju) {
+    int i_bit = trailz(iu & ~ju), j_bit = trailz(ju & ~iu);
+    return permutation_factor(iu, ju) * integral_value(S, i_bit + 1, j_bit + 1, n1, n1);
+  } else {
+    int i_bit = trailz(id & ~jd), j_bit = trailz(jd & ~id);
+    return permutation_factor(id, jd) * integral_value(S, i_bit + 1, j_bit + 1, n1, n1);
+  }
+}
+// chemistry.f90:1845-1930 two_body_single
+static double two_body_single(System &S, det_t iu, det_t id, det_t ju, det_t jd) {
+  double energy = 0.0;
+  det_t same_i, same_j, other;
+  if (iu != ju) { same_i = iu; same_j = ju; other = id; }
+  else          { same_i = id; same_j = jd; other = iu; }
+  int i_bit = trailz(same_i & ~same_j) + 1, j_bit = trailz(same_j & ~same_i) + 1;
+  det_t det = same_i;
+  while (det != 0) {
+    int i = trailz(det) + 1;
+    if (i != i_bit && i != j_bit)
+      energy = energy - integral_value(S, i_bit, i, i, j_bit) + integral_value(S, i_bit, j_bit, i, i);
+    det &= ~bit(i - 1);
+  }
+  det = other;
+  while (det != 0) {
+    int i = trailz(det) + 1;
+    energy = energy + integral_value(S, i_bit, j_bit, i, i);
+    det &= ~bit(i - 1);
+  }
+  return permutation_factor(same_i, same_j) * energy;
+}
+// chemistry.f90:1934-2001 two_body_double
+static double two_body_double(System &S, det_t iu, det_t id, det_t ju, det_t jd) {
+  int gamma, fi, si, fj, sj;
+  if (iu == ju) {
+    permutation_factor2(id, jd, gamma, fi, si, fj, sj);
+    return gamma * (integral_value(S, fi + 1, fj + 1, si + 1, sj + 1) - integral_value(S, fi + 1, sj + 1, si + 1, fj + 1));
+  } else if (id == jd) {
+    permutation_factor2(iu, ju, gamma, fi, si, fj, sj);
+    return gamma * (integral_value(S, fi + 1, fj + 1, si + 1, sj + 1) - integral_value(S, fi + 1, sj + 1, si + 1, fj + 1));
+  } else {
+    fi = trailz(iu & ~ju);
+    fj = trailz(ju & ~iu);
+    si = trailz(id & ~jd);
+    sj = trailz(jd & ~id);
+    return (permutation_factor(iu, ju) * permutation_factor(id, jd)) * integral_value(S, fi + 1, fj + 1, si + 1, sj + 1);
+  }
+}
+// chemistry.f90:1260-1320 hamiltonian_chem
+static double hamiltonian_chem(System &S, det_t iu, det_t id, det_t ju, det_t jd, int excite_level) {
+  double me = 0.0;
+  if (excite_level == 0) {
+    double e1 = one_body(S, iu, id);
+    double e2 = two_body(S, iu, id);
+    me = e1 + e2 + S.nuclear_nuclear_energy;
+  } else if (excite_level == 1) {
+    double e1 = one_body_single(S, iu, id, ju, jd);
+    double e2 = two_body_single(S, iu, id, ju, jd);
+    me = e1 + e2;
+  } else if (excite_level == 2) {
+    me = two_body_double(S, iu, id, ju, jd);
+  }
+  return me;
+}
+// chemistry.f90:1323-1377 hamiltonian_chem_time_sym
+static double hamiltonian_chem_time_sym(System &S, det_t iu, det_t id, det_t ju, det_t jd) {
+  double m1 = 0.0, m2 = 0.0, norm_ketinv = 1.0, norm_bra = 1.0;
+  bool check = true;
+  int lvl;
+  if (ju == jd) norm_ketinv = S.sqrt2inv;
+  if (iu == id) { norm_bra = S.sqrt2; check = false; }
+  if (iu == ju && id == jd) lvl = 0;
+  else lvl = excitation_level(iu, id, ju, jd);
+  if (lvl >= 0) m1 = hamiltonian_chem(S, iu, id, ju, jd, lvl);
+  if (check) {
+    if (ju != jd) {
+      lvl = excitation_level(id, iu, ju, jd);
+      if (lvl >= 0) m2 = hamiltonian_chem(S, id, iu, ju, jd, lvl);
+    } else {
+      m2 = m1;
+    }
+  }
+  return (norm_bra * norm_ketinv) * (m1 + (S.z * m2));
+}
+
+// ---------------------------------------------------------------------------
+// HEG: heg.f90:845-1010 hamiltonian_heg (with find_set_bits :775, get_gamma_exp :811)
+// ---------------------------------------------------------------------------
+static const double PI_ = 3.14159265358979323846264338327950288;
+static inline double ksum2(System &S, int p) {  // sum(k_vectors(:,p)**2), sequential
+  double s = 0.0;
+  for (int d = 0; d < S.n_dim; d++) s += S.k_vectors[(size_t)(p - 1) * S.n_dim + d] * S.k_vectors[(size_t)(p - 1) * S.n_dim + d];
+  return s;
+}
+static inline double kdiff2(System &S, int p, int q) {  // sum((k(:,p)-k(:,q))**2)
+  double s = 0.0;
+  for (int d = 0; d < S.n_dim; d++) {
+    double t = S.k_vectors[(size_t)(p - 1) * S.n_dim + d] - S.k_vectors[(size_t)(q - 1) * S.n_dim + d];
+    s += t * t;
+  }
+  return s;
+}
+static void find_set_bits(det_t det, std::vector<int> &pos) {
+  pos.clear();
+  while (det != 0) {
+    int p = trailz(det) + 1;
+    pos.push_back(p);
+    det &= ~bit(p - 1);
+  }
+}
+static int get_gamma_exp(det_t det, const std::vector<int> &occ, const std::vector<int> &eor_bits) {
+  int g = 0, ptr = 0;
+  for (size_t i = 0; i < eor_bits.size(); i++) {
+    int orb_id = eor_bits[i];
+    if (!btest(det, orb_id - 1)) continue;
+    while (occ[ptr] < orb_id) ptr++;
+    g += ptr;
+  }
+  return g;
+}
+static double hamiltonian_heg(System &S, det_t iu, det_t id, det_t ju, det_t jd, bool abs_only = false) {
+  const double FOUR_PI = 4.0 * PI_;
+  const double EPSILON = 1.0e-15;  // heg.f90:23
+  double me = 0.0;
+  double L3 = S.length_cell * S.length_cell * S.length_cell;  // length_cell**3 -> gfortran: x*x*x
+  if (iu == ju && id == jd) {
+    std::vector<int> ou, od;
+    find_set_bits(iu, ou);
+    find_set_bits(id, od);
+    for (int p : ou) me = me + ksum2(S, p) * 0.5;
+    for (int p : od) me = me + ksum2(S, p) * 0.5;
+    double pot = 0.0;
+    for (size_t i = 0; i < ou.size(); i++)
+      for (size_t j = i + 1; j < ou.size(); j++) pot = pot + FOUR_PI / kdiff2(S, ou[i], ou[j]);
+    for (size_t i = 0; i < od.size(); i++)
+      for (size_t j = i + 1; j < od.size(); j++) pot = pot + FOUR_PI / kdiff2(S, od[i], od[j]);
+    me = me - pot / L3;
+    return me;
+  }
+  det_t eor_up = iu ^ ju, eor_dn = id ^ jd;
+  int n_eor_up = popcnt(eor_up), n_eor_dn = popcnt(eor_dn);
+  if (n_eor_up + n_eor_dn != 4) return 0.0;
+  std::vector<int> eu, ed;
+  find_set_bits(eor_up, eu);
+  find_set_bits(eor_dn, ed);
+  double mom[3] = {0, 0, 0};
+  bool pset = false, qset = false, sset = false;
+  int orb_p = 0, orb_q = 0, orb_s = 0;
+  auto scan = [&](const std::vector<int> &bits, det_t det_i) {
+    for (int orb_id : bits) {
+      if (btest(det_i, orb_id - 1)) {
+        for (int d = 0; d < S.n_dim; d++) mom[d] = mom[d] - S.k_vectors[(size_t)(orb_id - 1) * S.n_dim + d];
+        if (!pset) { orb_p = orb_id; pset = true; }
+      } else {
+        for (int d = 0; d < S.n_dim; d++) mom[d] = mom[d] + S.k_vectors[(size_t)(orb_id - 1) * S.n_dim + d];
+        if (!qset) { orb_q = orb_id; qset = true; }
+        else if (!sset) { orb_s = orb_id; sset = true; }
+      }
+    }
+  };
+  scan(eu, iu);
+  scan(ed, id);
+  double m2 = 0.0;
+  for (int d = 0; d < S.n_dim; d++) m2 += mom[d] * mom[d];
+  if (m2 * (S.length_cell * S.length_cell) > EPSILON) return 0.0;
+  double pot = FOUR_PI / kdiff2(S, orb_p, orb_q);
+  if (n_eor_up != 2) pot = pot - FOUR_PI / kdiff2(S, orb_p, orb_s);
+  if (!abs_only) {
+    std::vector<int> oiu, oju, oid, ojd;
+    find_set_bits(iu, oiu);
+    find_set_bits(ju, oju);
+    find_set_bits(id, oid);
+    find_set_bits(jd, ojd);
+    int g = get_gamma_exp(iu, oiu, eu) + get_gamma_exp(ju, oju, eu) + get_gamma_exp(id, oid, ed) + get_gamma_exp(jd, ojd, ed);
+    if (g & 1) pot = -pot;
+  }
+  return pot / L3;
+}
+
+// ---------------------------------------------------------------------------
+// Hubbard k-space: hubbard.f90:2866-2924 hamiltonian_hubbard_k,
+// :9676-9722 is_connected_hubbard_fast.  Momentum conservation is imposed the
+// way find_connected_dets_hubbard_k (:5462) generates connections: the up hop
+// p->r and the dn hop q->s must satisfy k_p + k_q = k_r + k_s (mod lattice).
+// ---------------------------------------------------------------------------
+static bool is_connected_hubbard_fast(det_t u1, det_t d1, det_t u2, det_t d2) {
+  if (u1 == u2 && d1 == d2) return true;
+  if (popcnt(u1 & ~u2) != 1) return false;
+  return popcnt(d1 & ~d2) == 1;
+}
+static bool hubbard_momentum_ok(System &S, det_t u1, det_t d1, det_t u2, det_t d2) {
+  int p = trailz(u1 & ~u2), r = trailz(u2 & ~u1), q = trailz(d1 & ~d2), s = trailz(d2 & ~d1);
+  int dx = S.hk_vectors[2 * p] + S.hk_vectors[2 * q] - S.hk_vectors[2 * r] - S.hk_vectors[2 * s];
+  int dy = S.hk_vectors[2 * p + 1] + S.hk_vectors[2 * q + 1] - S.hk_vectors[2 * r + 1] - S.hk_vectors[2 * s + 1];
+  // k vectors are stored in units of pi/l (see generate_k_vectors :2179): period 2*l
+  return (((dx % (2 * S.l_x)) + 2 * S.l_x) % (2 * S.l_x) == 0) && (((dy % (2 * S.l_y)) + 2 * S.l_y) % (2 * S.l_y) == 0);
+}
+static double hamiltonian_hubbard_k(System &S, det_t ub, det_t db, det_t uk, det_t dk) {
+  if (ub == uk && db == dk) {
+    double me = S.ubyn * S.nup * S.ndn;
+    det_t det = ub;
+    while (det != 0) { int i = trailz(det) + 1; me = me + S.k_energies[i - 1]; det &= ~bit(i - 1); }
+    det = db;
+    while (det != 0) { int i = trailz(det) + 1; me = me + S.k_energies[i - 1]; det &= ~bit(i - 1); }
+    return me;
+  }
+  if (is_connected_hubbard_fast(ub, db, uk, dk) && hubbard_momentum_ok(S, ub, db, uk, dk))
+    return S.ubyn * permutation_factor(ub, uk) * permutation_factor(db, dk);
+  return 0.0;
+}
+
+// chemistry.f90:10273-10293 / heg.f90:3968-3984 / semistoch.f90:2234 hamiltonian
+static double hamiltonian(System &S, det_t u1, det_t d1, det_t u2, det_t d2) {
+  if (S.model == 0) {
+    if (S.time_sym) return hamiltonian_chem_time_sym(S, u1, d1, u2, d2);
+    int lvl = excitation_level(u1, d1, u2, d2);
+    return (lvl >= 0) ? hamiltonian_chem(S, u1, d1, u2, d2, lvl) : 0.0;
+  } else if (S.model == 1) {
+    int lvl = excitation_level(u1, d1, u2, d2);
+    return (lvl >= 0) ? hamiltonian_heg(S, u1, d1, u2, d2) : 0.0;
+  } else {
+    return hamiltonian_hubbard_k(S, u1, d1, u2, d2);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FCIDUMP reader + orbital reorder: chemistry.f90:383-398 (combine_2 init),
+// :538-869 read_integrals, :8921-9022 sort_integrals, :9378-9442
+// compute_orbital_energies.
+// ---------------------------------------------------------------------------
+static void compute_orbital_energies(System &S, det_t hf_up, det_t hf_dn, std::vector<double> &oe) {
+  int norb = S.norb, n1 = norb + 1;
+  oe.assign(norb, 0.0);
+  for (int i = 1; i <= norb; i++) {
+    oe[i - 1] = integral_value(S, i, i, n1, n1);
+    double ex = 0.0, di = 0.0;
+    for (int j = 1; j <= norb; j++) {
+      if (j != i && btest(hf_up, j - 1)) ex = ex - integral_value(S, i, j, j, i);
+      if (j != i && btest(hf_dn, j - 1)) ex = ex - integral_value(S, i, j, j, i);
+    }
+    for (int j = 1; j <= norb; j++) if (j != i && btest(hf_up, j - 1)) di = di + integral_value(S, i, i, j, j);
+    for (int j = 1; j <= norb; j++) if (btest(hf_dn, j - 1)) di = di + integral_value(S, i, i, j, j);
+    for (int j = 1; j <= norb; j++) if (j != i && btest(hf_dn, j - 1)) di = di + integral_value(S, i, i, j, j);
+    for (int j = 1; j <= norb; j++) if (btest(hf_up, j - 1)) di = di + integral_value(S, i, i, j, j);
+    oe[i - 1] = oe[i - 1] + .5 * (ex + di);
+  }
+}
+
+static int d2h_product(int i, int j) { return ((i - 1) ^ (j - 1)) + 1; }  // chemistry.f90:7273-7283 (also c1,cs,c2v,c2h)
+
+static int det_sym(System &S, det_t up, det_t dn) {  // chemistry.f90:10525-10549
+  int s = 1;
+  for (int k = 0; k < S.norb; k++) if (btest(up, k)) s = d2h_product(s, S.orbital_symmetries[k]);
+  for (int k = 0; k < S.norb; k++) if (btest(dn, k)) s = d2h_product(s, S.orbital_symmetries[k]);
+  return s;
+}
+
+static double diag_energy(System &S, det_t up, det_t dn) {
+  if (S.model == 0 && S.time_sym) return hamiltonian_chem_time_sym(S, up, dn, up, dn);
+  return hamiltonian(S, up, dn, up, dn);
+}
+
+// chemistry.f90:10457-10522 find_lowest_energy_det_in_cisd (semantics: lowest
+// diagonal energy among HF + all singles/doubles of symmetry `sym`; strict '<',
+// candidates enumerated HF, singles (up then dn), doubles)
+static void find_lowest_energy_det_in_cisd(System &S, det_t hf_up, det_t hf_dn, int sym, det_t &best_up, det_t &best_dn, double &best_e) {
+  best_e = 1e50;
+  best_up = hf_up; best_dn = hf_dn;
+  std::vector<det_t> ups, dns;
+  ups.push_back(hf_up); dns.push_back(hf_dn);
+  int norb = S.norb;
+  // singles
+  for (int spin = 0; spin < 2; spin++) {
+    det_t d = spin == 0 ? hf_up : hf_dn;
+    for (int p = 0; p < norb; p++) if (btest(d, p))
+      for (int r = 0; r < norb; r++) if (!btest(d, r)) {
+        det_t nd = (d & ~bit(p)) | bit(r);
+        if (spin == 0) { ups.push_back(nd); dns.push_back(hf_dn); } else { ups.push_back(hf_up); dns.push_back(nd); }
+      }
+  }
+  // same-spin doubles
+  for (int spin = 0; spin < 2; spin++) {
+    det_t d = spin == 0 ? hf_up : hf_dn;
+    for (int p = 0; p < norb; p++) if (btest(d, p)) for (int q = p + 1; q < norb; q++) if (btest(d, q))
+      for (int r = 0; r < norb; r++) if (!btest(d, r)) for (int s = r + 1; s < norb; s++) if (!btest(d, s)) {
+        det_t nd = (d & ~bit(p) & ~bit(q)) | bit(r) | bit(s);
+        if (spin == 0) { ups.push_back(nd); dns.push_back(hf_dn); } else { ups.push_back(hf_up); dns.push_back(nd); }
+      }
+  }
+  // opposite-spin doubles
+  for (int p = 0; p < norb; p++) if (btest(hf_up, p)) for (int r = 0; r < norb; r++) if (!btest(hf_up, r))
+    for (int q = 0; q < norb; q++) if (btest(hf_dn, q)) for (int s = 0; s < norb; s++) if (!btest(hf_dn, s)) {
+      ups.push_back((hf_up & ~bit(p)) | bit(r));
+      dns.push_back((hf_dn & ~bit(q)) | bit(s));
+    }
+  for (size_t i = 0; i < ups.size(); i++) {
+    if (det_sym(S, ups[i], dns[i]) != sym) continue;
+    if (S.time_sym && S.z < 0 && ups[i] == dns[i]) continue;
+    double e = diag_energy(S, ups[i], dns[i]);
+    if (e < best_e) { best_e = e; best_up = ups[i]; best_dn = dns[i]; }
+  }
+}
+
+static int read_fcidump_into(System &S, const char *path) {
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  char line[4096];
+  // chemistry.f90:603-625: 3 header lines, then lines until one containing '&'
+  for (int i = 0; i < 3; i++) if (!fgets(line, sizeof line, f)) { fclose(f); return -2; }
+  while (true) {
+    if (!fgets(line, sizeof line, f)) { fclose(f); return -2; }
+    if (strchr(line, '&')) break;
+  }
+  double v; int p, q, r, s;
+  int n1 = S.norb + 1;
+  while (fscanf(f, "%lf %d %d %d %d", &v, &p, &q, &r, &s) == 5) {  // :665-682
+    if (p == 0) p = n1;
+    if (q == 0) q = n1;
+    if (r == 0) r = n1;
+    if (s == 0) s = n1;
+    if (std::fabs(v) > 1.e-9) S.integrals[integral_index(S, p, q, r, s) - 1] = v;
+  }
+  fclose(f);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// heg.f90:173-240 system_setup_heg, :643-749 generate_k_vectors,
+// generic_sort.f90:554-592 shell_sort_real_rank2 (unstable; defines orbital order)
+// ---------------------------------------------------------------------------
+static void heg_setup(System &S) {
+  const double EPSILON = 1.0e-15;
+  int n_dim = S.n_dim;
+  double density = (n_dim == 2) ? 1.0 / (PI_ * (S.r_s * S.r_s)) : 3.0 / (4.0 * PI_ * (S.r_s * S.r_s * S.r_s));
+  S.length_cell = std::pow(S.nelec / density, 1.0 / n_dim);
+  int n_max = (int)(S.cutoff_radius + EPSILON);
+  S.n_max = n_max;
+  int side = 2 * n_max + 1;
+  int ntot = 1;
+  for (int d = 0; d < n_dim; d++) ntot *= side;
+  std::vector<double> values(side);
+  for (int i = -n_max, idx = 0; i <= n_max; i++, idx++) values[idx] = 2 * PI_ / S.length_cell * i;
+  std::vector<double> kv((size_t)n_dim * ntot);
+  int index = 0;
+  if (n_dim == 3) {
+    for (int i = -n_max; i <= n_max; i++) for (int j = -n_max; j <= n_max; j++) for (int k = -n_max; k <= n_max; k++) {
+      kv[(size_t)index * 3 + 0] = values[i + n_max];
+      kv[(size_t)index * 3 + 1] = values[j + n_max];
+      kv[(size_t)index * 3 + 2] = values[k + n_max];
+      index++;
+    }
+  } else {
+    for (int i = -n_max; i <= n_max; i++) for (int j = -n_max; j <= n_max; j++) {
+      kv[(size_t)index * 2 + 0] = values[i + n_max];
+      kv[(size_t)index * 2 + 1] = values[j + n_max];
+      index++;
+    }
+  }
+  auto s2 = [&](const double *v) { double s = 0; for (int d = 0; d < n_dim; d++) s += v[d] * v[d]; return s; };
+  // shell sort, 1-based logic of generic_sort.f90:566-590
+  std::vector<double> temp(n_dim);
+  int increment = ntot / 2;
+  while (increment > 0) {
+    for (int i = increment + 1; i <= ntot; i++) {
+      int j = i;
+      for (int d = 0; d < n_dim; d++) temp[d] = kv[(size_t)(i - 1) * n_dim + d];
+      while (j >= increment + 1) {
+        if (s2(&kv[(size_t)(j - increment - 1) * n_dim]) <= s2(temp.data())) break;
+        for (int d = 0; d < n_dim; d++) kv[(size_t)(j - 1) * n_dim + d] = kv[(size_t)(j - increment - 1) * n_dim + d];
+        j -= increment;
+      }
+      for (int d = 0; d < n_dim; d++) kv[(size_t)(j - 1) * n_dim + d] = temp[d];
+    }
+    if (increment == 2) increment = 1;
+    else increment = increment * 5 / 11;
+  }
+  int norb = 0;
+  for (int i = 0; i < ntot; i++) {
+    if (std::sqrt(s2(&kv[(size_t)i * n_dim])) > 2 * PI_ / S.length_cell * S.cutoff_radius + EPSILON) break;
+    norb++;
+  }
+  S.norb = norb;
+  S.k_vectors.assign(kv.begin(), kv.begin() + (size_t)norb * n_dim);
+  S.k_rel.assign((size_t)norb * 3, 0);
+  for (int i = 0; i < norb; i++)
+    for (int d = 0; d < n_dim; d++) S.k_rel[(size_t)i * 3 + d] = (int)std::lrint(S.k_vectors[(size_t)i * n_dim + d] * S.length_cell / (2 * PI_));
+  S.orb_lut.assign((size_t)side * side * side, -1);
+  for (int i = 0; i < norb; i++) {
+    int a = S.k_rel[i * 3] + n_max, b = S.k_rel[i * 3 + 1] + n_max, c = S.k_rel[i * 3 + 2] + n_max;
+    if (n_dim == 2) c = n_max;
+    S.orb_lut[((size_t)a * side + b) * side + c] = i + 1;
+  }
+  S.hf_up = maskr(S.nup);
+  S.hf_dn = maskr(S.ndn);
+}
+static int find_orb_id(System &S, int kx, int ky, int kz) {  // heg.f90:752-771
+  int n_max = S.n_max, side = 2 * n_max + 1;
+  if (kx < -n_max || kx > n_max || ky < -n_max || ky > n_max || kz < -n_max || kz > n_max) return -1;
+  return S.orb_lut[((size_t)(kx + n_max) * side + (ky + n_max)) * side + (kz + n_max)];
+}
+
+// ---------------------------------------------------------------------------
+// Hubbard k-space set-up: hubbard.f90:2179-2324 generate_k_vectors (square
+// lattice, pbc): k = (2*i, 2*j) in units of pi/l for i in 0..l_x-1, shifted to
+// the first Brillouin zone (-l, l]; k_energies = -2t(cos kx + cos ky);
+// ubyn = U / nsites.  Orbital order follows the reference loop order.
+// ---------------------------------------------------------------------------
+static void hubbard_setup(System &S) {
+  int ns = S.l_x * S.l_y;
+  S.norb = ns;
+  S.hk_vectors.assign(2 * ns, 0);
+  S.k_energies.assign(ns, 0.0);
+  int idx = 0;
+  for (int i = 0; i < S.l_x; i++)
+    for (int j = 0; j < S.l_y; j++) {
+      int kx = 2 * i, ky = 2 * j;
+      if (kx > S.l_x) kx -= 2 * S.l_x;
+      if (ky > S.l_y) ky -= 2 * S.l_y;
+      S.hk_vectors[2 * idx] = kx;
+      S.hk_vectors[2 * idx + 1] = ky;
+      S.k_energies[idx] = -2.0 * S.hub_t * (std::cos(PI_ * kx / S.l_x) + std::cos(PI_ * ky / S.l_y));
+      idx++;
+    }
+  S.ubyn = S.hub_U / ns;
+}
+
+// ---------------------------------------------------------------------------
+// Sparse build: chemistry.f90:7639-8009 generate_sparse_ham_chem_upper_triangular
+// (partial connections, incremental on sparse_ham%ndet), :9819-9848
+// get_n_minus_1_configs, :9851-9991 get_connected_dets_in_list; HEG twin
+// heg.f90:3553-3809,3846-3964 (identical result: rows keep j>i plus diagonal).
+// Hubbard: hubbard.f90:9435-9672 (connections + binary search; every connected
+// j>=i stored, no magnitude threshold because |H|=U/N).
+// ---------------------------------------------------------------------------
+struct KeyIdx { det_t key; int idx; };
+static void build_upper(System &S, i8b n_det, const det_t *dets_up, const det_t *dets_dn, bool incremental) {
+  i8b ndet_old = incremental ? S.sparse_ndet : 0;
+  if (ndet_old > n_det) ndet_old = 0;
+  i8b ndet_new = n_det - ndet_old;
+  int nup = S.nup, ndn = S.ndn;
+  std::vector<KeyIdx> beta(ndet_new), am1((size_t)ndet_new * nup);
+  for (i8b i = 0; i < ndet_new; i++) beta[i] = {dets_dn[ndet_old + i], (int)(ndet_old + i + 1)};
+  for (i8b i = 0; i < ndet_new; i++) {
+    det_t d = dets_up[ndet_old + i];
+    int e = 0;
+    det_t t = d;
+    while (t != 0) {  // get_occ_orbs order (more_tools.f90:5498): ascending orbitals
+      int o = trailz(t);
+      am1[(size_t)i * nup + e] = {d & ~bit(o), (int)(ndet_old + i + 1)};
+      t &= ~bit(o);
+      e++;
+    }
+  }
+  auto cmp = [](const KeyIdx &a, const KeyIdx &b) { return a.key < b.key || (a.key == b.key && a.idx < b.idx); };
+  std::sort(beta.begin(), beta.end(), cmp);   // generic_sort.f90:166 sort_by_first_argument_ik
+  std::sort(am1.begin(), am1.end(), cmp);
+  auto range = [](const std::vector<KeyIdx> &v, det_t key, size_t &lo, size_t &hi) {  // more_tools.f90:3842-3886
+    lo = std::lower_bound(v.begin(), v.end(), key, [](const KeyIdx &a, det_t k) { return a.key < k; }) - v.begin();
+    hi = std::upper_bound(v.begin(), v.end(), key, [](det_t k, const KeyIdx &a) { return k < a.key; }) - v.begin();
+  };
+  std::vector<i8b> new_counts(n_det, 0), new_idx;
+  std::vector<double> new_val;
+  new_idx.reserve(S.H_indices.size() + 16);
+  new_val.reserve(S.H_values.size() + 16);
+  std::vector<char> is_included(n_det + 1, 0);
+  std::vector<std::pair<int, double>> conn;
+  i8b isparse_old = 0;
+  const double thresh = 1.e-12;
+  for (i8b i = 1; i <= n_det; i++) {
+    if (i <= ndet_old) {  // :7818-7843 copy old row
+      i8b n_copy = S.H_nonzero_elements[i - 1];
+      for (i8b k = 0; k < n_copy; k++) { new_idx.push_back(S.H_indices[isparse_old + k]); new_val.push_back(S.H_values[isparse_old + k]); }
+      isparse_old += n_copy;
+      new_counts[i - 1] = n_copy;
+    }
+    det_t up = dets_up[i - 1], dn = dets_dn[i - 1];
+    conn.clear();
+    conn.push_back({(int)i, hamiltonian(S, up, dn, up, dn)});  // :9887-9890 diagonal first
+    auto consider = [&](int j) {
+      if (j > i && !is_included[j]) {
+        double elem = hamiltonian(S, up, dn, dets_up[j - 1], dets_dn[j - 1]);
+        if (std::fabs(elem) > thresh) { conn.push_back({j, elem}); is_included[j] = 1; }
+      }
+    };
+    if (S.model == 2) {
+      // Hubbard: every connected j>i, no threshold (hubbard.f90:9640-9668)
+      size_t lo, hi;
+      det_t t = up;
+      while (t != 0) {
+        int o = trailz(t);
+        range(am1, up & ~bit(o), lo, hi);
+        for (size_t k = lo; k < hi; k++) {
+          int j = am1[k].idx;
+          if (j > i && !is_included[j]) {
+            det_t uj = dets_up[j - 1], dj = dets_dn[j - 1];
+            if (uj != up && is_connected_hubbard_fast(up, dn, uj, dj) && hubbard_momentum_ok(S, up, dn, uj, dj)) {
+              conn.push_back({j, hamiltonian_hubbard_k(S, up, dn, uj, dj)});
+              is_included[j] = 1;
+            }
+          }
+        }
+        t &= ~bit(o);
+      }
+    } else {
+      size_t lo, hi;
+      range(beta, dn, lo, hi);  // :9893-9909 same-beta range
+      for (size_t k = lo; k < hi; k++) consider(beta[k].idx);
+      det_t t = up;             // :9912-9932 alpha_m1 ranges
+      while (t != 0) {
+        int o = trailz(t);
+        range(am1, up & ~bit(o), lo, hi);
+        for (size_t k = lo; k < hi; k++) consider(am1[k].idx);
+        t &= ~bit(o);
+      }
+      if (S.model == 0 && S.time_sym) {  // :9934-9979 spins flipped
+        range(beta, up, lo, hi);
+        for (size_t k = lo; k < hi; k++) consider(beta[k].idx);
+        t = dn;
+        while (t != 0) {
+          int o = trailz(t);
+          range(am1, dn & ~bit(o), lo, hi);
+          for (size_t k = lo; k < hi; k++) consider(am1[k].idx);
+          t &= ~bit(o);
+        }
+      }
+    }
+    (void)ndn;
+    std::sort(conn.begin(), conn.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });  // tools.f90:1631 sort_and_merge
+    for (auto &c : conn) {  // :7850-7874
+      if (c.first > i || (c.first == i && i > ndet_old)) {
+        new_idx.push_back(c.first);
+        new_val.push_back(c.second);
+        new_counts[i - 1]++;
+        is_included[c.first] = 0;
+      }
+    }
+  }
+  S.H_nonzero_elements.swap(new_counts);
+  S.H_indices.swap(new_idx);
+  S.H_values.swap(new_val);
+  S.sparse_ndet = n_det;
+}
+
+// more_tools.f90:3622-3655 fast_sparse_matrix_multiply_upper_triangular
+static void matvec_upper(i8b n, const i8b *idx, const i8b *cnt, const double *val, const double *x, double *y) {
+  for (i8b i = 0; i < n; i++) y[i] = 0.0;
+  i8b k = 0;
+  for (i8b i = 1; i <= n; i++)
+    for (i8b j = 1; j <= cnt[i - 1]; j++) {
+      i8b m = idx[k];
+      y[i - 1] = y[i - 1] + val[k] * x[m - 1];
+      if (i != m) y[m - 1] = y[m - 1] + val[k] * x[i - 1];
+      k++;
+    }
+}
+
+// more_tools.f90:2018-2244 davidson_sparse (epsilon=1e-10 :73)
+static double dotp(i8b n, const double *a, const double *b) { double s = 0; for (i8b i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+static int davidson_sparse(i8b n, int n_states, double *final_vector, double *lowest_eigenvalues, const i8b *idx,
+                           const i8b *cnt, const double *val, const double *initial_vector, std::vector<double> *ritz_log,
+                           int *n_matvec_out) {
+  const double epsilon = 1.e-10;
+  int iterations = 50;
+  if (n < iterations) iterations = (int)n;
+  int m = n_states * iterations;
+  std::vector<double> v((size_t)n * m, 0.0), Hv((size_t)n * m, 0.0), w((size_t)n * n_states, 0.0), Hw((size_t)n * n_states, 0.0);
+  std::vector<double> residual_norm(n_states, 1.0), prev(n_states, 1e300), h_krylov((size_t)m * m, 0.0);
+  int nmv = 0;
+  auto V = [&](int c) { return &v[(size_t)c * n]; };
+  auto HV = [&](int c) { return &Hv[(size_t)c * n]; };
+  if (initial_vector) {
+    for (int i = 0; i < n_states; i++) {
+      const double *iv = initial_vector + (size_t)i * n;
+      double norm = 1.0 / std::sqrt(dotp(n, iv, iv));
+      for (i8b k = 0; k < n; k++) V(i)[k] = norm * iv[k];
+      if (i > 0) {
+        for (int j = 0; j < i; j++) {
+          norm = dotp(n, V(i), V(j));
+          for (i8b k = 0; k < n; k++) V(i)[k] = V(i)[k] - norm * V(j)[k];
+        }
+        norm = dotp(n, V(i), V(i));
+        double ninv = 1.0 / std::sqrt(norm);
+        for (i8b k = 0; k < n; k++) V(i)[k] = V(i)[k] * ninv;
+      }
+    }
+  } else {
+    for (int i = 0; i < n_states; i++) V(i)[i] = 1.0;
+  }
+  if (n <= 1) {
+    lowest_eigenvalues[0] = val[0];
+    for (int i = 0; i < n_states; i++) for (i8b k = 0; k < n; k++) final_vector[(size_t)i * n + k] = w[(size_t)i * n + k];
+    if (n_matvec_out) *n_matvec_out = 0;
+    return 0;
+  }
+  std::vector<double> diag(n);
+  {
+    i8b ind = 0;
+    diag[0] = val[0];
+    for (i8b i = 1; i < n; i++) { ind += cnt[i - 1]; diag[i] = val[ind]; }
+  }
+  for (int i = 0; i < n_states; i++) { matvec_upper(n, idx, cnt, val, V(i), HV(i)); nmv++; }
+  for (int i = 0; i < n_states; i++) {
+    lowest_eigenvalues[i] = dotp(n, V(i), HV(i));
+    h_krylov[(size_t)i * m + i] = lowest_eigenvalues[i];
+    for (int j = i + 1; j < n_states; j++) {
+      h_krylov[(size_t)j * m + i] = dotp(n, V(i), HV(j));
+      h_krylov[(size_t)i * m + j] = h_krylov[(size_t)j * m + i];
+    }
+  }
+  if (ritz_log) for (int i = 0; i < n_states; i++) ritz_log->push_back(lowest_eigenvalues[i]);
+  for (int i = 0; i < n_states; i++) {
+    memcpy(&w[(size_t)i * n], V(i), n * sizeof(double));
+    memcpy(&Hw[(size_t)i * n], HV(i), n * sizeof(double));
+  }
+  i8b niter = std::min<i8b>(n, (i8b)n_states * iterations);
+  bool converged = false;
+  i8b it;
+  for (it = n_states + 1; it <= niter * 10; it++) {
+    int it_circ = (int)((it - 1) % niter) + 1;
+    if (it > niter && it_circ == 1) {  // :2144-2163 restart
+      for (int i = 0; i < n_states; i++) {
+        memcpy(V(i), &w[(size_t)i * n], n * sizeof(double));
+        memcpy(HV(i), &Hw[(size_t)i * n], n * sizeof(double));
+      }
+      for (int i = 0; i < n_states; i++) {
+        lowest_eigenvalues[i] = dotp(n, V(i), HV(i));
+        h_krylov[(size_t)i * m + i] = lowest_eigenvalues[i];
+        for (int j = i + 1; j < n_states; j++) {
+          h_krylov[(size_t)j * m + i] = dotp(n, V(i), HV(j));
+          h_krylov[(size_t)i * m + j] = h_krylov[(size_t)j * m + i];
+        }
+      }
+      continue;
+    }
+    int i = (it_circ - 1) % n_states;  // 0-based state
+    int c = it_circ - 1;               // 0-based column
+    double *vc = V(c);
+    const double *wi = &w[(size_t)i * n], *Hwi = &Hw[(size_t)i * n];
+    double E = lowest_eigenvalues[i];
+    for (i8b j = 0; j < n; j++) vc[j] = (Hwi[j] - E * wi[j]) / (E - diag[j]);
+    for (i8b j = 0; j < n; j++) if (std::fabs(E - diag[j]) < 1e-8) vc[j] = -1.0;
+    residual_norm[i] = dotp(n, vc, vc);
+    double rs = 0;
+    for (int s = 0; s < n_states; s++) rs += residual_norm[s];
+    if (rs < 1.e-12) converged = true;
+    for (int k = 0; k < c; k++) {
+      double norm = dotp(n, vc, V(k));
+      const double *vk = V(k);
+      for (i8b j = 0; j < n; j++) vc[j] = vc[j] - norm * vk[j];
+    }
+    double norm = dotp(n, vc, vc);
+    double ninv = 1.0 / std::sqrt(norm);
+    for (i8b j = 0; j < n; j++) vc[j] = vc[j] * ninv;
+    matvec_upper(n, idx, cnt, val, vc, HV(c));
+    nmv++;
+    for (int k = 0; k <= c; k++) {
+      h_krylov[(size_t)c * m + k] = dotp(n, V(k), HV(c));
+      h_krylov[(size_t)k * m + c] = h_krylov[(size_t)c * m + k];
+    }
+    if (it_circ % n_states == 0) {
+      int dim = it_circ;
+      std::vector<double> hsub((size_t)dim * dim), evals, evecs;
+      for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) hsub[(size_t)b * dim + a] = h_krylov[(size_t)b * m + a];
+      jacobi_eigh(dim, hsub, evals, evecs);
+      for (int s = 0; s < n_states; s++) lowest_eigenvalues[s] = evals[s];
+      for (int s = 0; s < n_states; s++) {
+        double *ws = &w[(size_t)s * n], *Hws = &Hw[(size_t)s * n];
+        for (i8b j = 0; j < n; j++) { ws[j] = 0; Hws[j] = 0; }
+        for (int k = 0; k < dim; k++) {
+          double ck = evecs[(size_t)s * dim + k];
+          const double *vk = V(k), *hvk = HV(k);
+          for (i8b j = 0; j < n; j++) { ws[j] += vk[j] * ck; Hws[j] += hvk[j] * ck; }
+        }
+      }
+      double md = 0;
+      for (int s = 0; s < n_states; s++) md = std::max(md, std::fabs(lowest_eigenvalues[s] - prev[s]));
+      if (md < epsilon) { converged = true; break; }
+      for (int s = 0; s < n_states; s++) prev[s] = lowest_eigenvalues[s];
+      if (ritz_log) for (int s = 0; s < n_states; s++) ritz_log->push_back(lowest_eigenvalues[s]);
+      if (converged) break;
+    }
+  }
+  for (int i = 0; i < n_states; i++) memcpy(final_vector + (size_t)i * n, &w[(size_t)i * n], n * sizeof(double));
+  if (n_matvec_out) *n_matvec_out = nmv;
+  return (int)it;
+}
+
+// ---------------------------------------------------------------------------
+// Heat-bath selection (TEST-INPUT GENERATOR ONLY): chemistry.f90:6819-7159
+// find_important_connected_dets_chem (+ dtm_hb :872-994), heg.f90:2475-2727
+// find_important_connected_dets_heg, semistoch.f90:1579-2231
+// find_doubly_excited, hci.f90:865-1039 get_next_det_list.  The sorted
+// per-pair (r,s,|H|) tables only prune the search; the selected set is
+// {singles: eps <= |H| <= min_H_done} U {doubles: eps < |H| <= min_H_done}.
+// ---------------------------------------------------------------------------
+static void chem_max_double(System &S) {
+  int norb = S.norb;
+  double mx = 0;
+  for (int p = 1; p <= norb; p++) for (int q = p + 1; q <= norb; q++)
+    for (int r = 1; r <= norb; r++) for (int s = r + 1; s <= norb; s++) {
+      if (p == r || q == s || p == s || q == r) continue;
+      det_t di = bit(p - 1) | bit(q - 1), dj = bit(r - 1) | bit(s - 1);
+      mx = std::max(mx, std::fabs(hamiltonian_chem(S, di, 0, dj, 0, 2)));
+    }
+  for (int p = 1; p <= norb; p++) for (int q = 1; q <= norb; q++)
+    for (int r = 1; r <= norb; r++) for (int s = 1; s <= norb; s++) {
+      if (p == r || q == s) continue;
+      mx = std::max(mx, std::fabs(hamiltonian_chem(S, bit(p - 1), bit(q - 1), bit(r - 1), bit(s - 1), 2)));
+    }
+  S.max_double = mx;
+}
+static void important_connected_chem(System &S, det_t det_up, det_t det_dn, double eps, double min_H_done,
+                                     std::vector<det_t> &out_up, std::vector<det_t> &out_dn) {
+  int norb = S.norb;
+  out_up.push_back(det_up); out_dn.push_back(det_dn);  // :6893-6895
+  auto emit = [&](det_t nu, det_t nd) {
+    if (S.time_sym) {
+      if (nu == nd && S.z < 0) return;
+      if (det_up == nd && det_dn == nu) return;
+    }
+    if (S.time_sym && nu > nd) std::swap(nu, nd);
+    out_up.push_back(nu); out_dn.push_back(nd);
+  };
+  // singles :6906-6985
+  for (int spin = 0; spin < 2; spin++) {
+    det_t d = spin == 0 ? det_up : det_dn;
+    for (int p = 1; p <= norb; p++) if (btest(d, p - 1))
+      for (int r = 1; r <= norb; r++) {
+        if (btest(d, r - 1)) continue;
+        if (S.orbital_symmetries[p - 1] != S.orbital_symmetries[r - 1]) continue;
+        det_t nd = (d & ~bit(p - 1)) | bit(r - 1);
+        det_t nu_ = spin == 0 ? nd : det_up, nd_ = spin == 0 ? det_dn : nd;
+        if (S.time_sym) {
+          if (nu_ == nd_ && S.z < 0) continue;
+          if (det_up == nd_ && det_dn == nu_) continue;
+        }
+        double me = hamiltonian_chem(S, det_up, det_dn, nu_, nd_, 1);
+        if (std::fabs(me) < eps) continue;
+        if (std::fabs(me) > min_H_done) continue;
+        emit(nu_, nd_);
+      }
+  }
+  if (eps > S.max_double) return;  // :6995
+  // doubles :7023-7157
+  auto try_double = [&](det_t nu, det_t nd) {
+    double absH = std::fabs(hamiltonian_chem(S, det_up, det_dn, nu, nd, 2));
+    if (absH <= eps) return;
+    if (absH > min_H_done) return;
+    emit(nu, nd);
+  };
+  for (int spin = 0; spin < 2; spin++) {
+    det_t d = spin == 0 ? det_up : det_dn;
+    for (int p = 0; p < norb; p++) if (btest(d, p)) for (int q = p + 1; q < norb; q++) if (btest(d, q))
+      for (int r = 0; r < norb; r++) if (!btest(d, r)) for (int s = r + 1; s < norb; s++) if (!btest(d, s)) {
+        det_t nd = (d & ~bit(p) & ~bit(q)) | bit(r) | bit(s);
+        if (spin == 0) try_double(nd, det_dn); else try_double(det_up, nd);
+      }
+  }
+  for (int p = 0; p < norb; p++) if (btest(det_up, p)) for (int q = 0; q < norb; q++) if (btest(det_dn, q))
+    for (int r = 0; r < norb; r++) if (!btest(det_up, r)) for (int s = 0; s < norb; s++) if (!btest(det_dn, s))
+      try_double((det_up & ~bit(p)) | bit(r), (det_dn & ~bit(q)) | bit(s));
+}
+static void heg_max_double(System &S) {
+  int norb = S.norb;
+  double mx = 0;
+  for (int p = 0; p < norb; p++) for (int q = p + 1; q < norb; q++) for (int r = 0; r < norb; r++) for (int s = r + 1; s < norb; s++) {
+    if (p == r || q == s || p == s || q == r) continue;
+    mx = std::max(mx, std::fabs(hamiltonian_heg(S, bit(p) | bit(q), 0, bit(r) | bit(s), 0, true)));
+  }
+  for (int p = 0; p < norb; p++) for (int q = 0; q < norb; q++) for (int r = 0; r < norb; r++) for (int s = 0; s < norb; s++) {
+    if (p == r || q == s) continue;
+    mx = std::max(mx, std::fabs(hamiltonian_heg(S, bit(p), bit(q), bit(r), bit(s), true)));
+  }
+  S.max_double = mx;
+}
+static void important_connected_heg(System &S, det_t det_up, det_t det_dn, double eps, std::vector<det_t> &out_up, std::vector<det_t> &out_dn) {
+  int norb = S.norb;
+  out_up.push_back(det_up); out_dn.push_back(det_dn);
+  if (eps > S.max_double) return;
+  auto try_double = [&](det_t nu, det_t nd) {
+    double absH = std::fabs(hamiltonian_heg(S, det_up, det_dn, nu, nd, true));
+    if (absH <= eps) return;   // heg.f90:2609,2625 (table keeps absH > EPSILON only)
+    out_up.push_back(nu); out_dn.push_back(nd);
+  };
+  for (int spin = 0; spin < 2; spin++) {
+    det_t d = spin == 0 ? det_up : det_dn;
+    for (int p = 0; p < norb; p++) if (btest(d, p)) for (int q = p + 1; q < norb; q++) if (btest(d, q))
+      for (int r = 0; r < norb; r++) if (!btest(d, r)) {
+        int sx = S.k_rel[p * 3] + S.k_rel[q * 3] - S.k_rel[r * 3], sy = S.k_rel[p * 3 + 1] + S.k_rel[q * 3 + 1] - S.k_rel[r * 3 + 1],
+            sz = S.k_rel[p * 3 + 2] + S.k_rel[q * 3 + 2] - S.k_rel[r * 3 + 2];
+        int s = find_orb_id(S, sx, sy, sz) - 1;
+        if (s < 0 || s <= r || btest(d, s)) continue;
+        det_t nd = (d & ~bit(p) & ~bit(q)) | bit(r) | bit(s);
+        if (spin == 0) try_double(nd, det_dn); else try_double(det_up, nd);
+      }
+  }
+  for (int p = 0; p < norb; p++) if (btest(det_up, p)) for (int q = 0; q < norb; q++) if (btest(det_dn, q))
+    for (int r = 0; r < norb; r++) if (!btest(det_up, r)) {
+      int sx = S.k_rel[p * 3] + S.k_rel[q * 3] - S.k_rel[r * 3], sy = S.k_rel[p * 3 + 1] + S.k_rel[q * 3 + 1] - S.k_rel[r * 3 + 1],
+          sz = S.k_rel[p * 3 + 2] + S.k_rel[q * 3 + 2] - S.k_rel[r * 3 + 2];
+      int s = find_orb_id(S, sx, sy, sz) - 1;
+      if (s < 0 || btest(det_dn, s)) continue;
+      try_double((det_up & ~bit(p)) | bit(r), (det_dn & ~bit(q)) | bit(s));
+    }
+}
+
+// hci.f90:66-862 perform_hci (variational stage only), :865-1039 get_next_det_list,
+// :1042-1097 iterative_diagonalize
+static int perform_hci(System &S, const double *eps_var_sched /*30*/, int n_states, int max_iters, int max_dets) {
+  std::vector<det_t> old_up(1, S.hf_up), old_dn(1, S.hf_dn);
+  if (S.model == 0 && S.time_sym && old_dn[0] < old_up[0]) std::swap(old_up[0], old_dn[0]);
+  i8b ndets_old = 1;
+  std::vector<double> old_wts((size_t)n_states, 0.0);  // (ndets, n_states) column-major
+  std::vector<double> energy(n_states, 0.0), old_energy(n_states, 0.0);
+  old_wts[0] = 1.0;
+  energy[0] = hamiltonian(S, old_up[0], old_dn[0], old_up[0], old_dn[0]);
+  old_energy = energy;
+  std::vector<double> min_H_done(1, 9.e99);
+  S.sparse_ndet = 0; S.H_indices.clear(); S.H_values.clear(); S.H_nonzero_elements.clear();
+  S.log_ritz.clear(); S.log_ndet.clear(); S.log_nnz.clear(); S.log_nritz.clear(); S.log_energy.clear();
+  double eps_var = eps_var_sched[0];
+  const double eps_last = eps_var_sched[29];
+  if (S.model == 0) chem_max_double(S); else if (S.model == 1) heg_max_double(S);
+  for (int iter = 1; iter <= max_iters; iter++) {
+    if (iter <= 30) eps_var = eps_var_sched[iter - 1];
+    std::vector<double> coeffs(ndets_old);
+    if (iter > 1) {
+      for (i8b i = 0; i < ndets_old; i++) {
+        double mx = 0;
+        for (int s = 0; s < n_states; s++) mx = std::max(mx, std::fabs(old_wts[(size_t)s * ndets_old + i]));
+        coeffs[i] = mx;
+      }
+    } else {
+      for (i8b i = 0; i < ndets_old; i++) coeffs[i] = old_wts[i];
+    }
+    // find_doubly_excited (semistoch.f90:1825-1850 chem / :1876-1888 heg)
+    std::vector<det_t> tu, td;
+    for (i8b i = 0; i < ndets_old; i++) {
+      if (std::fabs(coeffs[i]) * min_H_done[i] > eps_var) {
+        if (S.model == 0) important_connected_chem(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), min_H_done[i], tu, td);
+        else important_connected_heg(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), tu, td);
+      } else {
+        tu.push_back(old_up[i]); td.push_back(old_dn[i]);
+      }
+    }
+    std::vector<size_t> ord(tu.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return tu[a] < tu[b] || (tu[a] == tu[b] && td[a] < td[b]); });
+    std::vector<det_t> su, sd;
+    for (size_t k = 0; k < ord.size(); k++) {
+      size_t i = ord[k];
+      if (!su.empty() && su.back() == tu[i] && sd.back() == td[i]) continue;
+      su.push_back(tu[i]); sd.push_back(td[i]);
+    }
+    i8b ndets_new = (i8b)su.size();
+    // new list = old dets in old order, then not-yet-present dets sorted by label (hci.f90:945-991)
+    std::vector<size_t> oord(ndets_old);
+    for (i8b i = 0; i < ndets_old; i++) oord[i] = i;
+    std::sort(oord.begin(), oord.end(), [&](size_t a, size_t b) { return old_up[a] < old_up[b] || (old_up[a] == old_up[b] && old_dn[a] < old_dn[b]); });
+    std::vector<det_t> new_up(old_up), new_dn(old_dn);
+    {
+      size_t o = 0;
+      for (i8b i = 0; i < ndets_new; i++) {
+        while (o < oord.size() && (old_up[oord[o]] < su[i] || (old_up[oord[o]] == su[i] && old_dn[oord[o]] < sd[i]))) o++;
+        bool present = o < oord.size() && old_up[oord[o]] == su[i] && old_dn[oord[o]] == sd[i];
+        if (!present) { new_up.push_back(su[i]); new_dn.push_back(sd[i]); }
+      }
+    }
+    if ((i8b)new_up.size() != ndets_new) { /* every old det is regenerated as ref => sizes agree */ ndets_new = (i8b)new_up.size(); }
+    // hci.f90:1014-1016
+    std::vector<double> mh(ndets_new, 9.e99);
+    for (i8b i = 0; i < ndets_old; i++) mh[i] = std::min(min_H_done[i], (eps_var / std::fabs(coeffs[i]) - 1.e-14));
+    min_H_done.swap(mh);
+    if (ndets_new == ndets_old) continue;  // hci.f90:413-417
+    if (ndets_new <= (i8b)(1.00001 * ndets_old) && eps_var == eps_last) break;  // :420
+    if (max_dets > 0 && ndets_new > max_dets) break;
+    std::vector<double> starting((size_t)ndets_new * n_states, 0.0);
+    for (int s = 0; s < n_states; s++) for (i8b i = 0; i < ndets_old; i++) starting[(size_t)s * ndets_new + i] = old_wts[(size_t)s * ndets_old + i];
+    if (iter == 1) {
+      std::fill(starting.begin(), starting.end(), 0.0);
+      for (int s = 0; s < n_states; s++) starting[(size_t)s * ndets_new + s] = 1.0;
+    }
+    build_upper(S, ndets_new, new_up.data(), new_dn.data(), true);
+    std::vector<double> wts((size_t)ndets_new * n_states);
+    size_t r0 = S.log_ritz.size();
+    davidson_sparse(ndets_new, n_states, wts.data(), energy.data(), S.H_indices.data(), S.H_nonzero_elements.data(), S.H_values.data(), starting.data(), &S.log_ritz, nullptr);
+    S.log_nritz.push_back((i8b)(S.log_ritz.size() - r0));
+    S.log_ndet.push_back(ndets_new);
+    S.log_nnz.push_back((i8b)S.H_indices.size());
+    for (int s = 0; s < n_states; s++) S.log_energy.push_back(energy[s]);
+    old_wts.swap(wts);
+    ndets_old = ndets_new;
+    old_up.swap(new_up); old_dn.swap(new_dn);
+    double md = 0;
+    for (int s = 0; s < n_states; s++) md = std::max(md, std::fabs(energy[s] - old_energy[s]));
+    old_energy = energy;
+    if (md < 1.e-5 && eps_var == eps_last) break;  // :502
+  }
+  S.hci_up = old_up; S.hci_dn = old_dn; S.hci_wts = old_wts; S.hci_energy = energy;
+  return 0;
+}
+
+// =============================================================================
+// C ABI for ctypes (tests / bench cpu_baseline only)
+// =============================================================================
+extern "C" {
+
+void *orc_chem_new(const char *fcidump, int norb, int nelec, int nup, const int *orbsym, int time_sym, int z, int hf_symmetry) {
+  System *S = new System();
+  S->model = 0; S->norb = norb; S->nelec = nelec; S->nup = nup; S->ndn = nelec - nup;
+  S->time_sym = time_sym != 0; S->z = z;
+  S->sqrt2 = std::sqrt(2.0); S->sqrt2inv = 1.0 / S->sqrt2;  // chemistry.f90:360-361
+  int n1 = norb + 1;
+  S->combine_2.assign((size_t)n1 * n1, 0);
+  for (int i = 1; i <= norb; i++) for (int j = 1; j <= norb; j++) S->c2(i, j) = (i > j) ? (i * (i - 1)) / 2 + j : (j * (j - 1)) / 2 + i;
+  S->c2(n1, n1) = (n1 * norb) / 2 + n1;  // :394
+  S->orb_order.resize(n1); S->orb_order_inv.resize(n1);
+  for (int i = 0; i < n1; i++) { S->orb_order[i] = i + 1; S->orb_order_inv[i] = i + 1; }
+  S->orbital_symmetries.assign(orbsym, orbsym + norb);
+  i8b isize = integral_index(*S, n1, n1, n1, n1);
+  S->integrals.assign(isize, 0.0);
+  if (read_fcidump_into(*S, fcidump) != 0) { delete S; return nullptr; }
+  // HF det: first nup / ndn orbitals (chemistry.f90:694-702), optionally auto-assigned (:763-792)
+  det_t hf_up = maskr(nup), hf_dn = maskr(S->ndn);
+  if (hf_symmetry != 999) {
+    det_t du = 0, dd = 0; double e;
+    // the auto-assign loop runs before the orbital reorder (orb_order = identity)
+    S->nuclear_nuclear_energy = integral_value(*S, n1, n1, n1, n1);
+    while (true) {  // chemistry.f90:10442-10452
+      find_lowest_energy_det_in_cisd(*S, hf_up, hf_dn, hf_symmetry, du, dd, e);
+      if (du == hf_up && dd == hf_dn) break;
+      hf_up = du; hf_dn = dd;
+    }
+  }
+  // sort_integrals (chemistry.f90:8921-9022)
+  std::vector<double> oe;
+  compute_orbital_energies(*S, hf_up, hf_dn, oe);
+  S->orbital_energies = oe;
+  std::vector<double> tmp(oe);
+  for (int i = 1; i <= norb; i++) {
+    if (btest(hf_up, i - 1)) tmp[i - 1] = tmp[i - 1] - 1.e9;
+    if (btest(hf_dn, i - 1)) tmp[i - 1] = tmp[i - 1] - 1.e9;
+  }
+  for (int i = 1; i <= norb; i++) {
+    double mn = *std::min_element(tmp.begin(), tmp.end());
+    for (int j = 1; j <= norb; j++)
+      if (tmp[j - 1] == mn) { S->orb_order[i - 1] = j; S->orb_order_inv[j - 1] = i; tmp[j - 1] = 1.e99; break; }
+  }
+  std::vector<int> osym(norb);
+  std::vector<double> oes(norb);
+  for (int i = 0; i < norb; i++) { osym[i] = S->orbital_symmetries[S->orb_order[i] - 1]; oes[i] = oe[S->orb_order[i] - 1]; }
+  S->orbital_symmetries = osym; S->orbital_energies = oes;
+  det_t nu = 0, nd = 0;
+  for (int i = 1; i <= norb; i++) {
+    if (btest(hf_up, i - 1)) nu |= bit(S->orb_order_inv[i - 1] - 1);
+    if (btest(hf_dn, i - 1)) nd |= bit(S->orb_order_inv[i - 1] - 1);
+  }
+  hf_up = nu; hf_dn = nd;
+  if (S->time_sym && hf_dn < hf_up) std::swap(hf_up, hf_dn);  // :799-805
+  S->hf_up = hf_up; S->hf_dn = hf_dn;
+  // combine_2 remap (:855-866)
+  for (int i = 1; i <= norb; i++) {
+    int a = S->orb_order[i - 1];
+    for (int j = 1; j <= norb; j++) {
+      int b = S->orb_order[j - 1];
+      S->c2(i, j) = (a > b) ? (a * (a - 1)) / 2 + b : (b * (b - 1)) / 2 + a;
+    }
+  }
+  S->nuclear_nuclear_energy = integral_value(*S, n1, n1, n1, n1);  // :398
+  return S;
+}
+
+void *orc_heg_new(int n_dim, double r_s, int nelec, int nup, double cutoff_radius) {
+  System *S = new System();
+  S->model = 1; S->n_dim = n_dim; S->r_s = r_s; S->nelec = nelec; S->nup = nup; S->ndn = nelec - nup; S->cutoff_radius = cutoff_radius;
+  heg_setup(*S);
+  return S;
+}
+
+void *orc_hubbardk_new(int l_x, int l_y, double t, double U, int nup, int ndn) {
+  System *S = new System();
+  S->model = 2; S->l_x = l_x; S->l_y = l_y; S->hub_t = t; S->hub_U = U; S->nup = nup; S->ndn = ndn; S->nelec = nup + ndn;
+  hubbard_setup(*S);
+  return S;
+}
+
+void orc_free(void *h) { delete (System *)h; }
+
+int orc_norb(void *h) { return ((System *)h)->norb; }
+long long orc_nint(void *h) { return (long long)((System *)h)->integrals.size(); }
+void orc_get_chem(void *h, double *integrals, int *combine_2, int *orb_order, int *orbsym, double *orbital_energies, double *enuc, uint64_t *hf /*4 words*/) {
+  System *S = (System *)h;
+  if (integrals) memcpy(integrals, S->integrals.data(), S->integrals.size() * sizeof(double));
+  if (combine_2) memcpy(combine_2, S->combine_2.data(), S->combine_2.size() * sizeof(int));
+  if (orb_order) memcpy(orb_order, S->orb_order.data(), S->orb_order.size() * sizeof(int));
+  if (orbsym) memcpy(orbsym, S->orbital_symmetries.data(), S->norb * sizeof(int));
+  if (orbital_energies) memcpy(orbital_energies, S->orbital_energies.data(), S->norb * sizeof(double));
+  if (enuc) *enuc = S->nuclear_nuclear_energy;
+  if (hf) { memcpy(hf, &S->hf_up, 16); memcpy(hf + 2, &S->hf_dn, 16); }
+}
+void orc_get_heg(void *h, double *k_vectors /*n_dim*norb*/, double *length_cell, int *k_rel) {
+  System *S = (System *)h;
+  if (k_vectors) memcpy(k_vectors, S->k_vectors.data(), S->k_vectors.size() * sizeof(double));
+  if (length_cell) *length_cell = S->length_cell;
+  if (k_rel) memcpy(k_rel, S->k_rel.data(), S->k_rel.size() * sizeof(int));
+}
+void orc_get_hubbardk(void *h, int *k_vectors, double *k_energies, double *ubyn) {
+  System *S = (System *)h;
+  if (k_vectors) memcpy(k_vectors, S->hk_vectors.data(), S->hk_vectors.size() * sizeof(int));
+  if (k_energies) memcpy(k_energies, S->k_energies.data(), S->k_energies.size() * sizeof(double));
+  if (ubyn) *ubyn = S->ubyn;
+}
+
+// element H(i,j) for arrays of det pairs (dets as 16-byte little-endian integers)
+void orc_elements(void *h, long long n, const det_t *iu, const det_t *id, const det_t *ju, const det_t *jd, double *out) {
+  System *S = (System *)h;
+  for (long long k = 0; k < n; k++) out[k] = hamiltonian(*S, iu[k], id[k], ju[k], jd[k]);
+}
+int orc_excitation_level(const det_t *iu, const det_t *id, const det_t *ju, const det_t *jd) { return excitation_level(*iu, *id, *ju, *jd); }
+
+// build (incremental when ndet_old == rows already stored in the handle); returns stored nnz
+long long orc_build_upper(void *h, long long n, const det_t *up, const det_t *dn, int incremental) {
+  System *S = (System *)h;
+  if (!incremental) { S->sparse_ndet = 0; S->H_indices.clear(); S->H_values.clear(); S->H_nonzero_elements.clear(); }
+  build_upper(*S, n, up, dn, incremental != 0);
+  return (long long)S->H_indices.size();
+}
+void orc_get_upper(void *h, i8b *counts, i8b *indices, double *values) {
+  System *S = (System *)h;
+  memcpy(counts, S->H_nonzero_elements.data(), S->H_nonzero_elements.size() * sizeof(i8b));
+  memcpy(indices, S->H_indices.data(), S->H_indices.size() * sizeof(i8b));
+  memcpy(values, S->H_values.data(), S->H_values.size() * sizeof(double));
+}
+void orc_matvec_upper(long long n, const i8b *indices, const i8b *counts, const double *values, const double *x, double *y) {
+  matvec_upper(n, indices, counts, values, x, y);
+}
+// Davidson on an explicit upper-tri CSR.  ritz (capacity ritz_cap) receives the logged Ritz values; returns #logged
+int orc_davidson(long long n, int n_states, const i8b *indices, const i8b *counts, const double *values, const double *v0,
+                 double *evecs, double *evals, double *ritz, int ritz_cap, int *n_matvec) {
+  std::vector<double> log;
+  davidson_sparse(n, n_states, evecs, evals, indices, counts, values, v0, &log, n_matvec);
+  int m = (int)std::min<size_t>(log.size(), (size_t)ritz_cap);
+  for (int i = 0; i < m; i++) ritz[i] = log[i];
+  return (int)log.size();
+}
+// projector step of do_walk.f90:2255-2325 on the deterministic space:
+// deltaw = (-tau H) w  (stored matrix already scaled by -tau, semistoch.f90:657,880)
+// deltaw += e_trial*tau*w ; w += deltaw
+void orc_projector_step(long long n, const i8b *indices, const i8b *counts, const double *minus_tau_H_values, double tau,
+                        double e_trial, double *w, double *deltaw) {
+  matvec_upper(n, indices, counts, minus_tau_H_values, w, deltaw);
+  for (long long i = 0; i < n; i++) deltaw[i] = deltaw[i] + e_trial * tau * w[i];
+  for (long long i = 0; i < n; i++) w[i] = w[i] + deltaw[i];
+}
+
+int orc_hci(void *h, const double *eps_var_sched30, int n_states, int max_iters, int max_dets) {
+  return perform_hci(*(System *)h, eps_var_sched30, n_states, max_iters, max_dets);
+}
+long long orc_hci_ndets(void *h) { return (long long)((System *)h)->hci_up.size(); }
+int orc_hci_niter(void *h) { return (int)((System *)h)->log_ndet.size(); }
+void orc_hci_get(void *h, det_t *up, det_t *dn, double *wts, double *energy, i8b *log_ndet, i8b *log_nnz, i8b *log_nritz, double *log_energy) {
+  System *S = (System *)h;
+  if (up) memcpy(up, S->hci_up.data(), S->hci_up.size() * 16);
+  if (dn) memcpy(dn, S->hci_dn.data(), S->hci_dn.size() * 16);
+  if (wts) memcpy(wts, S->hci_wts.data(), S->hci_wts.size() * sizeof(double));
+  if (energy) memcpy(energy, S->hci_energy.data(), S->hci_energy.size() * sizeof(double));
+  if (log_ndet) memcpy(log_ndet, S->log_ndet.data(), S->log_ndet.size() * sizeof(i8b));
+  if (log_nnz) memcpy(log_nnz, S->log_nnz.data(), S->log_nnz.size() * sizeof(i8b));
+  if (log_nritz) memcpy(log_nritz, S->log_nritz.data(), S->log_nritz.size() * sizeof(i8b));
+  if (log_energy) memcpy(log_energy, S->log_energy.data(), S->log_energy.size() * sizeof(double));
+}
+long long orc_hci_nritz(void *h) { return (long long)((System *)h)->log_ritz.size(); }
+void orc_hci_get_ritz(void *h, double *ritz) { System *S = (System *)h; memcpy(ritz, S->log_ritz.data(), S->log_ritz.size() * sizeof(double)); }
+
+}  // extern "C"
