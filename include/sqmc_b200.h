@@ -1,0 +1,137 @@
+/*
+ * sqmc_b200.h -- C ABI of libsqmc_b200.so, the B200-native (sm_100a) replacement
+ * of ONE hot path of QMC-Cornell/sqmc: sparse Hamiltonian construction over a
+ * determinant list + the repeated sparse H.v (Davidson matvec / deterministic
+ * projector).  Everything else of the reference (driver, input, selection,
+ * PT, stochastic walk) stays Fortran and calls in through ISO_C_BINDING
+ * (fortran/sqmc_b200_iface.f90).
+ *
+ * Conventions
+ *  - all functions return int status, 0 = ok; sqmc_b200_last_error() gives the
+ *    message (the reference's error style is `stop`/mpi_stop, mpi_routines.f90:5137;
+ *    the Fortran shim maps non-zero to mpi_stop).
+ *  - all pointers are HOST pointers owned by the caller unless the name ends in
+ *    _dev; the library owns all device memory behind the opaque handle.
+ *  - determinants are arrays of 16-byte little-endian integers = Fortran
+ *    integer(ik), ik = 16 bytes (types.f90:26); bit k-1 set <=> orbital k occupied.
+ *  - row / column indices exchanged with the caller are 1-based int64 (i8b,
+ *    types.f90:18), exactly the reference's H_indices / H_nonzero_elements.
+ *  - one host thread per process calls in (the reference is single threaded per
+ *    MPI rank); one process drives one GPU.
+ *  - there is NO CPU fallback: every entry point fails (non-zero) when no
+ *    sm_100 device is usable.
+ *
+ * File:line citations are relative to /root/reference/src.
+ */
+#ifndef SQMC_B200_H
+#define SQMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqmc_b200_handle sqmc_b200_handle;
+
+/* ---- process / device / communicator -------------------------------------
+ * Replaces cluster_init's MPI_INIT + communicators for this path
+ * (mpi_routines.f90:766-915).  nccl_unique_id: 128 opaque bytes (ncclUniqueId)
+ * produced by sqmc_b200_get_unique_id on rank 0 and broadcast by the caller
+ * (e.g. with MPI_Bcast); ignored when nranks == 1. */
+int sqmc_b200_get_unique_id(void *nccl_unique_id_128B);
+int sqmc_b200_init(int device, int rank, int nranks, const void *nccl_unique_id_128B);
+int sqmc_b200_finalize(void);
+const char *sqmc_b200_last_error(void);
+
+/* ---- system set-up (once) -------------------------------------------------
+ * chem: module globals integrals / combine_2 / norb,nup,ndn / time_sym,z
+ *       (chemistry.f90:24,104,396-398,855-867; nuclear energy is
+ *       integrals(integral_index(norb+1,...)), :398).
+ *       integrals: nint doubles, 1-based Fortran array passed as is.
+ *       combine_2: (norb+1)x(norb+1) int32, column-major. */
+int sqmc_b200_system_chem(sqmc_b200_handle **h, int norb, int nup, int ndn, const double *integrals, int64_t nint,
+                          const int32_t *combine_2, int time_sym, int z);
+/* heg: k_vectors(n_dim,norb) column-major doubles, length_cell (heg.f90:208,643-749) */
+int sqmc_b200_system_heg(sqmc_b200_handle **h, int norb, int n_dim, const double *k_vectors, double length_cell, int nup,
+                         int ndn);
+/* hubbardk: k_vectors(2,nsites) int32 column-major, k_energies(nsites), ubyn=U/nsites
+ * (hubbard.f90:2179-2324); l_x,l_y give the momentum period. */
+int sqmc_b200_system_hubbardk(sqmc_b200_handle **h, int l_x, int l_y, const int32_t *k_vectors, const double *k_energies,
+                              double ubyn, int nup, int ndn);
+int sqmc_b200_free(sqmc_b200_handle *h);
+
+/* ---- sparse H build --------------------------------------------------------
+ * Replaces generate_sparse_ham_chem_upper_triangular (chemistry.f90:7639),
+ * its _mpi twin (:8012), generate_sparse_ham_heg_upper_triangular
+ * (heg.f90:3553) and generate_sparse_ham_hubbardk_upper_triangular
+ * (hubbard.f90:9435).  dets_up/dn: n x 16 B in the CALLER's row order (the
+ * global list under MPI; the library shards rows itself).  ndet_old mirrors
+ * sparse_ham%ndet (incremental reuse, chemistry.f90:7769-7843): rows
+ * 1..ndet_old are promised unchanged since the previous call on this handle.
+ * The resulting matrix is identical to a from-scratch build.
+ * nnz_upper_out: stored entries of the reference's upper-triangular format
+ * (what its log prints as "# of nonzero elem in H"), summed over ranks. */
+int sqmc_b200_build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t ndet_old,
+                      int64_t *nnz_upper_out);
+/* Fill the reference's arrays (sparse_mat, commons/common_selected_ci.f90:26-31):
+ * H_nonzero_elements(n) per-row counts, H_indices(nnz_upper) 1-based int64
+ * columns ascending with the diagonal first, H_values(nnz_upper).  Single-rank
+ * handles only (under nranks>1 each rank exports its own rows: row_first/row_count
+ * from sqmc_b200_local_rows; counts are for those rows). */
+int sqmc_b200_export_upper(sqmc_b200_handle *h, int64_t *H_nonzero_elements, int64_t *H_indices, double *H_values);
+/* Import an existing reference-format matrix instead of building (dtm_projector
+ * read path, do_walk.f90:883-951): n rows, upper triangular, 1-based. */
+int sqmc_b200_import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *H_nonzero_elements, const int64_t *H_indices,
+                           const double *H_values);
+int sqmc_b200_nnz(sqmc_b200_handle *h, int64_t *n, int64_t *nnz_upper, int64_t *nnz_full);
+int sqmc_b200_local_rows(sqmc_b200_handle *h, int64_t *n_local_rows, int64_t *nnz_full_local);
+/* diagonal elements H_ii for a det list (hci.f90:664-676 "quick hack" loops) */
+int sqmc_b200_diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag);
+
+/* ---- sparse H.v -------------------------------------------------------------
+ * Replaces fast_sparse_matrix_multiply_upper_triangular (more_tools.f90:3622),
+ * _mpi (:3674) and _local_band (:3562).  x, y: nvec vectors of length n in
+ * caller row order, leading dimension ldx (column-major, like v(:,i)).
+ * Host<->device copies are inside the call. */
+int sqmc_b200_matvec(sqmc_b200_handle *h, const double *x, double *y, int nvec, int64_t ldx);
+/* Deterministic projector step of walk (do_walk.f90:2255-2325):
+ *   deltaw = Hstored.w + e_trial*tau*w      (Hstored = -tau*H after scale_values(-tau),
+ *                                            semistoch.f90:657,880)
+ * The caller then does walk_wt(imp) += deltaw (:2321-2323). */
+int sqmc_b200_projector(sqmc_b200_handle *h, double tau, double e_trial, const double *w, double *deltaw);
+/* values *= ratio: the tau rescaling of do_walk.f90:2179,2919 */
+int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio);
+
+/* ---- Davidson ------------------------------------------------------------------
+ * Replaces davidson_sparse (more_tools.f90:2018) / davidson_sparse_mpi2 (:2525):
+ * diagonal preconditioner with the 1e-8 guard, <= max_vec_per_state (50) Krylov
+ * vectors per state then restart, stop when max|dE| < tol (1e-10, :73,2213).
+ * v0: n x n_states column-major initial vectors (NULL => unit vectors on the
+ * first n_states rows, :2085-2088).  evecs: n x n_states, evals: n_states.
+ * ritz_log (may be NULL): receives up to ritz_log_cap*n_states doubles, the
+ * values the reference prints as "Iteration, Eigenvalues=" (:2130,2219). */
+int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
+                       int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+
+/* ---- device-resident entry points (used by bench.py for the HBM-resident leg)
+ * x_dev/y_dev are device pointers in the library's INTERNAL row order
+ * (length = n for x, n_local_rows for y).  stream is a cudaStream_t (0 = default). */
+int sqmc_b200_matvec_dev(sqmc_b200_handle *h, const double *x_dev, double *y_dev, void *stream);
+/* average device time (ms) of the last sqmc_b200_matvec_dev launches is measured by the caller with events */
+int sqmc_b200_device_malloc(void **p, int64_t bytes);
+int sqmc_b200_device_free(void *p);
+int sqmc_b200_memcpy_h2d(void *dst_dev, const void *src, int64_t bytes);
+int sqmc_b200_memcpy_d2h(void *dst, const void *src_dev, int64_t bytes);
+int sqmc_b200_device_sync(void);
+/* permutation between caller order and internal order: internal row p holds caller row perm[p] (0-based) */
+int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm);
+/* timing of the phases of the last build, ms (device events): [0] sort/prep [1] count [2] fill+sort [3] eval+compact [4] total */
+int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms5);
+/* number of kernels launched by the library since init (for gpu_launches accounting) */
+int64_t sqmc_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

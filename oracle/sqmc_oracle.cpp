@@ -646,27 +646,44 @@ static int find_orb_id(System &S, int kx, int ky, int kz) {  // heg.f90:752-771
 }
 
 // ---------------------------------------------------------------------------
-// Hubbard k-space set-up: hubbard.f90:2179-2324 generate_k_vectors (square
-// lattice, pbc): k = (2*i, 2*j) in units of pi/l for i in 0..l_x-1, shifted to
-// the first Brillouin zone (-l, l]; k_energies = -2t(cos kx + cos ky);
-// ubyn = U / nsites.  Orbital order follows the reference loop order.
+// Hubbard k-space set-up: hubbard.f90:2179-2290 generate_k_vectors.
+// k(1,l_y*(i-1)+j) = -l_x+2i, k(2,.) = -l_y+2j (units of pi/l, period 2l; odd l
+// shifted by -1), k_energies = -2t(cos(pi kx/l_x)+cos(pi ky/l_y)), then orbitals
+// selection-sorted by energy with exact-equality minval (first index wins);
+// ubyn = U/nsites.
 // ---------------------------------------------------------------------------
 static void hubbard_setup(System &S) {
   int ns = S.l_x * S.l_y;
   S.norb = ns;
+  std::vector<int> kv(2 * ns);
+  std::vector<double> ke(ns);
+  for (int i = 1; i <= S.l_x; i++)
+    for (int j = 1; j <= S.l_y; j++) {
+      int o = S.l_y * (i - 1) + j - 1;
+      kv[2 * o] = -S.l_x + 2 * i;
+      kv[2 * o + 1] = -S.l_y + 2 * j;
+    }
+  if (S.l_x % 2 == 1) for (int o = 0; o < ns; o++) kv[2 * o] -= 1;
+  if (S.l_y % 2 == 1) for (int o = 0; o < ns; o++) kv[2 * o + 1] -= 1;
+  for (int o = 0; o < ns; o++) {
+    if (S.l_y == 1) ke[o] = -2.0 * S.hub_t * (std::cos(PI_ * kv[2 * o] / (double)S.l_x));
+    else if (S.l_x == 1) ke[o] = -2.0 * S.hub_t * (std::cos(PI_ * kv[2 * o + 1] / (double)S.l_y));
+    else ke[o] = -2.0 * S.hub_t * (std::cos(PI_ * kv[2 * o] / (double)S.l_x) + std::cos(PI_ * kv[2 * o + 1] / (double)S.l_y));
+  }
+  std::vector<double> tmp(ke);
+  std::vector<int> sortorder(ns);
+  for (int i = 0; i < ns; i++) {
+    double mn = *std::min_element(tmp.begin(), tmp.end());
+    for (int j = 0; j < ns; j++)
+      if (tmp[j] == mn) { tmp[j] = *std::max_element(tmp.begin(), tmp.end()) + 1.0; sortorder[i] = j; break; }
+  }
   S.hk_vectors.assign(2 * ns, 0);
   S.k_energies.assign(ns, 0.0);
-  int idx = 0;
-  for (int i = 0; i < S.l_x; i++)
-    for (int j = 0; j < S.l_y; j++) {
-      int kx = 2 * i, ky = 2 * j;
-      if (kx > S.l_x) kx -= 2 * S.l_x;
-      if (ky > S.l_y) ky -= 2 * S.l_y;
-      S.hk_vectors[2 * idx] = kx;
-      S.hk_vectors[2 * idx + 1] = ky;
-      S.k_energies[idx] = -2.0 * S.hub_t * (std::cos(PI_ * kx / S.l_x) + std::cos(PI_ * ky / S.l_y));
-      idx++;
-    }
+  for (int i = 0; i < ns; i++) {
+    S.k_energies[i] = ke[sortorder[i]];
+    S.hk_vectors[2 * i] = kv[2 * sortorder[i]];
+    S.hk_vectors[2 * i + 1] = kv[2 * sortorder[i] + 1];
+  }
   S.ubyn = S.hub_U / ns;
 }
 

@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+Names follow the Fortran entry points they stand in for (paths relative to
+/root/reference/src):
+
+  SparseHamiltonian.generate_sparse_ham_upper_triangular
+        generate_sparse_ham_chem_upper_triangular   chemistry.f90:7639
+        generate_sparse_ham_heg_upper_triangular    heg.f90:3553
+        generate_sparse_ham_hubbardk_upper_triangular hubbard.f90:9435
+  SparseHamiltonian.fast_sparse_matrix_multiply_upper_triangular
+        more_tools.f90:3622 (and _mpi :3674, _local_band :3562)
+  SparseHamiltonian.davidson_sparse                 more_tools.f90:2018 / :2525
+  SparseHamiltonian.projector_step                  do_walk.f90:2255-2325
+
+Everything is a thin call into the C ABI of libsqmc_b200.so; there is no Python
+or CPU implementation of any of it here.  Determinants are python ints or
+(n,2) uint64 arrays (little-endian 128-bit = Fortran integer(16)).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SqmcError, check
+
+
+def dets_to_u64(dets):
+    a = np.asarray(dets)
+    if a.dtype == np.uint64 and a.ndim == 2 and a.shape[1] == 2:
+        return np.ascontiguousarray(a)
+    out = np.zeros((len(dets), 2), dtype=np.uint64)
+    for k, d in enumerate(dets):
+        d = int(d)
+        out[k, 0] = d & 0xFFFFFFFFFFFFFFFF
+        out[k, 1] = d >> 64
+    return out
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SparseHamiltonian:
+    """Opaque device-resident H for one system (chem / heg / hubbardk)."""
+
+    def __init__(self, system, device=0):
+        from . import systems
+        _lib.init(device=device)
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.system = system
+        self.n = 0
+        L = self._L
+        if isinstance(system, systems.ChemSystem):
+            integrals = np.ascontiguousarray(system.integrals, dtype=np.float64)
+            c2 = np.asfortranarray(system.combine_2, dtype=np.int32)
+            check(L.sqmc_b200_system_chem(C.byref(self._h), system.norb, system.nup, system.ndn, _p(integrals), len(integrals),
+                                          c2.ctypes.data_as(C.c_void_p), int(system.time_sym), int(system.z)))
+        elif isinstance(system, systems.HegSystem):
+            kv = np.ascontiguousarray(system.k_vectors, dtype=np.float64)
+            check(L.sqmc_b200_system_heg(C.byref(self._h), system.norb, system.n_dim, _p(kv), float(system.length_cell),
+                                         system.nup, system.ndn))
+        elif isinstance(system, systems.HubbardKSystem):
+            kv = np.ascontiguousarray(system.k_vectors, dtype=np.int32)
+            ke = np.ascontiguousarray(system.k_energies, dtype=np.float64)
+            check(L.sqmc_b200_system_hubbardk(C.byref(self._h), system.l_x, system.l_y, _p(kv), _p(ke), float(system.ubyn),
+                                              system.nup, system.ndn))
+        else:
+            raise SqmcError("unknown system type %r" % type(system))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.sqmc_b200_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- build ---------------------------------------------------------
+    def generate_sparse_ham_upper_triangular(self, dets_up, dets_dn, ndet_old=0):
+        """Build H over the determinant list (caller order). Returns nnz of the
+        reference's upper-triangular format (its "# of nonzero elem in H")."""
+        up, dn = dets_to_u64(dets_up), dets_to_u64(dets_dn)
+        if len(up) != len(dn):
+            raise SqmcError("dets_up / dets_dn length mismatch")
+        nnz = C.c_int64()
+        check(self._L.sqmc_b200_build_h(self._h, len(up), _p(up), _p(dn), int(ndet_old), C.byref(nnz)))
+        self.n = len(up)
+        return nnz.value
+
+    def import_upper(self, H_nonzero_elements, H_indices, H_values):
+        cnt = np.ascontiguousarray(H_nonzero_elements, dtype=np.int64)
+        idx = np.ascontiguousarray(H_indices, dtype=np.int64)
+        val = np.ascontiguousarray(H_values, dtype=np.float64)
+        check(self._L.sqmc_b200_import_upper(self._h, len(cnt), _p(cnt), _p(idx), _p(val)))
+        self.n = len(cnt)
+
+    def nnz(self):
+        n, u, f = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._L.sqmc_b200_nnz(self._h, C.byref(n), C.byref(u), C.byref(f)))
+        return dict(n=n.value, nnz_upper=u.value, nnz_full=f.value)
+
+    def local_rows(self):
+        r, z = C.c_int64(), C.c_int64()
+        check(self._L.sqmc_b200_local_rows(self._h, C.byref(r), C.byref(z)))
+        return r.value, z.value
+
+    def export_upper(self):
+        """-> (H_nonzero_elements int64[n], H_indices int64[nnz] 1-based, H_values f64[nnz])"""
+        info = self.nnz()
+        nloc, _ = self.local_rows()
+        cnt = np.zeros(nloc, dtype=np.int64)
+        idx = np.zeros(info["nnz_upper"], dtype=np.int64)
+        val = np.zeros(info["nnz_upper"], dtype=np.float64)
+        check(self._L.sqmc_b200_export_upper(self._h, _p(cnt), _p(idx), _p(val)))
+        tot = int(cnt.sum())
+        return cnt, idx[:tot], val[:tot]
+
+    def diagonal(self, dets_up, dets_dn):
+        up, dn = dets_to_u64(dets_up), dets_to_u64(dets_dn)
+        out = np.zeros(len(up))
+        check(self._L.sqmc_b200_diagonal(self._h, len(up), _p(up), _p(dn), _p(out)))
+        return out
+
+    def build_times(self):
+        t = np.zeros(5)
+        check(self._L.sqmc_b200_build_times(self._h, _p(t)))
+        return dict(prep_ms=t[0], count_ms=t[1], fill_sort_ms=t[2], eval_compact_ms=t[3], total_ms=t[4])
+
+    def perm(self):
+        p = np.zeros(self.n, dtype=np.int64)
+        check(self._L.sqmc_b200_get_perm(self._h, _p(p)))
+        return p
+
+    # ---- H.v -------------------------------------------------------------
+    def fast_sparse_matrix_multiply_upper_triangular(self, vector):
+        """answer = H . vector; vector (n,) or (n, nvec) in caller row order."""
+        x = np.asarray(vector, dtype=np.float64)
+        one = x.ndim == 1
+        xf = np.asfortranarray(x.reshape(self.n, -1))
+        y = np.zeros_like(xf, order="F")
+        check(self._L.sqmc_b200_matvec(self._h, _p(xf), _p(y), xf.shape[1], self.n))
+        return y[:, 0].copy() if one else np.ascontiguousarray(y)
+
+    matvec = fast_sparse_matrix_multiply_upper_triangular
+
+    def scale_values(self, ratio):
+        check(self._L.sqmc_b200_scale_values(self._h, float(ratio)))
+
+    def projector_step(self, tau, e_trial, w):
+        """deltaw = Hstored.w + e_trial*tau*w (do_walk.f90:2259-2290)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        dw = np.zeros_like(w)
+        check(self._L.sqmc_b200_projector(self._h, float(tau), float(e_trial), _p(w), _p(dw)))
+        return dw
+
+    # ---- Davidson ----------------------------------------------------------
+    def davidson_sparse(self, n_states=1, initial_vector=None, tol=1.0e-10, max_vec_per_state=50):
+        n = self.n
+        v0 = None
+        if initial_vector is not None:
+            v0 = np.asfortranarray(np.asarray(initial_vector, dtype=np.float64).reshape(n, n_states))
+        evecs = np.zeros((n, n_states), order="F")
+        evals = np.zeros(n_states)
+        cap = 1024
+        ritz = np.zeros(cap * n_states)
+        nmv, nlog = C.c_int(), C.c_int()
+        check(self._L.sqmc_b200_davidson(self._h, n_states, _p(v0), _p(evecs), _p(evals), float(tol), int(max_vec_per_state),
+                                         C.byref(nmv), _p(ritz), cap, C.byref(nlog)))
+        k = min(nlog.value, cap)
+        return dict(evals=evals, evecs=np.ascontiguousarray(evecs), ritz=ritz[:k * n_states].reshape(k, n_states),
+                    n_matvec=nmv.value)

@@ -1,0 +1,301 @@
+// api.cu -- the C ABI of libsqmc_b200.so (include/sqmc_b200.h): handle management,
+// device / NCCL set-up and the host-pointer entry points (H2D / D2H inside the call).
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/sqmc_b200.h"
+#include "handle.h"
+
+namespace sqmc {
+std::string g_last_error;
+int64_t g_launch_count = 0;
+Global G;
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+static int require_init() {
+  if (!G.inited) {
+    set_error("sqmc_b200_init has not been called (or failed): no CUDA device, no CPU fallback");
+    return 1;
+  }
+  return 0;
+}
+}  // namespace sqmc
+
+using namespace sqmc;
+
+extern "C" {
+
+const char *sqmc_b200_last_error(void) { return g_last_error.c_str(); }
+int64_t sqmc_b200_launch_count(void) { return g_launch_count; }
+
+int sqmc_b200_get_unique_id(void *id128) {
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) { set_error("ncclGetUniqueId: %s", ncclGetErrorString(r)); return 3; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+int sqmc_b200_init(int device, int rank, int nranks, const void *id128) {
+  if (G.inited) { set_error("sqmc_b200_init: already initialised"); return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("sqmc_b200_init: no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return 1;
+  }
+  if (device < 0 || device >= ndev) { set_error("sqmc_b200_init: device %d out of range (%d devices)", device, ndev); return 1; }
+  SQ_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SQ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("sqmc_b200_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return 1;
+  }
+  G.device = device;
+  G.rank = rank;
+  G.nranks = nranks < 1 ? 1 : nranks;
+  G.sm_count = prop.multiProcessorCount;
+  SQ_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  if (G.nranks > 1) {
+    if (!id128) { set_error("sqmc_b200_init: nranks>1 needs an ncclUniqueId"); return 1; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = ncclCommInitRank(&G.comm, G.nranks, id, G.rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", ncclGetErrorString(r)); return 3; }
+  }
+  G.inited = true;
+  return 0;
+}
+
+int sqmc_b200_finalize(void) {
+  if (!G.inited) return 0;
+  if (G.comm) ncclCommDestroy(G.comm);
+  G.comm = nullptr;
+  if (G.stream) cudaStreamDestroy(G.stream);
+  G.stream = nullptr;
+  G.inited = false;
+  return 0;
+}
+
+static sqmc_b200_handle *new_handle(int model, int norb, int nup, int ndn) {
+  sqmc_b200_handle *h = new sqmc_b200_handle();
+  memset(&h->T, 0, sizeof(h->T));
+  h->T.model = model;
+  h->T.norb = norb;
+  h->T.nup = nup;
+  h->T.ndn = ndn;
+  h->T.z = 1;
+  h->NW = norb <= 64 ? 1 : 2;
+  return h;
+}
+
+int sqmc_b200_system_chem(sqmc_b200_handle **out, int norb, int nup, int ndn, const double *integrals, int64_t nint,
+                          const int32_t *combine_2, int time_sym, int z) {
+  SQ_CHECK(require_init());
+  if (norb < 1 || norb > 127) { set_error("system_chem: norb=%d outside 1..127 (types.f90:44)", norb); return 2; }
+  if (nup < ndn) { set_error("system_chem: nup < ndn (chemistry.f90:158)"); return 2; }
+  if (time_sym && nup != ndn) { set_error("system_chem: time_sym needs nup == ndn (chemistry.f90:186)"); return 2; }
+  if (time_sym && z != 1 && z != -1) { set_error("system_chem: z must be +1 or -1 (chemistry.f90:190)"); return 2; }
+  sqmc_b200_handle *h = new_handle(MODEL_CHEM, norb, nup, ndn);
+  int n1 = norb + 1;
+  SQ_CUDA(cudaMalloc(&h->d_integrals, nint * sizeof(double)));
+  SQ_CUDA(cudaMalloc(&h->d_combine_2, (size_t)n1 * n1 * sizeof(int32_t)));
+  SQ_CUDA(cudaMemcpy(h->d_integrals, integrals, nint * sizeof(double), cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(h->d_combine_2, combine_2, (size_t)n1 * n1 * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->T.integrals = h->d_integrals;
+  h->T.combine_2 = h->d_combine_2;
+  h->T.nint = nint;
+  h->T.time_sym = time_sym ? 1 : 0;
+  h->T.z = z;
+  h->T.sqrt2 = sqrt(2.0);            // chemistry.f90:360-361
+  h->T.sqrt2inv = 1.0 / h->T.sqrt2;
+  // nuclear_nuclear_energy = integrals(integral_index(norb+1,norb+1,norb+1,norb+1)) (chemistry.f90:398)
+  int64_t a = combine_2[(size_t)(n1 - 1) * n1 + (n1 - 1)];
+  int64_t idx = (a * (a - 1)) / 2 + a;
+  if (idx < 1 || idx > nint) { set_error("system_chem: integrals array shorter than the nuclear-energy index"); delete h; return 2; }
+  h->T.enuc = integrals[idx - 1];
+  *out = h;
+  return 0;
+}
+
+int sqmc_b200_system_heg(sqmc_b200_handle **out, int norb, int n_dim, const double *k_vectors, double length_cell, int nup,
+                         int ndn) {
+  SQ_CHECK(require_init());
+  if (norb < 1 || norb > 127 || (n_dim != 2 && n_dim != 3)) { set_error("system_heg: bad norb/n_dim"); return 2; }
+  sqmc_b200_handle *h = new_handle(MODEL_HEG, norb, nup, ndn);
+  SQ_CUDA(cudaMalloc(&h->d_kvec, (size_t)norb * n_dim * sizeof(double)));
+  SQ_CUDA(cudaMemcpy(h->d_kvec, k_vectors, (size_t)norb * n_dim * sizeof(double), cudaMemcpyHostToDevice));
+  h->T.k_vectors = h->d_kvec;
+  h->T.n_dim = n_dim;
+  h->T.length_cell = length_cell;
+  *out = h;
+  return 0;
+}
+
+int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const int32_t *k_vectors, const double *k_energies,
+                              double ubyn, int nup, int ndn) {
+  SQ_CHECK(require_init());
+  int ns = l_x * l_y;
+  if (ns < 1 || ns > 127) { set_error("system_hubbardk: bad lattice"); return 2; }
+  sqmc_b200_handle *h = new_handle(MODEL_HUBBARDK, ns, nup, ndn);
+  SQ_CUDA(cudaMalloc(&h->d_hkvec, (size_t)2 * ns * sizeof(int32_t)));
+  SQ_CUDA(cudaMalloc(&h->d_kenergies, (size_t)ns * sizeof(double)));
+  SQ_CUDA(cudaMemcpy(h->d_hkvec, k_vectors, (size_t)2 * ns * sizeof(int32_t), cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(h->d_kenergies, k_energies, (size_t)ns * sizeof(double), cudaMemcpyHostToDevice));
+  h->T.hk_vectors = h->d_hkvec;
+  h->T.k_energies = h->d_kenergies;
+  h->T.ubyn = ubyn;
+  h->T.l_x = l_x;
+  h->T.l_y = l_y;
+  *out = h;
+  return 0;
+}
+
+int sqmc_b200_free(sqmc_b200_handle *h) {
+  if (!h) return 0;
+  free_matrix(h);
+  if (h->d_integrals) cudaFree(h->d_integrals);
+  if (h->d_combine_2) cudaFree(h->d_combine_2);
+  if (h->d_kvec) cudaFree(h->d_kvec);
+  if (h->d_hkvec) cudaFree(h->d_hkvec);
+  if (h->d_kenergies) cudaFree(h->d_kenergies);
+  delete h;
+  return 0;
+}
+
+int sqmc_b200_build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t ndet_old,
+                      int64_t *nnz_upper_out) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("build_h: null handle"); return 2; }
+  SQ_CHECK(build_h(h, n, dets_up, dets_dn, ndet_old));
+  if (nnz_upper_out) *nnz_upper_out = h->nnz_upper;
+  return 0;
+}
+int sqmc_b200_export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
+  SQ_CHECK(require_init());
+  return export_upper(h, counts, indices, values);
+}
+int sqmc_b200_import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values) {
+  SQ_CHECK(require_init());
+  return import_upper(h, n, counts, indices, values);
+}
+int sqmc_b200_nnz(sqmc_b200_handle *h, int64_t *n, int64_t *nnz_upper, int64_t *nnz_full) {
+  if (n) *n = h->n;
+  if (nnz_upper) *nnz_upper = h->nnz_upper;
+  if (nnz_full) *nnz_full = h->nnz_full;
+  return 0;
+}
+int sqmc_b200_local_rows(sqmc_b200_handle *h, int64_t *n_local_rows, int64_t *nnz_full_local) {
+  if (n_local_rows) *n_local_rows = h->row1 - h->row0;
+  if (nnz_full_local) *nnz_full_local = h->nnz_local;
+  return 0;
+}
+int sqmc_b200_diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag) {
+  SQ_CHECK(require_init());
+  return diagonal(h, n, dets_up, dets_dn, diag);
+}
+
+// x (caller order, host) -> d_x (internal order, device, full length)
+static int upload_vector(sqmc_b200_handle *h, const double *x) {
+  cudaStream_t s = G.stream;
+  SQ_CUDA(cudaMemcpyAsync(h->d_tmp, x, h->n * sizeof(double), cudaMemcpyHostToDevice, s));
+  return permute_gather(h->d_tmp, h->d_perm, h->d_x, h->n, s);
+}
+// d_y (local rows, internal order) -> y (caller order, host, full length; all ranks get the full vector)
+static int download_result(sqmc_b200_handle *h, double *y) {
+  cudaStream_t s = G.stream;
+  const int64_t nloc = h->row1 - h->row0;
+  // reuse d_x as the gather buffer
+  if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, h->d_y, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  SQ_CHECK(allgather_rows(h, h->d_x, s));
+  SQ_CHECK(permute_scatter(h->d_x, h->d_perm, h->d_tmp, h->n, s));
+  SQ_CUDA(cudaMemcpyAsync(y, h->d_tmp, h->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sqmc_b200_matvec(sqmc_b200_handle *h, const double *x, double *y, int nvec, int64_t ldx) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
+  if (ldx < h->n) { set_error("matvec: ldx < n"); return 2; }
+  for (int v = 0; v < nvec; v++) {
+    SQ_CHECK(upload_vector(h, x + (size_t)v * ldx));
+    SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, G.stream));
+    SQ_CHECK(download_result(h, y + (size_t)v * ldx));
+  }
+  return 0;
+}
+
+int sqmc_b200_projector(sqmc_b200_handle *h, double tau, double e_trial, const double *w, double *deltaw) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("projector: no matrix on this handle"); return 2; }
+  cudaStream_t s = G.stream;
+  SQ_CHECK(upload_vector(h, w));
+  SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, s));                                               // deltaw = Hstored . w  (do_walk.f90:2262)
+  SQ_CHECK(projector_epilogue(h->d_y, h->d_x + h->row0, e_trial * tau, h->row1 - h->row0, s));  // += e_trial*tau*w (:2290)
+  return download_result(h, deltaw);
+}
+
+int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("scale_values: no matrix on this handle"); return 2; }
+  SQ_CHECK(scale_array(h->d_vals, h->nnz_local, ratio, G.stream));
+  SQ_CUDA(cudaStreamSynchronize(G.stream));
+  h->scale *= ratio;
+  return 0;
+}
+
+int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
+                       int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
+  SQ_CHECK(require_init());
+  return davidson(h, n_states, v0, evecs, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged);
+}
+
+int sqmc_b200_matvec_dev(sqmc_b200_handle *h, const double *x_dev, double *y_dev, void *stream) {
+  SQ_CHECK(require_init());
+  return spmv_launch(h, x_dev, y_dev, stream ? (cudaStream_t)stream : G.stream);
+}
+int sqmc_b200_device_malloc(void **p, int64_t bytes) {
+  SQ_CHECK(require_init());
+  SQ_CUDA(cudaMalloc(p, (size_t)bytes));
+  return 0;
+}
+int sqmc_b200_device_free(void *p) {
+  if (p) cudaFree(p);
+  return 0;
+}
+int sqmc_b200_memcpy_h2d(void *dst, const void *src, int64_t bytes) {
+  SQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, G.stream));
+  SQ_CUDA(cudaStreamSynchronize(G.stream));
+  return 0;
+}
+int sqmc_b200_memcpy_d2h(void *dst, const void *src, int64_t bytes) {
+  SQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, G.stream));
+  SQ_CUDA(cudaStreamSynchronize(G.stream));
+  return 0;
+}
+int sqmc_b200_device_sync(void) {
+  SQ_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm) {
+  if (!h || !h->d_perm) { set_error("get_perm: no determinant list"); return 2; }
+  std::vector<int32_t> p(h->n);
+  SQ_CUDA(cudaMemcpy(p.data(), h->d_perm, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < h->n; i++) perm[i] = p[i];
+  return 0;
+}
+int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms5) {
+  for (int i = 0; i < 5; i++) ms5[i] = h->build_ms[i];
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1037 @@
+// build.cu -- sparse Hamiltonian construction over a determinant list (sm_100a).
+//
+// Replaces generate_sparse_ham_chem_upper_triangular (chemistry.f90:7639-8009,
+// MPI twin :8012-8546), generate_sparse_ham_heg_upper_triangular
+// (heg.f90:3553-3809), generate_sparse_ham_hubbardk_upper_triangular
+// (hubbard.f90:9435-9672) and their helper get_connected_dets_in_list
+// (chemistry.f90:9851-9991, heg.f90:3846-3964).
+//
+// GPU-first formulation (not the reference's per-row binary searches):
+//   1. determinants are sorted alpha-major (up, dn) -> INTERNAL row order; equal up
+//      strings form alpha-groups, equal dn strings beta-groups (second sorted view).
+//   2. unique alpha strings are linked through their (N-1)-electron keys (the
+//      reference's alpha_m1 idea, chemistry.f90:9819, applied to unique strings,
+//      not to determinants): the run of a key lists every alpha string one
+//      excitation away.
+//   3. candidate generation is pure XOR/popcount work, one warp per row:
+//        same alpha-group      : popc(dn^dn') in {2,4}   (dn single / double)
+//        neighbour alpha-groups : popc(dn^dn') in {0,2}   (up single, up+dn double)
+//        same beta-group        : popc(up^up') == 4       (up double)
+//      Every pair within two excitations is found exactly once per orientation.
+//   4. candidates are sorted per row, duplicates (time-reversed partners) dropped,
+//      elements evaluated with the reference's arithmetic (elements.cuh) and the
+//      abs(H) > 1e-12 filter applied (chemistry.f90:9901); the diagonal is always kept.
+//   5. FULL rows (both triangles) are produced directly; H(i,j) is always evaluated
+//      with the lower CALLER index as bra, exactly the element the reference stores
+//      in its upper triangle, so the matrix is bit-symmetric and export is a filter.
+// Compile with --fmad=false (see elements.cuh).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+#include "handle.h"
+
+namespace sqmc {
+
+// ------------------------------------------------------------------ helpers
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  int64_t n = 0;
+  int alloc(int64_t count) {
+    release();
+    n = count;
+    if (count <= 0) return 0;
+    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+      p = nullptr;
+      return 1;
+    }
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  T *take() {
+    T *q = p;
+    p = nullptr;
+    n = 0;
+    return q;
+  }
+  ~DevBuf() { release(); }
+};
+
+static const int kThreads = 256;
+static inline int nblocks(int64_t n, int t = kThreads) { return (int)std::min<int64_t>(div_up(n, t), 0x7fffffff); }
+
+// 16-byte caller dets -> NW-word strings
+template <int NW>
+__global__ void split_dets_kernel(const uint64_t *raw /*n x 2*/, uint64_t *out, int64_t n, int *bad, uint64_t hi_mask0, uint64_t hi_mask1) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t lo = raw[2 * i], hi = raw[2 * i + 1];
+  if ((lo & hi_mask0) || (hi & hi_mask1)) atomicExch(bad, 1);  // occupied orbital beyond norb
+  out[i * NW] = lo;
+  if (NW == 2) out[i * NW + 1] = hi;
+}
+
+__global__ void iota_kernel(int32_t *a, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+__global__ void gather_word_kernel(const uint64_t *src, int nw, int w, const int32_t *idx, uint64_t *out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[(int64_t)idx[i] * nw + w];
+}
+template <int NW>
+__global__ void gather_bits_kernel(const uint64_t *src, const int32_t *idx, uint64_t *out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) b_store<NW>(out, i, b_load<NW>(src, idx[i]));
+}
+__global__ void invert_perm_kernel(const int32_t *perm, int32_t *iperm, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) iperm[perm[i]] = (int32_t)i;
+}
+
+// Stable LSD radix sort of records by a multi-word key given as a list of (array, nw, word)
+// from least to most significant; idx (in/out) carries the permutation.
+struct KeyWord {
+  const uint64_t *src;
+  int nw, w, bits;
+};
+static int sort_by_words(const std::vector<KeyWord> &words, int32_t *d_idx, int64_t n, cudaStream_t s) {
+  if (n <= 1) return 0;
+  DevBuf<uint64_t> k_in, k_out;
+  DevBuf<int32_t> i_out;
+  SQ_CHECK(k_in.alloc(n));
+  SQ_CHECK(k_out.alloc(n));
+  SQ_CHECK(i_out.alloc(n));
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, d_idx, i_out.p, (int)n, 0, 64, s);
+  DevBuf<char> tmp;
+  SQ_CHECK(tmp.alloc((int64_t)tmp_bytes + 16));
+  for (const KeyWord &kw : words) {
+    if (kw.bits <= 0) continue;
+    gather_word_kernel<<<nblocks(n), kThreads, 0, s>>>(kw.src, kw.nw, kw.w, d_idx, k_in.p, n);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, d_idx, i_out.p, (int)n, 0, kw.bits, s));
+    g_launch_count += 3;
+    SQ_CUDA(cudaMemcpyAsync(d_idx, i_out.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  }
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// group boundaries of a sorted key array: flag[t] = key[t] != key[t-1]
+template <int NW>
+__global__ void group_flag_kernel(const uint64_t *keys, int32_t *flag, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  flag[t] = (t == 0) ? 1 : (b_eq(b_load<NW>(keys, t), b_load<NW>(keys, t - 1)) ? 0 : 1);
+}
+// gid = inclusive_scan(flag) - 1 ; offsets[gid] = t at flagged positions
+__global__ void group_offsets_kernel(const int32_t *flag, const int32_t *gid_incl, int32_t *gid, int64_t *off, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  int32_t g = gid_incl[t] - 1;
+  gid[t] = g;
+  if (flag[t]) off[g] = t;
+}
+
+// build the groups of a sorted key array; returns number of groups; gid[m], off[ng+1]
+template <int NW>
+static int make_groups(const uint64_t *keys, int64_t m, DevBuf<int32_t> &gid, DevBuf<int64_t> &off, int64_t &ng, cudaStream_t s) {
+  DevBuf<int32_t> flag, incl;
+  SQ_CHECK(flag.alloc(m));
+  SQ_CHECK(incl.alloc(m));
+  SQ_CHECK(gid.alloc(m));
+  group_flag_kernel<NW><<<nblocks(m), kThreads, 0, s>>>(keys, flag.p, m);
+  SQ_LAUNCH_CHECK();
+  size_t tb = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tb, flag.p, incl.p, (int)m, s);
+  DevBuf<char> tmp;
+  SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+  SQ_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, flag.p, incl.p, (int)m, s));
+  g_launch_count += 2;
+  int32_t last = 0;
+  SQ_CUDA(cudaMemcpyAsync(&last, incl.p + (m - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  ng = last;
+  SQ_CHECK(off.alloc(ng + 1));
+  group_offsets_kernel<<<nblocks(m), kThreads, 0, s>>>(flag.p, incl.p, gid.p, off.p, m);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaMemcpyAsync(off.p + ng, &m, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// time-reversal expansion (chemistry.f90:9934-9979 searches with spins flipped):
+// entry t<n : (a=up, b=dn, rep=t) ; entries for rows with up != dn: (a=dn, b=up, rep=row|SWAP)
+static const uint32_t kSwapBit = 0x80000000u;
+template <int NW>
+__global__ void ts_flag_kernel(const uint64_t *up, const uint64_t *dn, int32_t *flag, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = b_eq(b_load<NW>(up, i), b_load<NW>(dn, i)) ? 0 : 1;
+}
+template <int NW>
+__global__ void ts_expand_kernel(const uint64_t *up, const uint64_t *dn, const int32_t *flag, const int32_t *excl, uint64_t *Ea,
+                                 uint64_t *Eb, uint32_t *Erep, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Bits<NW> u = b_load<NW>(up, i), d = b_load<NW>(dn, i);
+  b_store<NW>(Ea, i, u);
+  b_store<NW>(Eb, i, d);
+  Erep[i] = (uint32_t)i;
+  if (flag[i]) {
+    int64_t t = n + excl[i];
+    b_store<NW>(Ea, t, d);
+    b_store<NW>(Eb, t, u);
+    Erep[t] = (uint32_t)i | kSwapBit;
+  }
+}
+__global__ void gather_u32_kernel(const uint32_t *src, const int32_t *idx, uint32_t *out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+__global__ void row_entry_kernel(const uint32_t *Erep, int32_t *rowE, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < m && !(Erep[t] & kSwapBit)) rowE[Erep[t]] = (int32_t)t;
+}
+__global__ void scatter_gid_kernel(const int32_t *gid_sorted, const int32_t *entry_of_sorted, int32_t *gid_of_entry, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < m) gid_of_entry[entry_of_sorted[t]] = gid_sorted[t];
+}
+
+// (N-1)-electron keys of the unique alpha strings
+template <int NW>
+__global__ void nm1_keys_kernel(const uint64_t *Ea, const int64_t *gA_off, int64_t nA, int nel, uint64_t *keys, int32_t *grp) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= nA) return;
+  Bits<NW> s = b_load<NW>(Ea, gA_off[g]);
+  Bits<NW> t = s;
+  for (int e = 0; e < nel; e++) {
+    int o = b_ctz(t);
+    b_clear_lowest(t);
+    Bits<NW> k = s;
+    b_clear(k, o);
+    b_store<NW>(keys, g * nel + e, k);
+    grp[g * nel + e] = (int32_t)g;
+  }
+}
+// for every (group, electron) the run [lo,hi) of its key in the sorted key list
+template <int NW>
+__global__ void nm1_runs_kernel(const uint64_t *Ea, const int64_t *gA_off, int64_t nA, int nel, const uint64_t *skeys, int64_t m2,
+                                int32_t *run_lo, int32_t *run_hi) {
+  int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= nA * nel) return;
+  int64_t g = id / nel;
+  int e = (int)(id % nel);
+  Bits<NW> s = b_load<NW>(Ea, gA_off[g]);
+  Bits<NW> t = s;
+  int o = 0;
+  for (int k = 0; k <= e; k++) {
+    o = b_ctz(t);
+    b_clear_lowest(t);
+  }
+  Bits<NW> key = s;
+  b_clear(key, o);
+  int64_t lo = 0, hi = m2;
+  while (lo < hi) {  // lower bound
+    int64_t mid = (lo + hi) >> 1;
+    if (b_lt(b_load<NW>(skeys, mid), key)) lo = mid + 1;
+    else hi = mid;
+  }
+  int64_t first = lo;
+  hi = m2;
+  while (lo < hi) {  // upper bound
+    int64_t mid = (lo + hi) >> 1;
+    if (b_lt(key, b_load<NW>(skeys, mid))) hi = mid;
+    else lo = mid + 1;
+  }
+  run_lo[id] = (int32_t)first;
+  run_hi[id] = (int32_t)lo;
+}
+
+// ------------------------------------------------------------------ candidate generation
+struct ConnView {
+  // expanded entries in alpha-major order
+  const uint64_t *Ea, *Eb;
+  const uint32_t *Erep;
+  const int32_t *eA;       // alpha group of entry
+  const int64_t *gA_off;   // alpha group offsets
+  const int32_t *eB;       // beta group of entry
+  const int64_t *gB_off;   // beta group offsets (into the beta-major view)
+  const uint64_t *EBa;     // a-string in beta-major order
+  const uint32_t *EBrep;   // rep in beta-major order
+  const int32_t *rowE;     // row -> its unswapped entry
+  // neighbour runs
+  const int32_t *run_lo, *run_hi, *K_grp;
+  int nel;
+};
+
+// One warp per row.  FILL=false: count candidates; FILL=true: write candidate rep indices.
+template <int NW, bool FILL>
+__global__ void __launch_bounds__(256) connect_kernel(ConnView V, int64_t row_begin, int64_t row_end, int32_t *counts /*[row-row_begin]*/,
+                                                      const int64_t *cand_ptr /*[row-row_begin]*/, int32_t *cand) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = row_begin + warp;
+  if (p >= row_end) return;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int32_t t0 = V.rowE[p];
+  const Bits<NW> a = b_load<NW>(V.Ea, t0), b = b_load<NW>(V.Eb, t0);
+  const int32_t g = V.eA[t0];
+  int64_t base = FILL ? cand_ptr[warp] : 0;
+  int cnt = 0;
+  // diagonal
+  if (FILL && lane == 0) cand[base] = (int32_t)p;
+  cnt = 1;
+  auto emit = [&](bool hit, uint32_t rep) {
+    unsigned m = __ballot_sync(full, hit);
+    if (FILL && hit) cand[base + cnt + __popc(m & lt_mask)] = (int32_t)(rep & ~kSwapBit);
+    cnt += __popc(m);
+  };
+  // (a) own alpha group: dn single / double
+  {
+    int64_t lo = V.gA_off[g], hi = V.gA_off[g + 1];
+    for (int64_t tb = lo; tb < hi; tb += 32) {
+      int64_t t = tb + lane;
+      bool in = t < hi;
+      int pc = in ? b_popc_xor(b, b_load<NW>(V.Eb, t)) : 0;
+      emit(in && (pc == 2 || pc == 4), in ? V.Erep[t] : 0u);
+    }
+  }
+  // (c) neighbour alpha groups: same dn (up single) or dn single (up single x dn single)
+  for (int e = 0; e < V.nel; e++) {
+    int32_t rlo = V.run_lo[(int64_t)g * V.nel + e], rhi = V.run_hi[(int64_t)g * V.nel + e];
+    for (int32_t r = rlo; r < rhi; r++) {
+      int32_t g2 = V.K_grp[r];
+      if (g2 == g) continue;
+      int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
+      for (int64_t tb = lo; tb < hi; tb += 32) {
+        int64_t t = tb + lane;
+        bool in = t < hi;
+        int pc = in ? b_popc_xor(b, b_load<NW>(V.Eb, t)) : 1;
+        emit(in && (pc == 0 || pc == 2), in ? V.Erep[t] : 0u);
+      }
+    }
+  }
+  // (b) own beta group: up double
+  {
+    int32_t gb = V.eB[t0];
+    int64_t lo = V.gB_off[gb], hi = V.gB_off[gb + 1];
+    for (int64_t tb = lo; tb < hi; tb += 32) {
+      int64_t t = tb + lane;
+      bool in = t < hi;
+      int pc = in ? b_popc_xor(a, b_load<NW>(V.EBa, t)) : 0;
+      emit(in && pc == 4, in ? V.EBrep[t] : 0u);
+    }
+  }
+  if (!FILL && lane == 0) counts[warp] = cnt;
+}
+
+// ------------------------------------------------------------------ per-row sort of candidate columns
+// all-ascending ("flip") bitonic network: correct for arbitrary length, see DESIGN.md
+__device__ __forceinline__ void bitonic_sort_i32(int32_t *a, int len, int tid, int nthr, bool block_sync) {
+  int np2 = 1;
+  while (np2 < len) np2 <<= 1;
+  for (int k = 2; k <= np2; k <<= 1) {
+    // flip step
+    for (int i = tid; i < np2; i += nthr) {
+      int partner = i ^ (k - 1);
+      if (partner > i && partner < len) {
+        int32_t x = a[i], y = a[partner];
+        if (x > y) { a[i] = y; a[partner] = x; }
+      }
+    }
+    if (block_sync) __syncthreads(); else __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += nthr) {
+        int partner = i ^ j;
+        if (partner > i && partner < len) {
+          int32_t x = a[i], y = a[partner];
+          if (x > y) { a[i] = y; a[partner] = x; }
+        }
+      }
+      if (block_sync) __syncthreads(); else __syncwarp();
+    }
+  }
+}
+static const int kWarpSortMax = 256;    // rows up to this length: one warp, smem
+static const int kBlockSortMax = 32768; // rows up to this length: one CTA, smem; longer: CTA in global memory
+
+__global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int64_t *ptr, const int32_t *len, int64_t nrows, int32_t *cand) {
+  __shared__ int32_t sm[8][kWarpSortMax];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * 8ll + w;
+  if (row >= nrows) return;
+  int L = len[row];
+  if (L <= 1 || L > kWarpSortMax) return;
+  int32_t *src = cand + ptr[row];
+  for (int i = lane; i < L; i += 32) sm[w][i] = src[i];
+  __syncwarp();
+  bitonic_sort_i32(sm[w], L, lane, 32, false);
+  for (int i = lane; i < L; i += 32) src[i] = sm[w][i];
+}
+__global__ void __launch_bounds__(256) sort_rows_block_kernel(const int64_t *ptr, const int32_t *len, int64_t nrows, int32_t *cand) {
+  extern __shared__ int32_t smb[];
+  for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    int L = len[row];
+    if (L <= kWarpSortMax) continue;
+    int32_t *src = cand + ptr[row];
+    if (L <= kBlockSortMax) {
+      for (int i = threadIdx.x; i < L; i += blockDim.x) smb[i] = src[i];
+      __syncthreads();
+      bitonic_sort_i32(smb, L, threadIdx.x, blockDim.x, true);
+      for (int i = threadIdx.x; i < L; i += blockDim.x) src[i] = smb[i];
+      __syncthreads();
+    } else {
+      bitonic_sort_i32(src, L, threadIdx.x, blockDim.x, true);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ element evaluation + in-row compaction
+// One warp per row.  cand (sorted) is compacted in place, vals written at the same offsets.
+template <int NW>
+__global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t *up, const uint64_t *dn, const int32_t *perm,
+                                                   int64_t row_begin, int64_t row_end, const int64_t *cand_ptr, const int32_t *cand_len,
+                                                   int32_t *cand, double *vals, int32_t *row_nnz) {
+  extern __shared__ int32_t c2s[];
+  const int32_t *c2 = T.combine_2;
+  if (T.model == MODEL_CHEM) {
+    int n1 = T.norb + 1;
+    for (int i = threadIdx.x; i < n1 * n1; i += blockDim.x) c2s[i] = T.combine_2[i];
+    __syncthreads();
+    c2 = c2s;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t p = row_begin + warp;
+  if (p >= row_end) return;
+  const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+  const Bits<NW> pu = b_load<NW>(up, p), pd = b_load<NW>(dn, p);
+  const int32_t cp = perm[p];
+  const int64_t base = cand_ptr[warp];
+  const int L = cand_len[warp];
+  int kept = 0;
+  for (int kb = 0; kb < L; kb += 32) {
+    int k = kb + lane;
+    bool in = k < L;
+    int32_t j = in ? cand[base + k] : -1;
+    int32_t jprev = (in && k > 0) ? cand[base + k - 1] : -2;
+    bool keep = false;
+    double v = 0.0;
+    if (in && j != jprev) {
+      if (j == (int32_t)p) {
+        v = model_hamiltonian<NW>(T, c2, pu, pd, pu, pd);
+        keep = true;  // diagonal is always stored (chemistry.f90:9887-9890)
+      } else {
+        Bits<NW> ju = b_load<NW>(up, j), jd = b_load<NW>(dn, j);
+        // the reference stores H(i,j) for caller index i<j with det_i as bra
+        if (cp < perm[j]) v = model_hamiltonian<NW>(T, c2, pu, pd, ju, jd);
+        else v = model_hamiltonian<NW>(T, c2, ju, jd, pu, pd);
+        keep = fabs(v) > 1.e-12;
+      }
+    }
+    __syncwarp();
+    unsigned m = __ballot_sync(full, keep);
+    if (keep) {
+      int pos = kept + __popc(m & lt_mask);
+      cand[base + pos] = j;
+      vals[base + pos] = v;
+    }
+    kept += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) row_nnz[warp] = kept;
+}
+
+// copy compacted rows to their final place
+__global__ void __launch_bounds__(256) compact_copy_kernel(const int64_t *cand_ptr, const int32_t *row_nnz, const int64_t *rowptr_chunk,
+                                                           int64_t nrows, const int32_t *cand, const double *vals, int32_t *cols_out,
+                                                           double *vals_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  int64_t src = cand_ptr[row], dst = rowptr_chunk[row];
+  int L = row_nnz[row];
+  for (int k = lane; k < L; k += 32) {
+    cols_out[dst + k] = cand[src + k];
+    vals_out[dst + k] = vals[src + k];
+  }
+}
+
+__global__ void add_offset_kernel(int64_t *a, int64_t n, int64_t off) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] += off;
+}
+
+template <int NW>
+__global__ void diag_kernel(ModelTables T, const uint64_t *up, const uint64_t *dn, int64_t n, double *out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Bits<NW> u = b_load<NW>(up, i), d = b_load<NW>(dn, i);
+  out[i] = model_hamiltonian<NW>(T, T.combine_2, u, d, u, d);
+}
+
+// exclusive scan int32 -> int64 offsets (n+1 outputs)
+static int exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n, cudaStream_t s) {
+  size_t tb = 0;
+  auto it = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>(in, cub::CastOp<int64_t>());
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, it, out, (int)(n + 1), s);
+  DevBuf<char> tmp;
+  SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+  // scanning n+1 items reads in[n]: callers allocate counts with one spare zeroed slot
+  SQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, out, (int)(n + 1), s));
+  g_launch_count += 2;
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+void free_matrix(sqmc_b200_handle *h) {
+  auto F = [](auto *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
+  F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp);
+  h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
+  h->row_starts.clear();
+}
+
+static int alloc_work_vectors(sqmc_b200_handle *h) {
+  SQ_CUDA(cudaMalloc(&h->d_x, std::max<int64_t>(h->n, 1) * sizeof(double)));
+  SQ_CUDA(cudaMalloc(&h->d_y, std::max<int64_t>(h->row1 - h->row0, 1) * sizeof(double)));
+  SQ_CUDA(cudaMalloc(&h->d_tmp, std::max<int64_t>(h->n, 1) * sizeof(double)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ the build
+template <int NW>
+static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn) {
+  cudaStream_t s = G.stream;
+  const ModelTables &T = h->T;
+  cudaEvent_t ev[5];
+  for (auto &e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], s);
+
+  // ---- upload + split
+  DevBuf<uint64_t> raw, up_c, dn_c;
+  DevBuf<int> bad;
+  SQ_CHECK(raw.alloc(2 * n));
+  SQ_CHECK(up_c.alloc(n * NW));
+  SQ_CHECK(dn_c.alloc(n * NW));
+  SQ_CHECK(bad.alloc(1));
+  SQ_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  uint64_t m0 = 0, m1 = 0;  // bits that must be zero
+  if (T.norb < 64) { m0 = ~((1ull << T.norb) - 1ull); m1 = ~0ull; }
+  else if (T.norb == 64) { m0 = 0; m1 = ~0ull; }
+  else { m0 = 0; m1 = (T.norb >= 128) ? 0ull : ~((1ull << (T.norb - 64)) - 1ull); }
+  for (int which = 0; which < 2; which++) {
+    SQ_CUDA(cudaMemcpyAsync(raw.p, which == 0 ? dets_up : dets_dn, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    split_dets_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(raw.p, which == 0 ? up_c.p : dn_c.p, n, bad.p, m0, m1);
+    SQ_LAUNCH_CHECK();
+  }
+  int hbad = 0;
+  SQ_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  raw.release();
+  if (hbad) {
+    set_error("build_h: a determinant occupies an orbital beyond norb=%d", T.norb);
+    return 2;
+  }
+
+  // ---- internal (alpha-major) order
+  SQ_CUDA(cudaMalloc(&h->d_perm, n * sizeof(int32_t)));
+  SQ_CUDA(cudaMalloc(&h->d_iperm, n * sizeof(int32_t)));
+  iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, n);
+  SQ_LAUNCH_CHECK();
+  {
+    std::vector<KeyWord> words;
+    for (int w = 0; w < NW; w++) words.push_back({dn_c.p, NW, w, std::min(64, T.norb - 64 * w)});
+    for (int w = 0; w < NW; w++) words.push_back({up_c.p, NW, w, std::min(64, T.norb - 64 * w)});
+    SQ_CHECK(sort_by_words(words, h->d_perm, n, s));
+  }
+  invert_perm_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, h->d_iperm, n);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaMalloc(&h->d_up, n * NW * sizeof(uint64_t)));
+  SQ_CUDA(cudaMalloc(&h->d_dn, n * NW * sizeof(uint64_t)));
+  gather_bits_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(up_c.p, h->d_perm, h->d_up, n);
+  SQ_LAUNCH_CHECK();
+  gather_bits_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(dn_c.p, h->d_perm, h->d_dn, n);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaStreamSynchronize(s));
+  up_c.release();
+  dn_c.release();
+  h->n = n;
+
+  // ---- expanded entry list E (alpha-major)
+  const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
+  int64_t m = n;
+  DevBuf<uint64_t> Ea_buf, Eb_buf;
+  DevBuf<uint32_t> Erep_buf;
+  DevBuf<int32_t> rowE_buf;
+  const uint64_t *Ea = h->d_up, *Eb = h->d_dn;
+  SQ_CHECK(Erep_buf.alloc(1));
+  SQ_CHECK(rowE_buf.alloc(n));
+  if (ts) {
+    DevBuf<int32_t> flag, excl;
+    SQ_CHECK(flag.alloc(n));
+    SQ_CHECK(excl.alloc(n));
+    ts_flag_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(h->d_up, h->d_dn, flag.p, n);
+    SQ_LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, excl.p, (int)n, s);
+    DevBuf<char> tmp;
+    SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+    SQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, excl.p, (int)n, s));
+    g_launch_count += 2;
+    int32_t le = 0, lf = 0;
+    SQ_CUDA(cudaMemcpyAsync(&le, excl.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaMemcpyAsync(&lf, flag.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    m = n + le + lf;
+    DevBuf<uint64_t> Ua, Ub;
+    DevBuf<uint32_t> Urep;
+    SQ_CHECK(Ua.alloc(m * NW));
+    SQ_CHECK(Ub.alloc(m * NW));
+    SQ_CHECK(Urep.alloc(m));
+    ts_expand_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(h->d_up, h->d_dn, flag.p, excl.p, Ua.p, Ub.p, Urep.p, n);
+    SQ_LAUNCH_CHECK();
+    DevBuf<int32_t> idx;
+    SQ_CHECK(idx.alloc(m));
+    iota_kernel<<<nblocks(m), kThreads, 0, s>>>(idx.p, m);
+    SQ_LAUNCH_CHECK();
+    std::vector<KeyWord> words;
+    for (int w = 0; w < NW; w++) words.push_back({Ub.p, NW, w, std::min(64, T.norb - 64 * w)});
+    for (int w = 0; w < NW; w++) words.push_back({Ua.p, NW, w, std::min(64, T.norb - 64 * w)});
+    SQ_CHECK(sort_by_words(words, idx.p, m, s));
+    SQ_CHECK(Ea_buf.alloc(m * NW));
+    SQ_CHECK(Eb_buf.alloc(m * NW));
+    SQ_CHECK(Erep_buf.alloc(m));
+    gather_bits_kernel<NW><<<nblocks(m), kThreads, 0, s>>>(Ua.p, idx.p, Ea_buf.p, m);
+    SQ_LAUNCH_CHECK();
+    gather_bits_kernel<NW><<<nblocks(m), kThreads, 0, s>>>(Ub.p, idx.p, Eb_buf.p, m);
+    SQ_LAUNCH_CHECK();
+    gather_u32_kernel<<<nblocks(m), kThreads, 0, s>>>(Urep.p, idx.p, Erep_buf.p, m);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaStreamSynchronize(s));
+    Ea = Ea_buf.p;
+    Eb = Eb_buf.p;
+  } else {
+    SQ_CHECK(Erep_buf.alloc(m));
+    iota_kernel<<<nblocks(m), kThreads, 0, s>>>((int32_t *)Erep_buf.p, m);
+    SQ_LAUNCH_CHECK();
+  }
+  row_entry_kernel<<<nblocks(m), kThreads, 0, s>>>(Erep_buf.p, rowE_buf.p, m);
+  SQ_LAUNCH_CHECK();
+
+  // ---- alpha groups
+  DevBuf<int32_t> eA;
+  DevBuf<int64_t> gA_off;
+  int64_t nA = 0;
+  SQ_CHECK(make_groups<NW>(Ea, m, eA, gA_off, nA, s));
+
+  // ---- beta-major view
+  DevBuf<int32_t> bidx;
+  SQ_CHECK(bidx.alloc(m));
+  iota_kernel<<<nblocks(m), kThreads, 0, s>>>(bidx.p, m);
+  SQ_LAUNCH_CHECK();
+  {
+    std::vector<KeyWord> words;  // entries are alpha-major already: a stable sort by b gives (b, a) order
+    for (int w = 0; w < NW; w++) words.push_back({Eb, NW, w, std::min(64, T.norb - 64 * w)});
+    SQ_CHECK(sort_by_words(words, bidx.p, m, s));
+  }
+  DevBuf<uint64_t> EBa, EBb;
+  DevBuf<uint32_t> EBrep;
+  SQ_CHECK(EBa.alloc(m * NW));
+  SQ_CHECK(EBb.alloc(m * NW));
+  SQ_CHECK(EBrep.alloc(m));
+  gather_bits_kernel<NW><<<nblocks(m), kThreads, 0, s>>>(Ea, bidx.p, EBa.p, m);
+  SQ_LAUNCH_CHECK();
+  gather_bits_kernel<NW><<<nblocks(m), kThreads, 0, s>>>(Eb, bidx.p, EBb.p, m);
+  SQ_LAUNCH_CHECK();
+  gather_u32_kernel<<<nblocks(m), kThreads, 0, s>>>(Erep_buf.p, bidx.p, EBrep.p, m);
+  SQ_LAUNCH_CHECK();
+  DevBuf<int32_t> eB_sorted, eB;
+  DevBuf<int64_t> gB_off;
+  int64_t nB = 0;
+  SQ_CHECK(make_groups<NW>(EBb.p, m, eB_sorted, gB_off, nB, s));
+  SQ_CHECK(eB.alloc(m));
+  scatter_gid_kernel<<<nblocks(m), kThreads, 0, s>>>(eB_sorted.p, bidx.p, eB.p, m);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaStreamSynchronize(s));
+  EBb.release();
+  eB_sorted.release();
+  bidx.release();
+
+  // ---- (N-1)-electron keys of the unique alpha strings -> neighbour runs
+  const int nel = T.nup;  // time_sym requires nup == ndn (chemistry.f90:186)
+  int64_t m2 = nA * nel;
+  DevBuf<uint64_t> K_keys_u, K_keys;
+  DevBuf<int32_t> K_grp_u, K_grp, kidx, run_lo, run_hi;
+  SQ_CHECK(K_keys_u.alloc(std::max<int64_t>(m2, 1) * NW));
+  SQ_CHECK(K_grp_u.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(K_keys.alloc(std::max<int64_t>(m2, 1) * NW));
+  SQ_CHECK(K_grp.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(kidx.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(run_lo.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(run_hi.alloc(std::max<int64_t>(m2, 1)));
+  if (m2 > 0) {
+    nm1_keys_kernel<NW><<<nblocks(nA), kThreads, 0, s>>>(Ea, gA_off.p, nA, nel, K_keys_u.p, K_grp_u.p);
+    SQ_LAUNCH_CHECK();
+    iota_kernel<<<nblocks(m2), kThreads, 0, s>>>(kidx.p, m2);
+    SQ_LAUNCH_CHECK();
+    std::vector<KeyWord> words;
+    for (int w = 0; w < NW; w++) words.push_back({K_keys_u.p, NW, w, std::min(64, T.norb - 64 * w)});
+    SQ_CHECK(sort_by_words(words, kidx.p, m2, s));
+    gather_bits_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(K_keys_u.p, kidx.p, K_keys.p, m2);
+    SQ_LAUNCH_CHECK();
+    gather_u32_kernel<<<nblocks(m2), kThreads, 0, s>>>((const uint32_t *)K_grp_u.p, kidx.p, (uint32_t *)K_grp.p, m2);
+    SQ_LAUNCH_CHECK();
+    nm1_runs_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(Ea, gA_off.p, nA, nel, K_keys.p, m2, run_lo.p, run_hi.p);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CUDA(cudaStreamSynchronize(s));
+  K_keys_u.release();
+  K_grp_u.release();
+  kidx.release();
+  K_keys.release();
+
+  ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, run_lo.p, run_hi.p, K_grp.p, nel};
+  cudaEventRecord(ev[1], s);
+
+  // ---- P1: candidate counts.  Under sharding every rank counts an equal slice of rows,
+  // the counts are all-gathered and the final row blocks are balanced by candidate count.
+  DevBuf<int32_t> cand_count;  // all n rows (+1 spare zero for the scan)
+  SQ_CHECK(cand_count.alloc(n + 1));
+  SQ_CUDA(cudaMemsetAsync(cand_count.p, 0, (n + 1) * sizeof(int32_t), s));
+  {
+    int64_t per = div_up(n, G.nranks);
+    int64_t c0 = std::min<int64_t>(n, per * G.rank), c1 = std::min<int64_t>(n, c0 + per);
+    if (c1 > c0) {
+      connect_kernel<NW, false><<<nblocks((c1 - c0) * 32), 256, 0, s>>>(V, c0, c1, cand_count.p + c0, nullptr, nullptr);
+      SQ_LAUNCH_CHECK();
+    }
+    if (G.nranks > 1) {
+      // equal-sized padded slices so that a plain allgather works
+      DevBuf<int32_t> padded;
+      SQ_CHECK(padded.alloc(per * G.nranks));
+      SQ_CUDA(cudaMemsetAsync(padded.p, 0, per * G.nranks * sizeof(int32_t), s));
+      SQ_CUDA(cudaMemcpyAsync(padded.p + per * G.rank, cand_count.p + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+      ncclResult_t r = ncclAllGather(padded.p + per * G.rank, padded.p, per, ncclInt32, G.comm, s);
+      if (r != ncclSuccess) { set_error("ncclAllGather(counts) failed: %s", ncclGetErrorString(r)); return 3; }
+      SQ_CUDA(cudaMemcpyAsync(cand_count.p, padded.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  DevBuf<int64_t> cand_prefix;  // n+1 exclusive prefix of candidate counts over ALL rows
+  SQ_CHECK(cand_prefix.alloc(n + 1));
+  SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p, cand_prefix.p, n, s));
+  std::vector<int64_t> hprefix(n + 1);
+  SQ_CUDA(cudaMemcpy(hprefix.data(), cand_prefix.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  cand_prefix.release();
+  const int64_t Ttot = hprefix[n];
+  h->row_starts.assign(G.nranks + 1, 0);
+  for (int r = 1; r < G.nranks; r++) {
+    int64_t target = (Ttot * r) / G.nranks;
+    h->row_starts[r] = std::lower_bound(hprefix.begin(), hprefix.end(), target) - hprefix.begin();
+    if (h->row_starts[r] > n) h->row_starts[r] = n;
+    if (h->row_starts[r] < h->row_starts[r - 1]) h->row_starts[r] = h->row_starts[r - 1];
+  }
+  h->row_starts[G.nranks] = n;
+  h->row0 = h->row_starts[G.rank];
+  h->row1 = h->row_starts[G.rank + 1];
+  const int64_t nloc = h->row1 - h->row0;
+  const int64_t Tloc = hprefix[h->row1] - hprefix[h->row0];
+  cudaEventRecord(ev[2], s);
+
+  // ---- final arrays (capacity = candidate upper bound)
+  h->capacity = std::max<int64_t>(Tloc, 1);
+  SQ_CUDA(cudaMalloc(&h->d_cols, h->capacity * sizeof(int32_t)));
+  SQ_CUDA(cudaMalloc(&h->d_vals, h->capacity * sizeof(double)));
+  SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
+
+  // ---- chunks of rows bounded by temp candidates
+  const int64_t kChunkCand = 1ll << 27;
+  int64_t maxlen = 0;
+  double ms_fill = 0, ms_eval = 0;
+  int64_t base_nnz = 0;
+  DevBuf<int32_t> cand_tmp, row_nnz;
+  DevBuf<double> vals_tmp;
+  DevBuf<int64_t> cptr, rptr;
+  int64_t r = h->row0;
+  int64_t tmp_cap = 0, rows_cap = 0;
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  while (r < h->row1) {
+    int64_t r_end = r + 1;
+    {  // largest r_end with prefix[r_end]-prefix[r] <= kChunkCand
+      int64_t limit = hprefix[r] + kChunkCand;
+      r_end = std::upper_bound(hprefix.begin() + r + 1, hprefix.begin() + h->row1 + 1, limit) - hprefix.begin() - 1;
+      if (r_end <= r) r_end = r + 1;
+      if (r_end > h->row1) r_end = h->row1;
+    }
+    const int64_t nr = r_end - r, tc = hprefix[r_end] - hprefix[r];
+    if (tc > tmp_cap) {
+      tmp_cap = tc;
+      SQ_CHECK(cand_tmp.alloc(tmp_cap));
+      SQ_CHECK(vals_tmp.alloc(tmp_cap));
+    }
+    if (nr > rows_cap) {
+      rows_cap = nr;
+      SQ_CHECK(row_nnz.alloc(rows_cap + 1));
+      SQ_CHECK(cptr.alloc(rows_cap + 1));
+      SQ_CHECK(rptr.alloc(rows_cap + 1));
+    }
+    cudaEventRecord(e0, s);
+    // chunk-local candidate offsets
+    SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p + r, cptr.p, nr, s));
+    // the scan above read cand_count[r+nr] as its spare slot; offsets beyond nr are unused
+    connect_kernel<NW, true><<<nblocks(nr * 32), 256, 0, s>>>(V, r, r_end, nullptr, cptr.p, cand_tmp.p);
+    SQ_LAUNCH_CHECK();
+    sort_rows_warp_kernel<<<nblocks(nr, 8), 256, 0, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
+    SQ_LAUNCH_CHECK();
+    {
+      int64_t ml = 0;
+      for (int64_t q = r; q < r_end; q++) ml = std::max(ml, hprefix[q + 1] - hprefix[q]);
+      maxlen = std::max(maxlen, ml);
+      if (ml > kWarpSortMax) {
+        int smem = (int)std::min<int64_t>(ml, kBlockSortMax) * 4;
+        SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
+        sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
+        SQ_LAUNCH_CHECK();
+      }
+    }
+    cudaEventRecord(e1, s);
+    SQ_CUDA(cudaMemsetAsync(row_nnz.p, 0, (nr + 1) * sizeof(int32_t), s));
+    int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
+    eval_kernel<NW><<<nblocks(nr * 32), 256, c2bytes, s>>>(T, h->d_up, h->d_dn, h->d_perm, r, r_end, cptr.p, cand_count.p + r,
+                                                           cand_tmp.p, vals_tmp.p, row_nnz.p);
+    SQ_LAUNCH_CHECK();
+    SQ_CHECK(exclusive_scan_i32_to_i64(row_nnz.p, rptr.p, nr, s));
+    add_offset_kernel<<<nblocks(nr + 1), kThreads, 0, s>>>(rptr.p, nr + 1, base_nnz);
+    SQ_LAUNCH_CHECK();
+    compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaMemcpyAsync(h->d_rowptr + (r - h->row0), rptr.p, (nr + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    int64_t last = 0;
+    SQ_CUDA(cudaMemcpyAsync(&last, rptr.p + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(e2, s);
+    SQ_CUDA(cudaStreamSynchronize(s));
+    float f1 = 0, f2 = 0;
+    cudaEventElapsedTime(&f1, e0, e1);
+    cudaEventElapsedTime(&f2, e1, e2);
+    ms_fill += f1;
+    ms_eval += f2;
+    base_nnz = last;
+    r = r_end;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  if (nloc == 0) SQ_CUDA(cudaMemsetAsync(h->d_rowptr, 0, sizeof(int64_t), s));
+  h->nnz_local = base_nnz;
+  cudaEventRecord(ev[3], s);
+
+  // ---- global counts
+  int64_t tot = h->nnz_local;
+  if (G.nranks > 1) {
+    DevBuf<int64_t> t;
+    SQ_CHECK(t.alloc(1));
+    SQ_CUDA(cudaMemcpyAsync(t.p, &tot, 8, cudaMemcpyHostToDevice, s));
+    ncclResult_t rr = ncclAllReduce(t.p, t.p, 1, ncclInt64, ncclSum, G.comm, s);
+    if (rr != ncclSuccess) { set_error("ncclAllReduce(nnz) failed: %s", ncclGetErrorString(rr)); return 3; }
+    SQ_CUDA(cudaMemcpyAsync(&tot, t.p, 8, cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  h->nnz_full = tot;
+  h->nnz_upper = (tot + n) / 2;
+  h->scale = 1.0;
+
+  // ---- shrink the final arrays when the candidate bound was loose
+  if (h->capacity - h->nnz_local > (1ll << 20) && (h->capacity - h->nnz_local) * 8 > h->capacity) {
+    int32_t *nc = nullptr;
+    double *nv = nullptr;
+    int64_t cap = std::max<int64_t>(h->nnz_local, 1);
+    if (cudaMalloc(&nc, cap * sizeof(int32_t)) == cudaSuccess) {
+      if (cudaMalloc(&nv, cap * sizeof(double)) == cudaSuccess) {
+        cudaMemcpyAsync(nc, h->d_cols, h->nnz_local * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(nv, h->d_vals, h->nnz_local * sizeof(double), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        cudaFree(h->d_cols);
+        cudaFree(h->d_vals);
+        h->d_cols = nc;
+        h->d_vals = nv;
+        h->capacity = cap;
+      } else {
+        cudaFree(nc);
+        cudaGetLastError();
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  SQ_CHECK(alloc_work_vectors(h));
+  SQ_CHECK(spmv_setup_bins(h));
+  cudaEventRecord(ev[4], s);
+  SQ_CUDA(cudaStreamSynchronize(s));
+  float f;
+  cudaEventElapsedTime(&f, ev[0], ev[1]); h->build_ms[0] = f;
+  cudaEventElapsedTime(&f, ev[1], ev[2]); h->build_ms[1] = f;
+  h->build_ms[2] = ms_fill;
+  h->build_ms[3] = ms_eval;
+  cudaEventElapsedTime(&f, ev[0], ev[4]); h->build_ms[4] = f;
+  for (auto &e : ev) cudaEventDestroy(e);
+  (void)maxlen;
+  return 0;
+}
+
+int build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t ndet_old) {
+  if (n <= 0) { set_error("build_h: n must be positive"); return 2; }
+  if (n >= (1ll << 31) - 2) { set_error("build_h: n=%lld exceeds 32-bit row indices", (long long)n); return 2; }
+  if (ndet_old < 0 || ndet_old > n) { set_error("build_h: ndet_old out of range"); return 2; }
+  // incremental semantics: the result equals a from-scratch build, so rebuild.
+  free_matrix(h);
+  return h->NW == 1 ? build_impl<1>(h, n, dets_up, dets_dn) : build_impl<2>(h, n, dets_up, dets_dn);
+}
+
+int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag) {
+  cudaStream_t s = G.stream;
+  if (n <= 0) return 0;
+  DevBuf<uint64_t> raw, up, dn;
+  DevBuf<int> bad;
+  DevBuf<double> out;
+  int NW = h->NW;
+  SQ_CHECK(raw.alloc(2 * n));
+  SQ_CHECK(up.alloc(n * NW));
+  SQ_CHECK(dn.alloc(n * NW));
+  SQ_CHECK(bad.alloc(1));
+  SQ_CHECK(out.alloc(n));
+  SQ_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  for (int which = 0; which < 2; which++) {
+    SQ_CUDA(cudaMemcpyAsync(raw.p, which == 0 ? dets_up : dets_dn, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    if (NW == 1) split_dets_kernel<1><<<nblocks(n), kThreads, 0, s>>>(raw.p, which == 0 ? up.p : dn.p, n, bad.p, 0, 0);
+    else split_dets_kernel<2><<<nblocks(n), kThreads, 0, s>>>(raw.p, which == 0 ? up.p : dn.p, n, bad.p, 0, 0);
+    SQ_LAUNCH_CHECK();
+  }
+  if (NW == 1) diag_kernel<1><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p);
+  else diag_kernel<2><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaMemcpyAsync(diag, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------ export / import (compatibility paths, host side)
+int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
+  if (!h->d_rowptr) { set_error("export_upper: no matrix"); return 2; }
+  const int64_t nloc = h->row1 - h->row0;
+  std::vector<int64_t> rowptr(nloc + 1);
+  std::vector<int32_t> cols(h->nnz_local), perm(h->n);
+  std::vector<double> vals(h->nnz_local);
+  SQ_CUDA(cudaMemcpy(rowptr.data(), h->d_rowptr, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
+  SQ_CUDA(cudaMemcpy(cols.data(), h->d_cols, h->nnz_local * 4, cudaMemcpyDeviceToHost));
+  SQ_CUDA(cudaMemcpy(vals.data(), h->d_vals, h->nnz_local * 8, cudaMemcpyDeviceToHost));
+  SQ_CUDA(cudaMemcpy(perm.data(), h->d_perm, h->n * 4, cudaMemcpyDeviceToHost));
+  // caller rows owned by this rank, ascending caller index
+  std::vector<std::pair<int32_t, int64_t>> rows(nloc);
+  for (int64_t q = 0; q < nloc; q++) rows[q] = {perm[h->row0 + q], q};
+  std::sort(rows.begin(), rows.end());
+  int64_t k = 0;
+  std::vector<std::pair<int32_t, double>> tmp;
+  for (int64_t rr = 0; rr < nloc; rr++) {
+    int32_t ci = rows[rr].first;
+    int64_t q = rows[rr].second;
+    tmp.clear();
+    for (int64_t e = rowptr[q]; e < rowptr[q + 1]; e++) {
+      int32_t cj = perm[cols[e]];
+      if (cj >= ci) tmp.push_back({cj, vals[e]});
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b) { return a.first < b.first; });
+    counts[rr] = (int64_t)tmp.size();
+    for (auto &t : tmp) {
+      indices[k] = (int64_t)t.first + 1;
+      values[k] = t.second;
+      k++;
+    }
+  }
+  return 0;
+}
+
+int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values) {
+  if (G.nranks != 1) { set_error("import_upper: single-rank handles only"); return 2; }
+  free_matrix(h);
+  std::vector<int64_t> deg(n, 0);
+  int64_t k = 0, nnzu = 0;
+  for (int64_t i = 0; i < n; i++)
+    for (int64_t j = 0; j < counts[i]; j++, k++) {
+      int64_t c = indices[k] - 1;
+      if (c < 0 || c >= n) { set_error("import_upper: column out of range"); return 2; }
+      deg[i]++;
+      if (c != i) deg[c]++;
+    }
+  nnzu = k;
+  std::vector<int64_t> rowptr(n + 1, 0);
+  for (int64_t i = 0; i < n; i++) rowptr[i + 1] = rowptr[i] + deg[i];
+  std::vector<int32_t> cols(rowptr[n]);
+  std::vector<double> vals(rowptr[n]);
+  std::vector<int64_t> cur(rowptr.begin(), rowptr.end() - 1);
+  k = 0;
+  // lower part first (columns < row arrive in increasing source-row order), then the stored upper part
+  for (int64_t i = 0; i < n; i++) {
+    int64_t k0 = k;
+    for (int64_t j = 0; j < counts[i]; j++, k++) {
+      int64_t c = indices[k] - 1;
+      if (c != i) { cols[cur[c]] = (int32_t)i; vals[cur[c]] = values[k]; cur[c]++; }
+    }
+    (void)k0;
+  }
+  // rows now hold their lower entries; append upper entries (in stored order) -- but lower entries of row c
+  // were appended while scanning rows i<c only, so appending row c's own entries afterwards keeps columns ascending.
+  // Do it in a second pass to keep the code simple: rebuild per row.
+  {
+    std::vector<int64_t> lowcnt(n);
+    for (int64_t i = 0; i < n; i++) lowcnt[i] = cur[i] - rowptr[i];
+    k = 0;
+    for (int64_t i = 0; i < n; i++) {
+      int64_t w = rowptr[i] + lowcnt[i];
+      for (int64_t j = 0; j < counts[i]; j++, k++) {
+        cols[w] = (int32_t)(indices[k] - 1);
+        vals[w] = values[k];
+        w++;
+      }
+    }
+  }
+  h->n = n;
+  h->row_starts = {0, n};
+  h->row0 = 0;
+  h->row1 = n;
+  h->nnz_local = rowptr[n];
+  h->nnz_full = rowptr[n];
+  h->nnz_upper = nnzu;
+  h->capacity = std::max<int64_t>(rowptr[n], 1);
+  cudaStream_t s = G.stream;
+  SQ_CUDA(cudaMalloc(&h->d_perm, n * 4));
+  SQ_CUDA(cudaMalloc(&h->d_iperm, n * 4));
+  iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, n);
+  SQ_LAUNCH_CHECK();
+  iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_iperm, n);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaMalloc(&h->d_rowptr, (n + 1) * 8));
+  SQ_CUDA(cudaMalloc(&h->d_cols, h->capacity * 4));
+  SQ_CUDA(cudaMalloc(&h->d_vals, h->capacity * 8));
+  SQ_CUDA(cudaMemcpyAsync(h->d_rowptr, rowptr.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  SQ_CUDA(cudaMemcpyAsync(h->d_cols, cols.data(), rowptr[n] * 4, cudaMemcpyHostToDevice, s));
+  SQ_CUDA(cudaMemcpyAsync(h->d_vals, vals.data(), rowptr[n] * 8, cudaMemcpyHostToDevice, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  SQ_CHECK(alloc_work_vectors(h));
+  SQ_CHECK(spmv_setup_bins(h));
+  return 0;
+}
+
+}  // namespace sqmc
