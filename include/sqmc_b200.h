@@ -126,8 +126,9 @@ int sqmc_b200_memcpy_d2h(void *dst, const void *src_dev, int64_t bytes);
 int sqmc_b200_device_sync(void);
 /* permutation between caller order and internal order: internal row p holds caller row perm[p] (0-based) */
 int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm);
-/* timing of the phases of the last build, ms (device events): [0] sort/prep [1] count [2] fill+sort [3] eval+compact [4] total */
-int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms5);
+/* statistics of the last build: ms (device events) [0] sort/prep [1] count [2] fill+sort [3] eval+compact [4] total;
+ * [5] candidate pairs generated on this rank [6] unique alpha strings [7] unique beta strings */
+int sqmc_b200_build_times(sqmc_b200_handle *h, double *stats8);
 /* number of kernels launched by the library since init (for gpu_launches accounting) */
 int64_t sqmc_b200_launch_count(void);
 

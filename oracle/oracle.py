@@ -52,6 +52,7 @@ def lib():
         L.orc_build_upper.argtypes = [vp, i64, vp, vp, i32]
         L.orc_get_upper.argtypes = [vp, vp, vp, vp]
         L.orc_matvec_upper.argtypes = [i64, vp, vp, vp, vp, vp]
+        L.orc_matvec_upper_mt.argtypes = [i64, vp, vp, vp, vp, vp, i32]
         L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
         L.orc_hci.argtypes = [vp, vp, i32, i32, i32]
@@ -208,6 +209,16 @@ def matvec_upper(counts, idx, val, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.zeros_like(x)
     lib().orc_matvec_upper(len(counts), _p(idx), _p(counts), _p(val), _p(x), _p(y))
+    return y
+
+
+def matvec_upper_mt(counts, idx, val, x, nthreads):
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    lib().orc_matvec_upper_mt(len(counts), _p(idx), _p(counts), _p(val), _p(x), _p(y), int(nthreads))
     return y
 
 

@@ -30,6 +30,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 typedef unsigned __int128 det_t;  // integer(ik)=integer(16), types.f90:26 (values < 2^127)
@@ -1296,6 +1297,40 @@ void orc_get_upper(void *h, i8b *counts, i8b *indices, double *values) {
 }
 void orc_matvec_upper(long long n, const i8b *indices, const i8b *counts, const double *values, const double *x, double *y) {
   matvec_upper(n, indices, counts, values, x, y);
+}
+// Threaded emulation of the reference's MPI decomposition of the matvec
+// (davidson_sparse_mpi2, more_tools.f90:2640-2660 + fast_sparse_matrix_multiply_upper_triangular_mpi
+// :3674-3725): worker t owns rows t, t+T, ... (hash ownership deals rows out evenly,
+// mpi_routines.f90:419), multiplies its rows of the upper triangle into a private
+// n-long answer, and the answers are summed (the n-long MPI_ALLREDUCE of :2658).
+void orc_matvec_upper_mt(long long n, const i8b *indices, const i8b *counts, const double *values, const double *x, double *y, int nthreads) {
+  if (nthreads <= 1) { matvec_upper(n, indices, counts, values, x, y); return; }
+  std::vector<i8b> ptr(n + 1, 0);
+  for (long long i = 0; i < n; i++) ptr[i + 1] = ptr[i] + counts[i];
+  std::vector<std::vector<double>> priv(nthreads, std::vector<double>(n, 0.0));
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t]() {
+      double *a = priv[t].data();
+      for (long long i = t; i < n; i += nthreads)
+        for (i8b k = ptr[i]; k < ptr[i + 1]; k++) {
+          i8b m = indices[k] - 1;
+          a[i] = a[i] + values[k] * x[m];
+          if (i != m) a[m] = a[m] + values[k] * x[i];
+        }
+    });
+  for (auto &t : th) t.join();
+  th.clear();
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t]() {
+      long long lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+      for (long long i = lo; i < hi; i++) {
+        double s = 0.0;
+        for (int q = 0; q < nthreads; q++) s += priv[q][i];
+        y[i] = s;
+      }
+    });
+  for (auto &t : th) t.join();
 }
 // Davidson on an explicit upper-tri CSR.  ritz (capacity ritz_cap) receives the logged Ritz values; returns #logged
 int orc_davidson(long long n, int n_states, const i8b *indices, const i8b *counts, const double *values, const double *v0,

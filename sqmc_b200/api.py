@@ -126,9 +126,10 @@ class SparseHamiltonian:
         return out
 
     def build_times(self):
-        t = np.zeros(5)
+        t = np.zeros(8)
         check(self._L.sqmc_b200_build_times(self._h, _p(t)))
-        return dict(prep_ms=t[0], count_ms=t[1], fill_sort_ms=t[2], eval_compact_ms=t[3], total_ms=t[4])
+        return dict(prep_ms=t[0], count_ms=t[1], fill_sort_ms=t[2], eval_compact_ms=t[3], total_ms=t[4],
+                    candidates=int(t[5]), alpha_strings=int(t[6]), beta_strings=int(t[7]))
 
     def perm(self):
         p = np.zeros(self.n, dtype=np.int64)

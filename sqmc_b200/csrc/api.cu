@@ -293,8 +293,8 @@ int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm) {
   for (int64_t i = 0; i < h->n; i++) perm[i] = p[i];
   return 0;
 }
-int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms5) {
-  for (int i = 0; i < 5; i++) ms5[i] = h->build_ms[i];
+int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms8) {
+  for (int i = 0; i < 8; i++) ms8[i] = h->build_ms[i];
   return 0;
 }
 

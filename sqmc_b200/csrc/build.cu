@@ -886,6 +886,9 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->build_ms[2] = ms_fill;
   h->build_ms[3] = ms_eval;
   cudaEventElapsedTime(&f, ev[0], ev[4]); h->build_ms[4] = f;
+  h->build_ms[5] = (double)Tloc;
+  h->build_ms[6] = (double)nA;
+  h->build_ms[7] = (double)nB;
   for (auto &e : ev) cudaEventDestroy(e);
   (void)maxlen;
   return 0;

@@ -60,7 +60,7 @@ struct sqmc_b200_handle {
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
   double *d_tmp = nullptr; // n (caller order staging)
-  double build_ms[5] = {0, 0, 0, 0, 0};
+  double build_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [5] candidates (local) [6] alpha groups [7] beta groups
 };
 
 namespace sqmc {
