@@ -129,6 +129,11 @@ int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm);
 /* statistics of the last build: ms (device events) [0] sort/prep [1] count [2] fill+sort [3] eval+compact [4] total;
  * [5] candidate pairs generated on this rank [6] unique alpha strings [7] unique beta strings */
 int sqmc_b200_build_times(sqmc_b200_handle *h, double *stats8);
+/* Row sharding rule (pure host code, usable without a GPU): contiguous row blocks balanced by a
+ * work measure.  work_prefix: n+1 exclusive prefix sums; row_starts: nranks+1 outputs.  This is what
+ * build_h uses to shard rows of H over ranks (the reference deals dets out by hash ownership,
+ * mpi_routines.f90:419-445). */
+int sqmc_b200_partition_rows(const int64_t *work_prefix, int64_t n, int nranks, int64_t *row_starts);
 /* number of kernels launched by the library since init (for gpu_launches accounting) */
 int64_t sqmc_b200_launch_count(void);
 

@@ -293,6 +293,11 @@ int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm) {
   for (int64_t i = 0; i < h->n; i++) perm[i] = p[i];
   return 0;
 }
+int sqmc_b200_partition_rows(const int64_t *work_prefix, int64_t n, int nranks, int64_t *row_starts) {
+  if (n < 0 || nranks < 1) { set_error("partition_rows: bad arguments"); return 2; }
+  partition_rows(work_prefix, n, nranks, row_starts);
+  return 0;
+}
 int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms8) {
   for (int i = 0; i < 8; i++) ms8[i] = h->build_ms[i];
   return 0;

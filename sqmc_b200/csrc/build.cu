@@ -512,6 +512,21 @@ static int alloc_work_vectors(sqmc_b200_handle *h) {
   return 0;
 }
 
+// Contiguous row blocks balanced by work: rank r gets rows [starts[r], starts[r+1]) such that the
+// exclusive prefix `prefix` (n+1 entries, prefix[n] = total) is split as evenly as possible.
+void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *starts) {
+  const int64_t total = prefix[n];
+  starts[0] = 0;
+  for (int r = 1; r < nranks; r++) {
+    int64_t target = (total / nranks) * r + ((total % nranks) * r) / nranks;
+    int64_t pos = std::lower_bound(prefix, prefix + n + 1, target) - prefix;
+    if (pos > n) pos = n;
+    if (pos < starts[r - 1]) pos = starts[r - 1];
+    starts[r] = pos;
+  }
+  starts[nranks] = n;
+}
+
 // ------------------------------------------------------------------ the build
 template <int NW>
 static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn) {
@@ -739,13 +754,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   cand_prefix.release();
   const int64_t Ttot = hprefix[n];
   h->row_starts.assign(G.nranks + 1, 0);
-  for (int r = 1; r < G.nranks; r++) {
-    int64_t target = (Ttot * r) / G.nranks;
-    h->row_starts[r] = std::lower_bound(hprefix.begin(), hprefix.end(), target) - hprefix.begin();
-    if (h->row_starts[r] > n) h->row_starts[r] = n;
-    if (h->row_starts[r] < h->row_starts[r - 1]) h->row_starts[r] = h->row_starts[r - 1];
-  }
-  h->row_starts[G.nranks] = n;
+  partition_rows(hprefix.data(), n, G.nranks, h->row_starts.data());
   h->row0 = h->row_starts[G.rank];
   h->row1 = h->row_starts[G.rank + 1];
   const int64_t nloc = h->row1 - h->row0;

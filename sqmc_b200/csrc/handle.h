@@ -70,6 +70,7 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
 int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values);
 int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
 void free_matrix(sqmc_b200_handle *h);
+void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *starts);
 // spmv.cu
 int spmv_setup_bins(sqmc_b200_handle *h);
 int spmv_launch(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);

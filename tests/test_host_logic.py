@@ -1,0 +1,111 @@
+"""Host-side logic and the C-ABI surface (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import C2_FCIDUMP, C2_ORBSYM, ROOT, have_gpu
+
+
+def test_library_exports_every_declared_symbol():
+    from sqmc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sqmc_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sqmc_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = C.CDLL(_lib.so_path())
+    for name in declared:
+        assert hasattr(L, name), "libsqmc_b200.so does not export %s" % name
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    import sqmc_b200 as sq
+    with pytest.raises(sq.SqmcError) as e:
+        sq.SparseHamiltonian(sq.HegSystem(3, 0.5, 14, 7, 1.49))
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "sqmc_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), "%s mentions the oracle" % f
+
+
+def test_chem_setup_matches_oracle_tables(oracle):
+    import sqmc_b200 as sq
+    cs = sq.ChemSystem(C2_FCIDUMP)
+    t = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM).chem_tables()
+    assert np.array_equal(cs.integrals, t["integrals"])
+    assert np.array_equal(cs.combine_2.ravel(order="F"), t["combine_2"])
+    assert cs.enuc == t["enuc"] and cs.hf_up == t["hf_up"] and cs.hf_dn == t["hf_dn"]
+    assert np.array_equal(cs.orbital_symmetries, t["orbital_symmetries"])
+    assert cs.norb == 26 and cs.nup == 4 and cs.ndn == 4
+    assert len(cs.integrals) == 71631
+
+
+def test_all_nine_geometries_load():
+    import sqmc_b200 as sq
+    for r in ("1.0", "1.1", "1.2", "1.24253", "1.3", "1.4", "1.6", "1.8", "2.0"):
+        cs = sq.ChemSystem(os.path.join(ROOT, "data", "C2_v2z_curve", "r" + r, "FCIDUMP"))
+        assert cs.norb == 26 and sorted(cs.orb_order[:26].tolist()) == list(range(1, 27))
+
+
+def test_heg_and_hubbard_setup_match_oracle(oracle):
+    import sqmc_b200 as sq
+    for cut in (1.49, 2.0):
+        hs = sq.HegSystem(3, 0.5, 14, 7, cut)
+        ho = oracle.System.heg(3, 0.5, 14, 7, cut).heg_tables()
+        assert np.array_equal(hs.k_vectors, ho["k_vectors"]) and hs.length_cell == ho["length_cell"]
+    hu = sq.HubbardKSystem(4, 4, 1.0, 4.0, 8, 8)
+    huo = oracle.System.hubbardk(4, 4, 1.0, 4.0, 8, 8).hubbardk_tables()
+    assert np.array_equal(hu.k_vectors, huo["k_vectors"]) and np.array_equal(hu.k_energies, huo["k_energies"])
+    assert hu.ubyn == huo["ubyn"] == 0.25
+
+
+def test_c2_space_generator(oracle):
+    import sqmc_b200 as sq
+    from sqmc_b200 import spaces
+    cs = sq.ChemSystem(C2_FCIDUMP)
+    up, dn, total = spaces.c2_lowest_energy_space(cs, 5000)
+    assert total == 27944940  # A_g sector of C2 cc-pVDZ frozen core
+    assert len(up) == 5000 and up.dtype == np.uint64
+    lab = list(zip(up[:, 0].tolist(), dn[:, 0].tolist()))
+    assert lab == sorted(lab) and len(set(lab)) == 5000
+    S = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM)
+    d = S.elements(up, dn, up, dn)
+    up2, dn2, _ = spaces.c2_lowest_energy_space(cs, 6000)
+    d2 = S.elements(up2, dn2, up2, dn2)
+    assert d.max() <= np.sort(d2)[5000:].min() + 1e-9   # the 5000 chosen are the lowest
+    hf = (int(up[0, 0]), int(dn[0, 0]))
+    assert hf == (cs.hf_up, cs.hf_dn)
+    upt, dnt, tot_t = spaces.c2_lowest_energy_space(cs, 1000, time_sym=True)
+    assert tot_t == 13979945 and np.all(upt[:, 0] <= dnt[:, 0])
+
+
+def test_partition_rows_rule():
+    from sqmc_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    for n, R in ((1000, 2), (1000, 8), (7, 8), (1, 2)):
+        w = rng.integers(1, 2000, n).astype(np.int64)
+        prefix = np.zeros(n + 1, dtype=np.int64)
+        prefix[1:] = np.cumsum(w)
+        starts = np.zeros(R + 1, dtype=np.int64)
+        assert L.sqmc_b200_partition_rows(prefix.ctypes.data_as(C.c_void_p), n, R, starts.ctypes.data_as(C.c_void_p)) == 0
+        assert starts[0] == 0 and starts[-1] == n and np.all(np.diff(starts) >= 0)
+        if n >= 100 * R:
+            loads = np.array([prefix[starts[r + 1]] - prefix[starts[r]] for r in range(R)])
+            assert loads.max() - loads.min() <= 2 * w.max()
+
+
+def test_splitmix_vector_is_rank_independent():
+    from sqmc_b200 import spaces
+    x = spaces.splitmix_vector(1000)
+    assert abs(np.linalg.norm(x) - 1) < 1e-14 and np.array_equal(x, spaces.splitmix_vector(1000))
+    assert x.min() < 0 < x.max()
