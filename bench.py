@@ -110,8 +110,9 @@ def run_reference(args):
     sample = "C2 cc-pVDZ r1.24253 time_sym=f, %d lowest-energy A_g dets (nnz_full=%d); %d threads, rows dealt round-robin, private y + reduction" % (n, nnz_full, cores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 cc-pVDZ r1.24253 lowest-energy A_g determinants, time_sym=f (CPU sample of the bench workload)",
-                       "n_dets": n, "nnz_full": nnz_full},
+            "config": {"workload": "C2 cc-pVDZ r1.24253 (FCIDUMP), time_sym=f, %d lowest-diagonal-energy A_g determinants; step = one H.v"
+                                   % args.n_dets, "n_dets": args.n_dets, "sample_n_dets": n, "sample_nnz_full": nnz_full,
+                       "note": "each step is one CPU H.v on the bounded sample described in cpu_baseline.sample"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "build_nnz_upper_per_s_1core": len(idx) / t_build},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -250,7 +251,7 @@ def main():
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmv_dram_bytes_per_launch.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1 and n == 10_000_000:  # the committed ncu capture is of this exact launch
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:

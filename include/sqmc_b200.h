@@ -115,9 +115,12 @@ int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, doub
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
 
 /* ---- device-resident entry points (used by bench.py for the HBM-resident leg)
- * x_dev/y_dev are device pointers in the library's INTERNAL row order
- * (length = n for x, n_local_rows for y).  stream is a cudaStream_t (0 = default). */
-int sqmc_b200_matvec_dev(sqmc_b200_handle *h, const double *x_dev, double *y_dev, void *stream);
+ * x_dev/y_dev are device pointers in the library's INTERNAL row order (length n for x,
+ * n_local_rows for y).  Under nranks>1 only this rank's row block of x_dev needs to be valid on
+ * entry: the call first all-gathers the owners' blocks in place over NCCL (what Davidson does with
+ * every new basis vector; the reference: zero-padded MPI_ALLREDUCE, more_tools.f90:2647), then
+ * multiplies.  stream is a cudaStream_t (NULL = the library's own stream). */
+int sqmc_b200_matvec_dev(sqmc_b200_handle *h, double *x_dev, double *y_dev, void *stream);
 /* average device time (ms) of the last sqmc_b200_matvec_dev launches is measured by the caller with events */
 int sqmc_b200_device_malloc(void **p, int64_t bytes);
 int sqmc_b200_device_free(void *p);

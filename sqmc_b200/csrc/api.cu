@@ -259,9 +259,12 @@ int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, doub
   return davidson(h, n_states, v0, evecs, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged);
 }
 
-int sqmc_b200_matvec_dev(sqmc_b200_handle *h, const double *x_dev, double *y_dev, void *stream) {
+int sqmc_b200_matvec_dev(sqmc_b200_handle *h, double *x_dev, double *y_dev, void *stream) {
   SQ_CHECK(require_init());
-  return spmv_launch(h, x_dev, y_dev, stream ? (cudaStream_t)stream : G.stream);
+  if (!h || !h->d_rowptr) { set_error("matvec_dev: no matrix on this handle"); return 2; }
+  cudaStream_t s = stream ? (cudaStream_t)stream : G.stream;
+  SQ_CHECK(allgather_rows(h, x_dev, s));  // no-op on one rank
+  return spmv_launch(h, x_dev, y_dev, s);
 }
 int sqmc_b200_device_malloc(void **p, int64_t bytes) {
   SQ_CHECK(require_init());

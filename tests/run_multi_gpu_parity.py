@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Row-sharded path on N GPUs (launched with torchrun): build, export, H.v, Davidson and projector
+against the CPU oracle.  Used by tests/test_gpu_multi.py and by hand:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_multi_gpu_parity.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import sqmc_b200 as sq
+    from sqmc_b200 import _lib
+    from conftest import C2_FCIDUMP, C2_ORBSYM
+    from oracle import oracle as O
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    obj = [_lib.get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    _lib.init(device=local, rank=rank, nranks=world, unique_id=obj[0])
+    for time_sym in (False, True):
+        S = O.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=time_sym, z=1, hf_symmetry=1)
+        r = S.hci(1e-3, eps_var_sched=[2e-3, 2e-3], n_states=1, max_iters=3)
+        cnt, idx, val = S.build_upper(r["up"], r["dn"])
+        n = len(cnt)
+        H = sq.SparseHamiltonian(sq.ChemSystem(C2_FCIDUMP, time_sym=time_sym, z=1), device=local)
+        nnz = H.generate_sparse_ham_upper_triangular(r["up"], r["dn"])
+        assert nnz == len(idx), (nnz, len(idx))
+        nloc, nnz_loc = H.local_rows()
+        tot = torch.tensor([nloc, nnz_loc], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        assert tot[0].item() == n and tot[1].item() == 2 * nnz - n
+        # export: this rank's rows (ascending caller index) against the oracle's rows
+        perm = H.perm()
+        gc, gi, gv = H.export_upper()
+        # rows owned: internal rows [row0,row1) -> need row0: all-gather nloc
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([nloc], dtype=torch.int64, device="cuda"))
+        row0 = int(sum(s.item() for s in sizes[:rank]))
+        mine = np.sort(perm[row0:row0 + nloc])
+        ptr = np.zeros(n + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(cnt)
+        assert np.array_equal(gc, cnt[mine])
+        ri = np.concatenate([idx[ptr[i]:ptr[i + 1]] for i in mine]) if len(mine) else np.zeros(0, dtype=np.int64)
+        rv = np.concatenate([val[ptr[i]:ptr[i + 1]] for i in mine]) if len(mine) else np.zeros(0)
+        assert np.array_equal(gi, ri) and np.array_equal(gv, rv)
+        x = np.random.default_rng(12345).uniform(-1, 1, n)
+        y = H.matvec(x)
+        yref = O.matvec_upper(cnt, idx, val, x)
+        assert np.max(np.abs(y - yref)) <= 1e-12 * np.max(np.abs(yref))
+        ref = O.davidson(cnt, idx, val, n_states=1)
+        got = H.davidson_sparse(n_states=1)
+        assert got["ritz"].shape == ref["ritz"].shape and np.max(np.abs(got["ritz"] - ref["ritz"])) < 1e-8
+        assert abs(abs(np.dot(got["evecs"][:, 0], ref["evecs"][:, 0])) - 1) < 1e-6
+        tau, e_trial = 0.01, float(val[0])
+        H.scale_values(-tau)
+        w = x / np.linalg.norm(x)
+        dw = H.projector_step(tau, e_trial, w)
+        _, dwr = O.projector_step(cnt, idx, -tau * val, tau, e_trial, w)
+        assert np.max(np.abs(dw - dwr)) <= 1e-12 * np.max(np.abs(dwr)) + 1e-15
+        if rank == 0:
+            print("multi-gpu parity ok: world=%d time_sym=%s n=%d nnz=%d E=%.10f" % (world, time_sym, n, nnz, got["evals"][0]))
+        H.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
