@@ -86,6 +86,10 @@ int sqmc_b200_import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *H_nonz
                            const double *H_values);
 int sqmc_b200_nnz(sqmc_b200_handle *h, int64_t *n, int64_t *nnz_upper, int64_t *nnz_full);
 int sqmc_b200_local_rows(sqmc_b200_handle *h, int64_t *n_local_rows, int64_t *nnz_full_local);
+/* One FULL row (both triangles) of the resident matrix in the caller's numbering: 1-based row in,
+ * 1-based ascending columns out.  len = -1 when another rank owns the row.  Inspection / test aid
+ * (the reference can only do this by scanning its upper-triangular arrays). */
+int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int64_t *cols, double *vals, int64_t *len);
 /* diagonal elements H_ii for a det list (hci.f90:664-676 "quick hack" loops) */
 int sqmc_b200_diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag);
 

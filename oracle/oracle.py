@@ -48,6 +48,8 @@ def lib():
         L.orc_get_heg.argtypes = [vp] * 4
         L.orc_get_hubbardk.argtypes = [vp] * 4
         L.orc_elements.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.orc_row.restype = i64
+        L.orc_row.argtypes = [vp, i64, vp, vp, i64, i64, vp, vp]
         L.orc_build_upper.restype = i64
         L.orc_build_upper.argtypes = [vp, i64, vp, vp, i32]
         L.orc_get_upper.argtypes = [vp, vp, vp, vp]
@@ -161,6 +163,16 @@ class System:
         out = np.zeros(len(iu))
         lib().orc_elements(self.h, len(iu), _p(iu), _p(id_), _p(ju), _p(jd), _p(out))
         return out
+
+    def row(self, up, dn, i, cap=1 << 16):
+        """brute-force full row i (0-based) -> (cols 1-based ascending, vals)"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        cols = np.zeros(cap, dtype=np.int64)
+        vals = np.zeros(cap)
+        k = lib().orc_row(self.h, len(up), _p(up), _p(dn), int(i), cap, _p(cols), _p(vals))
+        assert k <= cap
+        return cols[:k].copy(), vals[:k].copy()
 
     def build_upper(self, up, dn, incremental=False):
         """-> (counts int64[n], indices int64[nnz] 1-based, values f64[nnz]) : reference layout."""

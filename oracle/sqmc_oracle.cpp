@@ -1282,6 +1282,24 @@ void orc_elements(void *h, long long n, const det_t *iu, const det_t *id, const 
 }
 int orc_excitation_level(const det_t *iu, const det_t *id, const det_t *ju, const det_t *jd) { return excitation_level(*iu, *id, *ju, *jd); }
 
+// Brute-force FULL row i (0-based) of H over a det list: every j with abs(H)>1e-12 (diagonal always),
+// element evaluated with the lower index as bra (= what the reference stores in its upper triangle).
+// O(n) element tests per row; used by the full-size GPU tests to check pattern completeness.
+long long orc_row(void *h, long long n, const det_t *up, const det_t *dn, long long i, long long cap, i8b *cols, double *vals) {
+  System *S = (System *)h;
+  long long k = 0;
+  for (long long j = 0; j < n; j++) {
+    double e;
+    if (j == i) e = hamiltonian(*S, up[i], dn[i], up[i], dn[i]);
+    else if (i < j) e = hamiltonian(*S, up[i], dn[i], up[j], dn[j]);
+    else e = hamiltonian(*S, up[j], dn[j], up[i], dn[i]);
+    if (j == i || std::fabs(e) > 1.e-12) {
+      if (k < cap) { cols[k] = j + 1; vals[k] = e; }
+      k++;
+    }
+  }
+  return k;
+}
 // build (incremental when ndet_old == rows already stored in the handle); returns stored nnz
 long long orc_build_upper(void *h, long long n, const det_t *up, const det_t *dn, int incremental) {
   System *S = (System *)h;

@@ -18,7 +18,7 @@ SYMBOLS = [
     "sqmc_b200_local_rows", "sqmc_b200_diagonal", "sqmc_b200_matvec", "sqmc_b200_projector",
     "sqmc_b200_scale_values", "sqmc_b200_davidson", "sqmc_b200_matvec_dev", "sqmc_b200_device_malloc",
     "sqmc_b200_device_free", "sqmc_b200_memcpy_h2d", "sqmc_b200_memcpy_d2h", "sqmc_b200_device_sync",
-    "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows",
+    "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row",
 ]
 
 
@@ -64,6 +64,7 @@ def load():
     L.sqmc_b200_get_perm.argtypes = [vp, vp]
     L.sqmc_b200_build_times.argtypes = [vp, vp]
     L.sqmc_b200_partition_rows.argtypes = [vp, i64, i32, vp]
+    L.sqmc_b200_get_row.argtypes = [vp, i64, i64, vp, vp, vp]
     _lib = L
     return L
 

@@ -119,6 +119,16 @@ class SparseHamiltonian:
         tot = int(cnt.sum())
         return cnt, idx[:tot], val[:tot]
 
+    def get_row(self, caller_row, cap=1 << 16):
+        """full row `caller_row` (1-based): (columns 1-based ascending, values); None if another rank owns it."""
+        cols = np.zeros(cap, dtype=np.int64)
+        vals = np.zeros(cap)
+        ln = C.c_int64()
+        check(self._L.sqmc_b200_get_row(self._h, int(caller_row), cap, _p(cols), _p(vals), C.byref(ln)))
+        if ln.value < 0:
+            return None
+        return cols[:ln.value].copy(), vals[:ln.value].copy()
+
     def diagonal(self, dets_up, dets_dn):
         up, dn = dets_to_u64(dets_up), dets_to_u64(dets_dn)
         out = np.zeros(len(up))

@@ -1,7 +1,10 @@
 // api.cu -- the C ABI of libsqmc_b200.so (include/sqmc_b200.h): handle management,
 // device / NCCL set-up and the host-pointer entry points (H2D / D2H inside the call).
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/sqmc_b200.h"
 #include "handle.h"
@@ -294,6 +297,32 @@ int sqmc_b200_get_perm(sqmc_b200_handle *h, int64_t *perm) {
   std::vector<int32_t> p(h->n);
   SQ_CUDA(cudaMemcpy(p.data(), h->d_perm, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < h->n; i++) perm[i] = p[i];
+  return 0;
+}
+int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int64_t *cols, double *vals, int64_t *len) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("get_row: no matrix on this handle"); return 2; }
+  if (caller_row < 1 || caller_row > h->n) { set_error("get_row: row out of range"); return 2; }
+  int32_t p = 0;
+  SQ_CUDA(cudaMemcpy(&p, h->d_iperm + (caller_row - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (p < h->row0 || p >= h->row1) { *len = -1; return 0; }  // another rank owns this row
+  int64_t rp[2];
+  SQ_CUDA(cudaMemcpy(rp, h->d_rowptr + (p - h->row0), 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  int64_t L = rp[1] - rp[0];
+  *len = L;
+  if (L > cap) { set_error("get_row: row has %lld entries, capacity %lld", (long long)L, (long long)cap); return 2; }
+  std::vector<int32_t> c(L), pc(L);
+  std::vector<double> v(L);
+  SQ_CUDA(cudaMemcpy(c.data(), h->d_cols + rp[0], L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  SQ_CUDA(cudaMemcpy(v.data(), h->d_vals + rp[0], L * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<int64_t, double>> e(L);
+  for (int64_t k = 0; k < L; k++) {
+    int32_t cj = 0;
+    SQ_CUDA(cudaMemcpy(&cj, h->d_perm + c[k], sizeof(int32_t), cudaMemcpyDeviceToHost));
+    e[k] = {(int64_t)cj + 1, v[k]};
+  }
+  std::sort(e.begin(), e.end(), [](const std::pair<int64_t, double> &a, const std::pair<int64_t, double> &b) { return a.first < b.first; });
+  for (int64_t k = 0; k < L; k++) { cols[k] = e[k].first; vals[k] = e[k].second; }
   return 0;
 }
 int sqmc_b200_partition_rows(const int64_t *work_prefix, int64_t n, int nranks, int64_t *row_starts) {

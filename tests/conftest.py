@@ -52,3 +52,11 @@ def c2_space(oracle):
     s = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=False, z=1, hf_symmetry=1)
     r = s.hci(1e-3, eps_var_sched=[2e-3, 2e-3], n_states=1, max_iters=3)
     return s, r
+
+
+@pytest.fixture(scope="session")
+def c2_hci_full(oracle):
+    """the complete oracle HCI run on the shipped C2 input (time_sym=t, n_states=1): final det list + per-iteration log"""
+    s = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=True, z=1, hf_symmetry=1)
+    r = s.hci(1e-3, eps_var_sched=[2e-3, 2e-3], n_states=1)
+    return s, r
