@@ -251,6 +251,7 @@ int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio) {
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("scale_values: no matrix on this handle"); return 2; }
   SQ_CHECK(scale_array(h->d_vals, h->nnz_local, ratio, G.stream));
+  if (h->d_diag) SQ_CHECK(scale_array(h->d_diag, h->row1 - h->row0, ratio, G.stream));
   SQ_CUDA(cudaStreamSynchronize(G.stream));
   h->scale *= ratio;
   return 0;
@@ -306,15 +307,23 @@ int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int6
   int32_t p = 0;
   SQ_CUDA(cudaMemcpy(&p, h->d_iperm + (caller_row - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (p < h->row0 || p >= h->row1) { *len = -1; return 0; }  // another rank owns this row
-  int64_t rp[2];
-  SQ_CUDA(cudaMemcpy(rp, h->d_rowptr + (p - h->row0), 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
-  int64_t L = rp[1] - rp[0];
+  std::vector<int32_t> c;
+  std::vector<double> v;
+  int64_t L = 0;
+  if (h->wcsr) {
+    SQ_CHECK(wcsr_get_row(h, p, c, v));
+    L = (int64_t)c.size();
+  } else {
+    int64_t rp[2];
+    SQ_CUDA(cudaMemcpy(rp, h->d_rowptr + (p - h->row0), 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    L = rp[1] - rp[0];
+    c.resize(L);
+    v.resize(L);
+    SQ_CUDA(cudaMemcpy(c.data(), h->d_cols + rp[0], L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(v.data(), h->d_vals + rp[0], L * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   *len = L;
   if (L > cap) { set_error("get_row: row has %lld entries, capacity %lld", (long long)L, (long long)cap); return 2; }
-  std::vector<int32_t> c(L), pc(L);
-  std::vector<double> v(L);
-  SQ_CUDA(cudaMemcpy(c.data(), h->d_cols + rp[0], L * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  SQ_CUDA(cudaMemcpy(v.data(), h->d_vals + rp[0], L * sizeof(double), cudaMemcpyDeviceToHost));
   std::vector<std::pair<int64_t, double>> e(L);
   for (int64_t k = 0; k < L; k++) {
     int32_t cj = 0;

@@ -35,36 +35,6 @@
 namespace sqmc {
 
 // ------------------------------------------------------------------ helpers
-template <typename T>
-struct DevBuf {
-  T *p = nullptr;
-  int64_t n = 0;
-  int alloc(int64_t count) {
-    release();
-    n = count;
-    if (count <= 0) return 0;
-    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
-    if (e != cudaSuccess) {
-      set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
-      p = nullptr;
-      return 1;
-    }
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-  T *take() {
-    T *q = p;
-    p = nullptr;
-    n = 0;
-    return q;
-  }
-  ~DevBuf() { release(); }
-};
-
 static const int kThreads = 256;
 static inline int nblocks(int64_t n, int t = kThreads) { return (int)std::min<int64_t>(div_up(n, t), 0x7fffffff); }
 
@@ -501,6 +471,9 @@ void free_matrix(sqmc_b200_handle *h) {
   };
   F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
   F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp);
+  F(h->d_gA_off); F(h->d_eA); F(h->d_gB_off); F(h->d_eBpos); F(h->d_bidx); F(h->d_binv);
+  wcsr_free(h);
+  h->nA = h->nB = 0;
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
   h->row_starts.clear();
 }
@@ -683,6 +656,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_LAUNCH_CHECK();
   SQ_CUDA(cudaStreamSynchronize(s));
   EBb.release();
+  DevBuf<int32_t> eB_sorted_keep, bidx_keep;
+  if (!ts) {  // keep the beta-major view for the WCSR layout (entries == rows when there is no time-reversal expansion)
+    eB_sorted_keep.p = eB_sorted.take();
+    bidx_keep.p = bidx.take();
+  }
   eB_sorted.release();
   bidx.release();
 
@@ -885,8 +863,21 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       cudaGetLastError();
     }
   }
+  if (!ts) {
+    h->nA = nA;
+    h->nB = nB;
+    h->d_gA_off = gA_off.take();
+    h->d_eA = eA.take();
+    h->d_gB_off = gB_off.take();
+    h->d_eBpos = eB_sorted_keep.take();
+    h->d_bidx = bidx_keep.take();
+    SQ_CUDA(cudaMalloc(&h->d_binv, n * sizeof(int32_t)));
+    invert_perm_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_bidx, h->d_binv, n);
+    SQ_LAUNCH_CHECK();
+  }
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
+  SQ_CHECK(wcsr_convert(h));
   cudaEventRecord(ev[4], s);
   SQ_CUDA(cudaStreamSynchronize(s));
   float f;
@@ -944,11 +935,17 @@ int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double 
   if (!h->d_rowptr) { set_error("export_upper: no matrix"); return 2; }
   const int64_t nloc = h->row1 - h->row0;
   std::vector<int64_t> rowptr(nloc + 1);
-  std::vector<int32_t> cols(h->nnz_local), perm(h->n);
-  std::vector<double> vals(h->nnz_local);
-  SQ_CUDA(cudaMemcpy(rowptr.data(), h->d_rowptr, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
-  SQ_CUDA(cudaMemcpy(cols.data(), h->d_cols, h->nnz_local * 4, cudaMemcpyDeviceToHost));
-  SQ_CUDA(cudaMemcpy(vals.data(), h->d_vals, h->nnz_local * 8, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> cols, perm(h->n);
+  std::vector<double> vals;
+  if (h->wcsr) {
+    SQ_CHECK(wcsr_decode_host(h, rowptr, cols, vals));
+  } else {
+    cols.resize(h->nnz_local);
+    vals.resize(h->nnz_local);
+    SQ_CUDA(cudaMemcpy(rowptr.data(), h->d_rowptr, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(cols.data(), h->d_cols, h->nnz_local * 4, cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(vals.data(), h->d_vals, h->nnz_local * 8, cudaMemcpyDeviceToHost));
+  }
   SQ_CUDA(cudaMemcpy(perm.data(), h->d_perm, h->n * 4, cudaMemcpyDeviceToHost));
   // caller rows owned by this rank, ascending caller index
   std::vector<std::pair<int32_t, int64_t>> rows(nloc);

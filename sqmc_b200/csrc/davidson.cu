@@ -88,23 +88,6 @@ __global__ void combine_kernel(const double *__restrict__ V, int64_t ld, int dim
     out[(int64_t)s * ld + j] = acc;
   }
 }
-// diag[q] = H(row0+q,row0+q): columns of a row are ascending -> binary search
-__global__ void extract_diag_kernel(const int64_t *rowptr, const int32_t *cols, const double *vals, int64_t row0, int64_t nloc, double *diag) {
-  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (q >= nloc) return;
-  int64_t lo = rowptr[q], hi = rowptr[q + 1];
-  int32_t target = (int32_t)(row0 + q);
-  double d = 0.0;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    int32_t c = cols[mid];
-    if (c == target) { d = vals[mid]; break; }
-    if (c < target) lo = mid + 1;
-    else hi = mid;
-  }
-  diag[q] = d;
-}
-
 static void jacobi_eigh(int n, std::vector<double> a, std::vector<double> &evals, std::vector<double> &evecs) {
   // cyclic Jacobi, column-major; eigenvalues ascending, eigenvectors in columns
   evecs.assign((size_t)n * n, 0.0);
@@ -283,15 +266,12 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     double d = 0;
     SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
     evals[0] = d;
-    evecs[0] = 0.0;
+    evecs[0] = 1.0;
     if (n_matvec_out) *n_matvec_out = 0;
     if (n_ritz_logged) *n_ritz_logged = 0;
     return 0;
   }
-  if (nloc > 0) {
-    extract_diag_kernel<<<D.blocks(nloc), 256, 0, s>>>(h->d_rowptr, h->d_cols, h->d_vals, h->row0, nloc, D.diag);
-    SQ_LAUNCH_CHECK();
-  }
+  SQ_CHECK(extract_diag(h, D.diag, s));
   for (int i = 0; i < n_states; i++) SQ_CHECK(D.apply_h(Vc(i), HVc(i)));
   for (int j = 0; j < n_states; j++) {
     SQ_CHECK(D.dots(D.V, n_states, HVc(j), D.scal));

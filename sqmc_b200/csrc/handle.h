@@ -19,9 +19,65 @@ struct Global {
 };
 extern Global G;
 
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  int64_t n = 0;
+  int alloc(int64_t count) {
+    release();
+    n = count;
+    if (count <= 0) return 0;
+    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+      p = nullptr;
+      return 1;
+    }
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  T *take() {
+    T *q = p;
+    p = nullptr;
+    n = 0;
+    return q;
+  }
+  ~DevBuf() { release(); }
+};
+
 // number of degree bins for the SpMV (sub-warp vector sizes 2,4,8,16,32 + CTA-per-row)
 static const int kNumBins = 6;
 
+}  // namespace sqmc
+
+namespace sqmc {
+// One part of the window-staged layout ("WCSR", csrc/wcsr.cu): rows cut into tiles of <= kTileRows rows of
+// one row group; inside a tile the entries are ordered (column window, row, column) and stored as
+// packed (row_local << 16 | col_local) + f64 value; a window is (a piece of) one column group whose
+// slice of x is staged in shared memory by a bulk async copy.
+struct WPart {
+  int64_t nrows = 0, ntiles = 0, nwin = 0, ent0 = 0, nnz = 0;
+  int32_t *tile_row0 = nullptr;   // [ntiles] first row (part-local numbering)
+  int32_t *tile_nrows = nullptr;  // [ntiles]
+  int64_t *tile_ent0 = nullptr;   // [ntiles+1] first entry of the tile, relative to ent0
+  int64_t *tile_win0 = nullptr;   // [ntiles+1] first window record of the tile
+  int32_t *win_col0 = nullptr;    // [nwin] first staged column (even)
+  int32_t *win_len = nullptr;     // [nwin] staged columns (even)
+  int32_t *win_slab = nullptr;    // [nwin][kSlabs+1] entry offsets of the row slabs, relative to the tile's first entry
+  int64_t *rowptr = nullptr;      // [nrows+1] CSR offsets before conversion (kept for decoding), relative to ent0
+  int32_t *colwin = nullptr;      // [ncols] column -> global window id (conversion only)
+  int32_t *gwin_col0 = nullptr, *gwin_len = nullptr;  // global window table
+  int64_t ngwin = 0;
+};
+static const int kTileRows = 256;
+static const int kSlabs = 16;          // warps per CTA of the WCSR kernel; slab = kTileRows / kSlabs rows
+static const int kWinMax = 2048;       // max columns per staged window
+static const int kMaxWinPerTile = 160; // conversion keeps a [windows][rows] count matrix in shared memory
 }  // namespace sqmc
 
 struct sqmc_b200_handle {
@@ -56,6 +112,23 @@ struct sqmc_b200_handle {
   int32_t *d_bin_rows = nullptr;  // concatenated lists
   int64_t bin_off[sqmc::kNumBins + 1] = {0};
 
+  // ---- group structure of the determinant list (kept for the WCSR layout; non-time-sym builds only) ----
+  int64_t nA = 0, nB = 0;
+  int64_t *d_gA_off = nullptr;   // [nA+1] alpha-group offsets (internal rows)
+  int32_t *d_eA = nullptr;       // [n] internal row -> alpha group
+  int64_t *d_gB_off = nullptr;   // [nB+1] beta-group offsets (beta-major positions)
+  int32_t *d_eBpos = nullptr;    // [n] beta-major position -> beta group
+  int32_t *d_bidx = nullptr;     // [n] beta-major position -> internal row
+  int32_t *d_binv = nullptr;     // [n] internal row -> beta-major position
+  // ---- WCSR layout (active when wcsr == true; then d_cols holds packed indices) ----
+  bool wcsr = false;
+  sqmc::WPart WA, WB;
+  int32_t *d_browL = nullptr;      // [nloc] local beta-major row -> internal row
+  int32_t *d_browL_inv = nullptr;  // [nloc] (internal row - row0) -> local beta-major row
+  double *d_diag = nullptr;        // [nloc] diagonal of the local rows
+  double *d_xb = nullptr;          // [n] x in beta-major order
+  double *d_yb = nullptr;          // [nloc] partial y of the same-beta part, local beta-major order
+
   // ---- work buffers ----
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
@@ -79,6 +152,13 @@ int permute_scatter(const double *src, const int32_t *idx, double *dst, int64_t 
 int scale_array(double *a, int64_t n, double r, cudaStream_t s);
 int projector_epilogue(double *deltaw, const double *w, double c, int64_t n, cudaStream_t s);  // deltaw += c*w
 int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-place allgather of row blocks
+// wcsr.cu
+int wcsr_convert(sqmc_b200_handle *h);      // CSR -> WCSR in place when the space is dense enough (or SQMC_WCSR=1)
+int wcsr_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
+int wcsr_decode_host(sqmc_b200_handle *h, std::vector<int64_t> &rowptr, std::vector<int32_t> &cols, std::vector<double> &vals);
+void wcsr_free(sqmc_b200_handle *h);
+int wcsr_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
+int extract_diag(sqmc_b200_handle *h, double *diag_dev, cudaStream_t s);
 // davidson.cu
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
              int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);

@@ -163,6 +163,7 @@ static int launch_vec(sqmc_b200_handle *h, int bin, const double *x, double *y, 
 // y_dev: local rows (row1-row0), x_dev: global length n, both internal order
 int spmv_launch(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
+  if (h->wcsr) return wcsr_spmv(h, x, y, s);
   SQ_CHECK(launch_vec<2>(h, 0, x, y, s));
   SQ_CHECK(launch_vec<4>(h, 1, x, y, s));
   SQ_CHECK(launch_vec<8>(h, 2, x, y, s));
