@@ -36,6 +36,7 @@ namespace sqmc {
 
 // ------------------------------------------------------------------ helpers
 static const int kThreads = 256;
+static const int64_t kSlack = 1024;
 static inline int nblocks(int64_t n, int t = kThreads) { return (int)std::min<int64_t>(div_up(n, t), 0x7fffffff); }
 
 // 16-byte caller dets -> NW-word strings
@@ -741,8 +742,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
 
   // ---- final arrays (capacity = candidate upper bound)
   h->capacity = std::max<int64_t>(Tloc, 1);
-  SQ_CUDA(cudaMalloc(&h->d_cols, h->capacity * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_vals, h->capacity * sizeof(double)));
+  // + kSlack entries: the WCSR kernel's masked 128-bit loads may touch up to 2 steps past the last entry
+  SQ_CUDA(cudaMalloc(&h->d_cols, (h->capacity + kSlack) * sizeof(int32_t)));
+  SQ_CUDA(cudaMalloc(&h->d_vals, (h->capacity + kSlack) * sizeof(double)));
+  SQ_CUDA(cudaMemsetAsync(h->d_cols + h->capacity, 0, kSlack * sizeof(int32_t), s));
+  SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
   SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
 
   // ---- chunks of rows bounded by temp candidates
@@ -845,8 +849,10 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     int32_t *nc = nullptr;
     double *nv = nullptr;
     int64_t cap = std::max<int64_t>(h->nnz_local, 1);
-    if (cudaMalloc(&nc, cap * sizeof(int32_t)) == cudaSuccess) {
-      if (cudaMalloc(&nv, cap * sizeof(double)) == cudaSuccess) {
+    if (cudaMalloc(&nc, (cap + kSlack) * sizeof(int32_t)) == cudaSuccess) {
+      if (cudaMalloc(&nv, (cap + kSlack) * sizeof(double)) == cudaSuccess) {
+        cudaMemsetAsync(nc + cap, 0, kSlack * sizeof(int32_t), s);
+        cudaMemsetAsync(nv + cap, 0, kSlack * sizeof(double), s);
         cudaMemcpyAsync(nc, h->d_cols, h->nnz_local * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(nv, h->d_vals, h->nnz_local * sizeof(double), cudaMemcpyDeviceToDevice, s);
         cudaStreamSynchronize(s);

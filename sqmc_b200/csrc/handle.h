@@ -58,26 +58,29 @@ static const int kNumBins = 6;
 namespace sqmc {
 // One part of the window-staged layout ("WCSR", csrc/wcsr.cu): rows cut into tiles of <= kTileRows rows of
 // one row group; inside a tile the entries are ordered (column window, row, column) and stored as
-// packed (row_local << 16 | col_local) + f64 value; a window is (a piece of) one column group whose
-// slice of x is staged in shared memory by a bulk async copy.
+// packed (row_local << 16 | col_local) + f64 value; a window is a piece (<= kWinMax columns) of one
+// column group whose slice of x is staged in shared memory by a bulk async copy.  Work items are
+// (window, <= kItemMax consecutive entries); one warp consumes an item.
+struct WItem {
+  int32_t col0, len;  // staged columns [col0, col0+len), col0 and len even
+  int32_t k0, k1;     // entries [k0, k1) relative to the tile's first entry
+};
 struct WPart {
-  int64_t nrows = 0, ntiles = 0, nwin = 0, ent0 = 0, nnz = 0;
+  int64_t nrows = 0, ntiles = 0, nitems = 0, ent0 = 0, nnz = 0;
   int32_t *tile_row0 = nullptr;   // [ntiles] first row (part-local numbering)
   int32_t *tile_nrows = nullptr;  // [ntiles]
   int64_t *tile_ent0 = nullptr;   // [ntiles+1] first entry of the tile, relative to ent0
-  int64_t *tile_win0 = nullptr;   // [ntiles+1] first window record of the tile
-  int32_t *win_col0 = nullptr;    // [nwin] first staged column (even)
-  int32_t *win_len = nullptr;     // [nwin] staged columns (even)
-  int32_t *win_slab = nullptr;    // [nwin][kSlabs+1] entry offsets of the row slabs, relative to the tile's first entry
-  int64_t *rowptr = nullptr;      // [nrows+1] CSR offsets before conversion (kept for decoding), relative to ent0
+  int64_t *tile_item0 = nullptr;  // [ntiles+1] first work item of the tile
+  WItem *items = nullptr;         // [nitems]
+  int64_t *rowptr = nullptr;      // [nrows+1] CSR offsets before conversion, relative to ent0 (conversion only)
   int32_t *colwin = nullptr;      // [ncols] column -> global window id (conversion only)
-  int32_t *gwin_col0 = nullptr, *gwin_len = nullptr;  // global window table
+  int32_t *gwin_col0 = nullptr, *gwin_len = nullptr;  // global window table (conversion only)
   int64_t ngwin = 0;
 };
 static const int kTileRows = 256;
-static const int kSlabs = 16;          // warps per CTA of the WCSR kernel; slab = kTileRows / kSlabs rows
-static const int kWinMax = 2048;       // max columns per staged window
-static const int kMaxWinPerTile = 160; // conversion keeps a [windows][rows] count matrix in shared memory
+static const int kWWarps = 16;     // warps per CTA of the WCSR kernel
+static const int kWinMax = 512;    // max columns per staged window (4 KB of x)
+static const int kItemMax = 2048;  // max entries per work item
 }  // namespace sqmc
 
 struct sqmc_b200_handle {

@@ -11,11 +11,14 @@
 // So H is split into part A (alpha-major rows, columns in own + neighbour alpha-groups) and part B
 // (beta-major rows, columns in the own beta-group).  Each part is cut into tiles of <= 256 rows of one
 // row group; the entries of a tile are stored window-major -- (column window, row, column) -- as
-// packed (row_local << 16 | col_local) + f64: still 12 bytes per entry.  One CTA owns a tile: the x
-// slice of the next window is brought into shared memory by a bulk async copy (cp.async.bulk +
-// mbarrier) while the current window is consumed with shared-memory gathers; each of the 16 warps owns
-// a slab of 16 rows, does a shuffle segmented reduction and accumulates into shared-memory row sums
-// (one writer per row: deterministic).  y = A x + P^T B (P x), P = alpha-major -> beta-major.
+// packed (row_local << 16 | col_local) + f64: still 12 bytes per entry.  One CTA owns a tile; its 16
+// warps each consume work items (one window piece, <= 2048 consecutive entries): the warp brings the
+// x slice of its NEXT item into its private shared-memory buffer with a bulk async copy
+// (cp.async.bulk + mbarrier, double buffered) while it streams the current item with unrolled
+// evict-first loads, gathers x from shared memory, does a shuffle segmented reduction by row and
+// accumulates into its private shared-memory row sums; the 16 partial sums of a row are added in a
+// fixed order at the end of the tile (deterministic, no atomics, no block barrier in the hot loop).
+// y = A x + P^T B (P x), P = alpha-major -> beta-major.
 //
 // The layout is produced from the CSR the build emits (pure permutation of entries, in place, with
 // bounded scratch) and decoded back on the host for export / get_row.  It replaces, for large dense
@@ -30,8 +33,7 @@
 
 namespace sqmc {
 
-static const int kWThreads = kSlabs * 32;  // 512
-static const int kSlabRows = kTileRows / kSlabs;
+static const int kWThreads = kWWarps * 32;  // 512
 
 static inline unsigned gblocks(int64_t n, int t = 256) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(div_up(n, t), 0x7fffffff)); }
 
@@ -142,33 +144,43 @@ __device__ __forceinline__ int win_rank(const uint32_t *bitmap, const uint32_t *
   return (int)wprefix[id >> 5] + __popc(bitmap[id >> 5] & ((1u << (id & 31)) - 1u));
 }
 
-// pass 1: number of distinct windows per tile
-__global__ void __launch_bounds__(kWThreads) tile_count_windows_kernel(WPart P, const int32_t *cols, int nwords, int64_t *win_count) {
+// pass 1: number of work items per tile (windows present, entries per window).  cntw: per-CTA scratch of
+// ngwin counters indexed by global window id (kept zeroed between tiles).
+__global__ void __launch_bounds__(kWThreads) tile_count_items_kernel(WPart P, const int32_t *cols, int nwords, int32_t *cntw_all, int64_t *item_count,
+                                                                     int *max_windows) {
   extern __shared__ uint32_t sm1[];
   uint32_t *bitmap = sm1;
-  __shared__ int total;
+  __shared__ int total, totalw;
+  int32_t *cntw = cntw_all + (int64_t)blockIdx.x * P.ngwin;
   for (int64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0;
-    if (threadIdx.x == 0) total = 0;
+    if (threadIdx.x == 0) { total = 0; totalw = 0; }
     __syncthreads();
     const int64_t e0 = P.tile_ent0[t], e1 = P.tile_ent0[t + 1];
     for (int64_t k = e0 + threadIdx.x; k < e1; k += blockDim.x) {
       int32_t id = P.colwin[cols[P.ent0 + k]];
       atomicOr(&bitmap[id >> 5], 1u << (id & 31));
+      atomicAdd(&cntw[id], 1);
     }
     __syncthreads();
-    int c = 0;
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) c += __popc(bitmap[i]);
+    int c = 0, cw = 0;
+    for (int i = threadIdx.x; i < nwords * 32; i += blockDim.x) {
+      if (bitmap[i >> 5] & (1u << (i & 31))) {
+        c += (cntw[i] + kItemMax - 1) / kItemMax;
+        cw++;
+        cntw[i] = 0;
+      }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); cw += __shfl_xor_sync(0xffffffffu, cw, o); }
+    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&total, c); atomicAdd(&totalw, cw); }
     __syncthreads();
-    if (threadIdx.x == 0) win_count[t] = total;
+    if (threadIdx.x == 0) { item_count[t] = total; atomicMax(max_windows, totalw); }
     __syncthreads();
   }
 }
 
-// pass 2: reorder the entries of a tile from (row, col) to (window, row, col), pack indices, write window records.
+// pass 2: reorder the entries of a tile from (row, col) to (window, row, col), pack indices, write work items.
 // cnt: [W][R] counts -> offsets, in shared memory when it fits (cnt_smem_ints), else in per-CTA global scratch.
 __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_t *cols, double *vals, int nwords, int cnt_smem_ints,
                                                                  int32_t *cnt_scratch, int64_t cnt_scratch_stride, int32_t *scr_idx,
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_
       atomicOr(&bitmap[id >> 5], 1u << (id & 31));
     }
     __syncthreads();
-    // ---- b. exclusive prefix of popcounts over the bitmap words (nwords <= 2048 = 4 per thread)
+    // ---- b. exclusive prefix of popcounts over the bitmap words
     {
       const int per = (nwords + kWThreads - 1) / kWThreads;
       int s = 0;
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_
     // ---- c. counts per (window, row)
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    for (int r = warp; r < R; r += kSlabs) {
+    for (int r = warp; r < R; r += kWWarps) {
       const int64_t s = P.rowptr[trow0 + r] - e0, e = P.rowptr[trow0 + r + 1] - e0;
       for (int64_t k = s + lane; k < e; k += 32) {
         int w = win_rank(bitmap, wprefix, P.colwin[tc[k]]);
@@ -245,26 +257,30 @@ __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_
       for (int64_t i = i0; i < i1; i++) { int v = cnt[i]; cnt[i] = run; run += v; }
       __syncthreads();
     }
-    // ---- e. window records
-    const int64_t wrec0 = P.tile_win0[t];
-    for (int i = threadIdx.x; i < nwords * 32; i += blockDim.x) {
-      if (bitmap[i >> 5] & (1u << (i & 31))) {
-        int w = win_rank(bitmap, wprefix, i);
-        int32_t c0 = P.gwin_col0[i];
-        P.win_col0[wrec0 + w] = c0;
-        P.win_len[wrec0 + w] = P.gwin_len[i];
-        int32_t *slab = P.win_slab + (wrec0 + w) * (kSlabs + 1);
-        for (int sidx = 0; sidx <= kSlabs; sidx++) {
-          int rr = sidx * kSlabRows;
-          int64_t off;
-          if (rr < R) off = cnt[(int64_t)w * R + rr];
-          else off = (w + 1 < W) ? cnt[(int64_t)(w + 1) * R] : (int32_t)E;
-          slab[sidx] = (int32_t)off;
+    // ---- e. work items: each window's entry range cut into pieces of <= kItemMax entries (serial, ~W steps)
+    if (threadIdx.x == 0) {
+      WItem *it = P.items + P.tile_item0[t];
+      int w = 0;
+      for (int word = 0; word < nwords; word++) {
+        uint32_t bits = bitmap[word];
+        while (bits) {
+          int id = word * 32 + (__ffs(bits) - 1);
+          bits &= bits - 1;
+          int32_t kb = cnt[(int64_t)w * R], ke = (w + 1 < W) ? cnt[(int64_t)(w + 1) * R] : (int32_t)E;
+          for (int32_t k = kb; k < ke; k += kItemMax) {
+            WItem v;
+            v.col0 = P.gwin_col0[id];
+            v.len = P.gwin_len[id];
+            v.k0 = k;
+            v.k1 = min(ke, k + kItemMax);
+            *it++ = v;
+          }
+          w++;
         }
       }
     }
     // ---- f. scatter to scratch in (window, row, col) order
-    for (int r = warp; r < R; r += kSlabs) {
+    for (int r = warp; r < R; r += kWWarps) {
       const int64_t s = P.rowptr[trow0 + r] - e0, e = P.rowptr[trow0 + r + 1] - e0;
       int carry_w = -1, carry_n = 0;  // run continuing from the previous 32-entry chunk
       for (int64_t kb = s; kb < e; kb += 32) {
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_
         int wprev = __shfl_up_sync(0xffffffffu, w, 1);
         bool head = in && (lane == 0 || w != wprev);
         unsigned hm = __ballot_sync(0xffffffffu, head);
-        int last_head = 31 - __clz(hm & ((2u << lane) - 1u));  // lane of the head of my run (bit 0 is always a head)
+        int last_head = 31 - __clz(hm & ((2u << lane) - 1u));  // lane of the head of my run (lane 0 is always a head)
         int rel = lane - last_head;
         if (last_head == 0 && w == carry_w) rel += carry_n;
         if (in) {
@@ -284,7 +300,6 @@ __global__ void __launch_bounds__(kWThreads) tile_reorder_kernel(WPart P, int32_
           my_scr_idx[dst] = (int32_t)(((uint32_t)r << 16) | (uint32_t)(c - P.gwin_col0[id]));
           my_scr_val[dst] = tv[k];
         }
-        // carry for the next chunk: window and length of the run that reaches lane 31
         int w31 = __shfl_sync(0xffffffffu, w, 31), rel31 = __shfl_sync(0xffffffffu, rel, 31);
         carry_w = w31;
         carry_n = rel31 + 1;
@@ -345,77 +360,178 @@ __device__ __forceinline__ double ld_v(const double *p, const StreamPol &S) {
   return r;
 }
 
-// one CTA per tile (grid-stride); x: the part's column space (global length ncols); y: the part's local rows
-__global__ void __launch_bounds__(kWThreads) wcsr_spmv_kernel(WPart P, const int32_t *__restrict__ idx, const double *__restrict__ vals,
-                                                              const double *__restrict__ x, int64_t ncols, double *__restrict__ y) {
-  __shared__ __align__(16) double xw[2][kWinMax + 2];
-  __shared__ double yacc[kTileRows];
-  __shared__ __align__(8) uint64_t full[2];
+__device__ __forceinline__ uint4 ld_idx4(const int32_t *p, const StreamPol &S) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(S.p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_v2(const double *p, const StreamPol &S) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(S.p));
+  return r;
+}
+
+// 256 consecutive entries, 8 per lane, loaded with 128-bit loads (k is a multiple of 8 in absolute entry index).
+// Entries outside [kmin, kmax) (the unaligned head / the tail of an item) are masked: product 0 and the row id of
+// the nearest valid entry, so they merge into an existing segment.  Each lane sums its 8 entries sequentially
+// (branch-free running segmented sum); rows closed inside a lane are flushed by that lane; the open last
+// segments are combined across lanes with ONE segmented scan per 256 entries.
+struct VecRegs {
+  uint4 a, b;
+  double2 v0, v1, v2, v3;
+};
+__device__ __forceinline__ VecRegs vec_load(const int32_t *pidx, const double *pval, int64_t k, int lane, const StreamPol &SP) {
+  VecRegs r;
+  const int64_t base = k + lane * 8;
+  r.a = ld_idx4(pidx + base, SP);
+  r.b = ld_idx4(pidx + base + 4, SP);
+  r.v0 = ld_v2(pval + base, SP);
+  r.v1 = ld_v2(pval + base + 2, SP);
+  r.v2 = ld_v2(pval + base + 4, SP);
+  r.v3 = ld_v2(pval + base + 6, SP);
+  return r;
+}
+// k: first entry of the step (may be < kmin); valid entries are [kmin, kmax); row_first/row_last: rows of entries kmin / kmax-1
+__device__ __forceinline__ void vec_consume(const VecRegs &g, int64_t k, int64_t kmin, int64_t kmax, int row_first, int row_last, int lane,
+                                            const double *xb, double *yacc) {
+  const uint32_t u[8] = {g.a.x, g.a.y, g.a.z, g.a.w, g.b.x, g.b.y, g.b.z, g.b.w};
+  const double v[8] = {g.v0.x, g.v0.y, g.v1.x, g.v1.y, g.v2.x, g.v2.y, g.v3.x, g.v3.y};
+  const int64_t base = k + lane * 8;
+  int r[8];
+  double p[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int64_t kk = base + j;
+    const bool lo = kk < kmin, hi = kk >= kmax;
+    r[j] = lo ? row_first : (hi ? row_last : (int)(u[j] >> 16));
+    const double xv = xb[u[j] & 0x3ffu];  // col_local <= kWinMax + 1 < 1024; masked entries read a harmless slot
+    p[j] = (lo || hi) ? 0.0 : v[j] * xv;
+  }
+  // running segmented sums inside the lane
+  double sum[8];
+  sum[0] = p[0];
+#pragma unroll
+  for (int j = 1; j < 8; j++) sum[j] = (r[j] == r[j - 1]) ? sum[j - 1] + p[j] : p[j];
+  // segments closed inside the lane: the first one is kept (it may continue the previous lane's row), later ones are complete rows
+  bool multi = false;
+  double af = 0.0;
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    if (r[j + 1] != r[j]) {
+      if (!multi) { af = sum[j]; multi = true; }
+      else yacc[r[j]] += sum[j];
+    }
+  }
+  const int rf = r[0], rl = r[7];
+  double al = sum[7];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, al, d);
+    int kk = __shfl_up_sync(0xffffffffu, rl, d);
+    if (lane >= d && kk == rl) al += t;
+  }
+  const int rl_next = __shfl_down_sync(0xffffffffu, rl, 1);
+  const int rl_prev = __shfl_up_sync(0xffffffffu, rl, 1);
+  const int rf_next = __shfl_down_sync(0xffffffffu, rf, 1);
+  const double af_next = __shfl_down_sync(0xffffffffu, af, 1);
+  const int multi_next = __shfl_down_sync(0xffffffffu, (int)multi, 1);
+  if (lane == 31 || rl_next != rl) {
+    double tot = al;
+    if (lane < 31 && multi_next && rf_next == rl) tot += af_next;  // the next lane's first segment continues this row
+    yacc[rl] += tot;
+  }
+  if (multi && (lane == 0 || rl_prev != rf)) yacc[rf] += af;  // first segment that does not continue the previous lane's row
+  __syncwarp();
+}
+
+static const int kXwStride = kWinMax + 2;  // doubles per staging buffer
+static const int kWcsrSmemBytes = kWWarps * 2 * kXwStride * 8 + kWWarps * kTileRows * 8 + kWWarps * 2 * 8;
+
+// Persistent CTAs (one per SM) take tiles from an atomic counter.  x: the part's column space (length ncols);
+// y: the part's local rows.
+__global__ void __launch_bounds__(kWThreads, 1) wcsr_spmv_kernel(WPart P, const int32_t *__restrict__ idx, const double *__restrict__ vals,
+                                                                 const double *__restrict__ x, int64_t ncols, double *__restrict__ y,
+                                                                 unsigned long long *tile_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *xw_all = reinterpret_cast<double *>(smem_raw);                                   // [warp][2][kXwStride]
+  double *yacc_all = xw_all + kWWarps * 2 * kXwStride;                                     // [warp][kTileRows]
+  uint64_t *bars_all = reinterpret_cast<uint64_t *>(yacc_all + kWWarps * kTileRows);       // [warp][2]
+  __shared__ long long s_tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *xw = xw_all + warp * 2 * kXwStride;
+  double *yacc = yacc_all + warp * kTileRows;
+  uint64_t *bar = bars_all + warp * 2;
   const StreamPol SP;
-  if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+  if (lane == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t phase[2] = {0, 0};
+  uint32_t phase0 = 0, phase1 = 0;
   const int32_t *pidx = idx + P.ent0;
   const double *pval = vals + P.ent0;
-  for (int64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    const int64_t t = s_tile;
+    if (t >= P.ntiles) break;
     const int R = P.tile_nrows[t];
     const int64_t e0 = P.tile_ent0[t];
-    const int64_t w0 = P.tile_win0[t], nwin = P.tile_win0[t + 1] - w0;
-    for (int i = threadIdx.x; i < kTileRows; i += blockDim.x) yacc[i] = 0.0;
-    // stage window `wi` into buffer b: bulk copy of the 16-byte aligned part + (rare) tail by plain loads
-    auto stage = [&](int64_t wi, int b) {
-      if (threadIdx.x == 0) {
-        const int32_t c0 = P.win_col0[w0 + wi];
-        const int32_t len = P.win_len[w0 + wi];
+    const int64_t i0 = P.tile_item0[t], ni = P.tile_item0[t + 1] - i0;
+    for (int i = lane; i < kTileRows; i += 32) yacc[i] = 0.0;
+    // stage the x slice of item j into buffer b (lane 0): bulk copy of the in-range even part + (rare) tail
+    auto stage = [&](int64_t j, int b) {
+      if (lane == 0) {
+        const int4 itv = *reinterpret_cast<const int4 *>(P.items + i0 + j);
+        const int32_t c0 = itv.x, len = itv.y;
         int32_t blen = len;
         if ((int64_t)c0 + blen > ncols) blen = (int32_t)((ncols - c0) & ~1ll);
         if (blen > 0) {
-          mbar_expect_tx(&full[b], (uint32_t)blen * 8u);
-          bulk_g2s(&xw[b][0], x + c0, (uint32_t)blen * 8u, &full[b]);
+          mbar_expect_tx(&bar[b], (uint32_t)blen * 8u);
+          bulk_g2s(xw + b * kXwStride, x + c0, (uint32_t)blen * 8u, &bar[b]);
         } else {
-          mbar_arrive(&full[b]);
+          mbar_arrive(&bar[b]);
         }
-        for (int i = blen; i < len && (int64_t)c0 + i < ncols; i++) xw[b][i] = x[c0 + i];
+        for (int i = blen; i < len && (int64_t)c0 + i < ncols; i++) xw[b * kXwStride + i] = x[c0 + i];
       }
     };
-    __syncthreads();  // yacc zeroed; previous tile's buffers free
-    if (nwin > 0) stage(0, 0);
-    __syncthreads();  // tail stores of window 0 visible
-    for (int64_t wi = 0; wi < nwin; wi++) {
-      const int b = (int)(wi & 1);
-      if (wi + 1 < nwin) stage(wi + 1, b ^ 1);
-      mbar_wait(&full[b], phase[b]);
-      phase[b] ^= 1;
-      const int32_t *slab = P.win_slab + (w0 + wi) * (kSlabs + 1);
-      const int64_t s0 = e0 + slab[warp], s1 = e0 + slab[warp + 1];
-      const double *xb = xw[b];
-      for (int64_t kb = s0; kb < s1; kb += 32) {
-        const int64_t k = kb + lane;
-        const bool in = k < s1;
-        uint32_t u = in ? ld_idx(pidx + k, SP) : 0xffffffffu;
-        double v = in ? ld_v(pval + k, SP) : 0.0;
-        int key = in ? (int)(u >> 16) : -1;
-        double prod = in ? v * xb[u & 0xffffu] : 0.0;
-        // inclusive segmented scan over lanes (keys are ascending inside a slab)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          double tp = __shfl_up_sync(0xffffffffu, prod, d);
-          int tk = __shfl_up_sync(0xffffffffu, key, d);
-          if (lane >= d && tk == key) prod += tp;
+    if (warp < ni) stage(warp, 0);
+    __syncwarp();
+    int b = 0;
+    for (int64_t j = warp; j < ni; j += kWWarps, b ^= 1) {
+      if (j + kWWarps < ni) stage(j + kWWarps, b ^ 1);
+      const int4 itv = *reinterpret_cast<const int4 *>(P.items + i0 + j);
+      const int64_t k0 = e0 + itv.z, k1 = e0 + itv.w;
+      if (b == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+      else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+      const double *xb = xw + b * kXwStride;
+      {
+        // masked 256-entry vector steps from the 8-aligned (absolute index) start; 2 steps of loads kept in flight
+        const int row_first = (int)((uint32_t)__ldg(pidx + k0) >> 16), row_last = (int)((uint32_t)__ldg(pidx + k1 - 1) >> 16);
+        int64_t k = k0 - ((P.ent0 + k0) & 7);
+        VecRegs c0 = vec_load(pidx, pval, k, lane, SP);
+        VecRegs c1;
+        if (k + 256 < k1) c1 = vec_load(pidx, pval, k + 256, lane, SP);
+        for (; k < k1; k += 256) {
+          VecRegs c2;
+          if (k + 512 < k1) c2 = vec_load(pidx, pval, k + 512, lane, SP);
+          vec_consume(c0, k, k0, k1, row_first, row_last, lane, xb, yacc);
+          c0 = c1;
+          c1 = c2;
         }
-        int knext = __shfl_down_sync(0xffffffffu, key, 1);
-        if (in && (lane == 31 || knext != key)) yacc[key] += prod;  // segment tail; rows of a slab belong to this warp only
-        __syncwarp();
       }
-      __syncthreads();  // everyone is done with buffer b (and tail stores for window wi+1 are visible)
+      __syncwarp();  // buffer b fully consumed (and tail stores of the staged buffer visible) before it is refilled
     }
+    __syncthreads();
     const int32_t trow0 = P.tile_row0[t];
-    for (int i = threadIdx.x; i < R; i += blockDim.x) y[trow0 + i] = yacc[i];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWWarps; w++) acc += yacc_all[w * kTileRows + i];
+      y[trow0 + i] = acc;
+    }
+    __syncthreads();
   }
 }
 
@@ -428,15 +544,22 @@ __global__ void add_perm_kernel(double *y, const double *yb, const int32_t *brow
   if (i < nloc) y[i] = y[i] + yb[browL_inv[i]];
 }
 
+static unsigned long long *g_tile_counters = nullptr;  // [2]
+
 int wcsr_spmv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0;
   if (nloc == 0) return 0;
-  const int grid = G.sm_count * 4;
+  if (!g_tile_counters) {
+    SQ_CUDA(cudaMalloc(&g_tile_counters, 2 * sizeof(unsigned long long)));
+    SQ_CUDA(cudaFuncSetAttribute(wcsr_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcsrSmemBytes));
+  }
+  SQ_CUDA(cudaMemsetAsync(g_tile_counters, 0, 2 * sizeof(unsigned long long), s));
   gather_perm_kernel<<<gblocks(h->n), 256, 0, s>>>(x, h->d_bidx, h->d_xb, h->n);
   SQ_LAUNCH_CHECK();
-  wcsr_spmv_kernel<<<(unsigned)std::min<int64_t>(grid, std::max<int64_t>(h->WA.ntiles, 1)), kWThreads, 0, s>>>(h->WA, h->d_cols, h->d_vals, x, h->n, y);
+  const int grid = G.sm_count;
+  wcsr_spmv_kernel<<<grid, kWThreads, kWcsrSmemBytes, s>>>(h->WA, h->d_cols, h->d_vals, x, h->n, y, g_tile_counters);
   SQ_LAUNCH_CHECK();
-  wcsr_spmv_kernel<<<(unsigned)std::min<int64_t>(grid, std::max<int64_t>(h->WB.ntiles, 1)), kWThreads, 0, s>>>(h->WB, h->d_cols, h->d_vals, h->d_xb, h->n, h->d_yb);
+  wcsr_spmv_kernel<<<grid, kWThreads, kWcsrSmemBytes, s>>>(h->WB, h->d_cols, h->d_vals, h->d_xb, h->n, h->d_yb, g_tile_counters + 1);
   SQ_LAUNCH_CHECK();
   add_perm_kernel<<<gblocks(nloc), 256, 0, s>>>(y, h->d_yb, h->d_browL_inv, nloc);
   SQ_LAUNCH_CHECK();
@@ -449,7 +572,7 @@ static void free_part(WPart &P) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(P.tile_row0); F(P.tile_nrows); F(P.tile_ent0); F(P.tile_win0); F(P.win_col0); F(P.win_len); F(P.win_slab); F(P.rowptr); F(P.colwin);
+  F(P.tile_row0); F(P.tile_nrows); F(P.tile_ent0); F(P.tile_item0); F(P.items); F(P.rowptr); F(P.colwin);
   F(P.gwin_col0); F(P.gwin_len);
   P = WPart();
 }
@@ -515,7 +638,7 @@ static void make_tiles(const std::vector<int32_t> &grp, const std::vector<int64_
   ent0.push_back(rowptr[n]);
 }
 
-static int convert_part(sqmc_b200_handle *h, WPart &P, const std::vector<int32_t> &grp_of_row, int64_t &max_w_out, cudaStream_t s) {
+static int convert_part(sqmc_b200_handle *h, WPart &P, const std::vector<int32_t> &grp_of_row, cudaStream_t s) {
   // rowptr (relative to P.ent0) is already on the device in P.rowptr
   std::vector<int64_t> rowptr(P.nrows + 1);
   SQ_CUDA(cudaMemcpy(rowptr.data(), P.rowptr, (P.nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -529,31 +652,37 @@ static int convert_part(sqmc_b200_handle *h, WPart &P, const std::vector<int32_t
   int64_t max_tile_ent = 0;
   for (int64_t t = 0; t < P.ntiles; t++) max_tile_ent = std::max(max_tile_ent, ent0[t + 1] - ent0[t]);
   const int nwords = (int)div_up(P.ngwin, 32);
-  // pass 1: windows per tile
-  DevBuf<int64_t> wcount;
-  SQ_CHECK(wcount.alloc(P.ntiles + 1));
-  SQ_CUDA(cudaMemsetAsync(wcount.p, 0, (P.ntiles + 1) * sizeof(int64_t), s));
+  // pass 1: work items per tile
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(P.ntiles, 1), G.sm_count * 2);
+  DevBuf<int64_t> icount;
+  DevBuf<int> maxw_dev;
+  int max_w_tile = 0;
+  SQ_CHECK(maxw_dev.alloc(1));
+  SQ_CUDA(cudaMemsetAsync(maxw_dev.p, 0, sizeof(int), s));
+  SQ_CHECK(icount.alloc(P.ntiles + 1));
+  SQ_CUDA(cudaMemsetAsync(icount.p, 0, (P.ntiles + 1) * sizeof(int64_t), s));
   if (P.ntiles > 0) {
-    tile_count_windows_kernel<<<grid, kWThreads, nwords * 4, s>>>(P, h->d_cols, nwords, wcount.p);
+    DevBuf<int32_t> cntw;
+    SQ_CHECK(cntw.alloc(std::max<int64_t>(P.ngwin, 1) * grid));
+    SQ_CUDA(cudaMemsetAsync(cntw.p, 0, std::max<int64_t>(P.ngwin, 1) * grid * sizeof(int32_t), s));
+    tile_count_items_kernel<<<grid, kWThreads, nwords * 4, s>>>(P, h->d_cols, nwords, cntw.p, icount.p, maxw_dev.p);
     SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaMemcpyAsync(&max_w_tile, maxw_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
   }
-  std::vector<int64_t> wc(P.ntiles + 1, 0), win0(P.ntiles + 1, 0);
-  SQ_CUDA(cudaMemcpyAsync(wc.data(), wcount.p, (P.ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  SQ_CUDA(cudaStreamSynchronize(s));
-  int64_t maxw = 0;
-  for (int64_t t = 0; t < P.ntiles; t++) { win0[t + 1] = win0[t] + wc[t]; maxw = std::max(maxw, wc[t]); }
-  max_w_out = maxw;
-  P.nwin = win0[P.ntiles];
-  SQ_CHECK(upload(P.tile_win0, win0));
-  SQ_CUDA(cudaMalloc(&P.win_col0, std::max<int64_t>(P.nwin, 1) * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&P.win_len, std::max<int64_t>(P.nwin, 1) * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&P.win_slab, std::max<int64_t>(P.nwin, 1) * (kSlabs + 1) * sizeof(int32_t)));
+  std::vector<int64_t> ic(P.ntiles + 1, 0), item0(P.ntiles + 1, 0);
+  SQ_CUDA(cudaMemcpy(ic.data(), icount.p, (P.ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  for (int64_t t = 0; t < P.ntiles; t++) item0[t + 1] = item0[t] + ic[t];
+  P.nitems = item0[P.ntiles];
+  SQ_CHECK(upload(P.tile_item0, item0));
+  SQ_CUDA(cudaMalloc(&P.items, std::max<int64_t>(P.nitems, 1) * sizeof(WItem)));
   if (P.ntiles == 0) return 0;
-  // pass 2: reorder
+  // pass 2: reorder.  The [windows][rows] count matrix lives in shared memory when it fits, else in global scratch
+  // sized for the widest tile found in pass 1.
   int cnt_smem_ints = (int)((200 * 1024 - 2 * nwords * 4) / 4);
   if (cnt_smem_ints < 0) cnt_smem_ints = 0;
-  const int64_t need = maxw * kTileRows;
+  int64_t max_w = std::max<int64_t>(max_w_tile, 1);
+  const int64_t need = max_w * kTileRows;
   int smem_bytes = 2 * nwords * 4 + (int)std::min<int64_t>(need, cnt_smem_ints) * 4;
   if (need <= cnt_smem_ints) cnt_smem_ints = (int)need;
   DevBuf<int32_t> cnt_scr, scr_idx;
@@ -567,6 +696,11 @@ static int convert_part(sqmc_b200_handle *h, WPart &P, const std::vector<int32_t
                                                           std::max<int64_t>(max_tile_ent, 1));
   SQ_LAUNCH_CHECK();
   SQ_CUDA(cudaStreamSynchronize(s));
+  // conversion-only tables are no longer needed
+  cudaFree(P.rowptr); P.rowptr = nullptr;
+  cudaFree(P.colwin); P.colwin = nullptr;
+  cudaFree(P.gwin_col0); P.gwin_col0 = nullptr;
+  cudaFree(P.gwin_len); P.gwin_len = nullptr;
   return 0;
 }
 
@@ -686,9 +820,8 @@ static int convert_impl(sqmc_b200_handle *h) {
     SQ_CUDA(cudaMemcpy(eBpos.data(), h->d_eBpos, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < nloc; i++) grpB[i] = eBpos[binv[browL[i]]];
   }
-  int64_t maxwA = 0, maxwB = 0;
-  SQ_CHECK(convert_part(h, A, grpA, maxwA, s));
-  SQ_CHECK(convert_part(h, B, grpB, maxwB, s));
+  SQ_CHECK(convert_part(h, A, grpA, s));
+  SQ_CHECK(convert_part(h, B, grpB, s));
   SQ_CUDA(cudaMalloc(&h->d_xb, std::max<int64_t>(n, 1) * sizeof(double)));
   SQ_CUDA(cudaMalloc(&h->d_yb, std::max<int64_t>(nloc, 1) * sizeof(double)));
   h->wcsr = true;
@@ -698,8 +831,12 @@ static int convert_impl(sqmc_b200_handle *h) {
 int wcsr_convert(sqmc_b200_handle *h) {
   // only for builds without time-reversal expansion (the group structure is kept then)
   if (!h->d_gA_off || !h->d_bidx || h->T.time_sym) return 0;
+  // OPT-IN (SQMC_WCSR=1 forces the conversion, SQMC_WCSR=2 converts dense spaces only).  Default off: on B200 the
+  // layout is correct and removes the L1TEX gather traffic, but its row-sum bookkeeping costs more issue slots
+  // than the gathers it saves (profiles/r01_wcsr_experiment.txt: 36.7 ms vs 23.4 ms per H.v at 10^7 dets).
   const char *e = getenv("SQMC_WCSR");
-  int mode = e ? atoi(e) : -1;  // -1 auto, 0 off, 1 force
+  int mode = e ? atoi(e) : 0;
+  if (mode == 2) mode = -1;
   if (mode == 0) return 0;
   int64_t ngw_bound = h->nA + h->n / kWinMax + 1, ngw_bound_b = h->nB + h->n / kWinMax + 1;
   if (ngw_bound > 65536 || ngw_bound_b > 65536) return 0;  // window bitmap of the conversion lives in shared memory
@@ -715,14 +852,13 @@ int wcsr_convert(sqmc_b200_handle *h) {
 __global__ void wcsr_extract_row_kernel(WPart P, const int32_t *idx, const double *vals, int64_t t, int rl, int32_t *out_cols, double *out_vals,
                                         int *counter, int cap) {
   const int64_t e0 = P.tile_ent0[t];
-  for (int64_t w = P.tile_win0[t]; w < P.tile_win0[t + 1]; w++) {
-    const int32_t *slab = P.win_slab + w * (kSlabs + 1);
-    const int32_t c0 = P.win_col0[w];
-    for (int64_t k = e0 + slab[0] + threadIdx.x; k < e0 + slab[kSlabs]; k += blockDim.x) {
+  for (int64_t j = P.tile_item0[t]; j < P.tile_item0[t + 1]; j++) {
+    const WItem it = P.items[j];
+    for (int64_t k = e0 + it.k0 + threadIdx.x; k < e0 + it.k1; k += blockDim.x) {
       uint32_t u = (uint32_t)idx[P.ent0 + k];
       if ((int)(u >> 16) == rl) {
         int q = atomicAdd(counter, 1);
-        if (q < cap) { out_cols[q] = c0 + (int32_t)(u & 0xffffu); out_vals[q] = vals[P.ent0 + k]; }
+        if (q < cap) { out_cols[q] = it.col0 + (int32_t)(u & 0xffffu); out_vals[q] = vals[P.ent0 + k]; }
       }
     }
   }
@@ -786,22 +922,20 @@ int wcsr_decode_host(sqmc_b200_handle *h, std::vector<int64_t> &rowptr, std::vec
   std::vector<std::vector<std::pair<int32_t, double>>> rows(nloc);
   for (int part = 0; part < 2; part++) {
     WPart &P = part == 0 ? h->WA : h->WB;
-    std::vector<int32_t> trow0(P.ntiles), wcol0(std::max<int64_t>(P.nwin, 1));
-    std::vector<int64_t> tent0(P.ntiles + 1), twin0(P.ntiles + 1);
-    std::vector<int32_t> slab(std::max<int64_t>(P.nwin, 1) * (kSlabs + 1));
     if (P.ntiles == 0) continue;
+    std::vector<int32_t> trow0(P.ntiles);
+    std::vector<int64_t> tent0(P.ntiles + 1), titem0(P.ntiles + 1);
+    std::vector<WItem> items(std::max<int64_t>(P.nitems, 1));
     SQ_CUDA(cudaMemcpy(trow0.data(), P.tile_row0, P.ntiles * 4, cudaMemcpyDeviceToHost));
     SQ_CUDA(cudaMemcpy(tent0.data(), P.tile_ent0, (P.ntiles + 1) * 8, cudaMemcpyDeviceToHost));
-    SQ_CUDA(cudaMemcpy(twin0.data(), P.tile_win0, (P.ntiles + 1) * 8, cudaMemcpyDeviceToHost));
-    SQ_CUDA(cudaMemcpy(wcol0.data(), P.win_col0, P.nwin * 4, cudaMemcpyDeviceToHost));
-    SQ_CUDA(cudaMemcpy(slab.data(), P.win_slab, P.nwin * (kSlabs + 1) * 4, cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(titem0.data(), P.tile_item0, (P.ntiles + 1) * 8, cudaMemcpyDeviceToHost));
+    if (P.nitems) SQ_CUDA(cudaMemcpy(items.data(), P.items, P.nitems * sizeof(WItem), cudaMemcpyDeviceToHost));
     for (int64_t t = 0; t < P.ntiles; t++) {
-      for (int64_t w = twin0[t]; w < twin0[t + 1]; w++) {
-        int64_t k0 = tent0[t] + slab[w * (kSlabs + 1)], k1 = tent0[t] + slab[w * (kSlabs + 1) + kSlabs];
-        for (int64_t k = k0; k < k1; k++) {
+      for (int64_t j = titem0[t]; j < titem0[t + 1]; j++) {
+        for (int64_t k = tent0[t] + items[j].k0; k < tent0[t] + items[j].k1; k++) {
           uint32_t u = (uint32_t)idx[P.ent0 + k];
           int64_t prow = trow0[t] + (u >> 16);
-          int32_t pcol = wcol0[w] + (int32_t)(u & 0xffffu);
+          int32_t pcol = items[j].col0 + (int32_t)(u & 0xffffu);
           int64_t lrow = part == 0 ? prow : (browL[prow] - h->row0);  // local alpha-major row
           int32_t icol = part == 0 ? pcol : bidx[pcol];               // internal column
           rows[lrow].push_back({icol, v[P.ent0 + k]});
