@@ -11,7 +11,9 @@
 // ncclAllReduce, the new basis vector is all-gathered before the SpMV
 // (the reference does both with n-long MPI_ALLREDUCEs, :2647,2658).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "handle.h"
@@ -135,6 +137,28 @@ static void jacobi_eigh(int n, std::vector<double> a, std::vector<double> &evals
   evecs.swap(v2);
 }
 
+// optional phase timing (SQMC_DAV_PROFILE=1): host clock around synchronised phases, printed to stderr
+struct PhaseTimer {
+  bool on;
+  cudaStream_t s;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer(cudaStream_t st) : s(st) {
+    const char *e = getenv("SQMC_DAV_PROFILE");
+    on = e && atoi(e) > 0;
+  }
+  void start() {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    t0 = std::chrono::steady_clock::now();
+  }
+  void stop(int i) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    acc[i] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
 struct Dav {
   sqmc_b200_handle *h;
   cudaStream_t s;
@@ -207,6 +231,8 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   Dav D;
   D.h = h;
   D.s = G.stream;
+  PhaseTimer PT(G.stream);
+  PT.start();
   D.n = n;
   D.nloc = h->row1 - h->row0;
   D.ld = std::max<int64_t>(D.nloc, 1);
@@ -258,6 +284,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     }
   }
 
+  PT.stop(0);  // allocation + initial vectors
   std::vector<double> lowest(n_states, 0.0), prev(n_states, 1e300), residual_norm(n_states, 1.0);
   std::vector<double> h_krylov((size_t)m * m, 0.0), col(m + 8);
   auto HK = [&](int i, int j) -> double & { return h_krylov[(size_t)j * m + i]; };
@@ -300,6 +327,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     }
     const int i = (it_circ - 1) % n_states;
     const int c = it_circ - 1;
+    PT.start();
     if (nloc > 0) {
       resid_precond_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.HW + (int64_t)i * ld, D.W + (int64_t)i * ld, D.diag, lowest[i], Vc(c), nloc);
       SQ_LAUNCH_CHECK();
@@ -312,18 +340,24 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     }
     SQ_CHECK(D.dots(Vc(c), 1, Vc(c), D.scal + m + 2));
     SQ_CHECK(D.normalize(Vc(c), D.scal + m + 2));
+    PT.stop(1);  // residual + Gram-Schmidt
+    PT.start();
     SQ_CHECK(D.apply_h(Vc(c), HVc(c)));
+    PT.stop(2);  // H.v
+    PT.start();
     SQ_CHECK(D.dots(D.V, c + 1, HVc(c), D.scal));  // Krylov column (:2194-2197)
     SQ_CUDA(cudaMemcpyAsync(D.scal + c + 1, d_resid, sizeof(double), cudaMemcpyDeviceToDevice, s));
     SQ_CHECK(D.fetch(D.scal, c + 2, col.data()));
     for (int k = 0; k <= c; k++) { HK(k, c) = col[k]; HK(c, k) = col[k]; }
     residual_norm[i] = col[c + 1];
+    PT.stop(3);  // Krylov column
     double rs = 0;
     for (int q = 0; q < n_states; q++) rs += residual_norm[q];
     if (rs < 1.e-12) converged = true;
 
     if (it_circ % n_states == 0) {
       const int dim = it_circ;
+      PT.start();
       std::vector<double> hsub((size_t)dim * dim), ev, evec;
       for (int a = 0; a < dim; a++)
         for (int b = 0; b < dim; b++) hsub[(size_t)b * dim + a] = HK(a, b);
@@ -337,6 +371,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
         SQ_LAUNCH_CHECK();
       }
       SQ_CUDA(cudaStreamSynchronize(s));  // evec goes out of scope
+      PT.stop(4);  // subspace diagonalisation + Ritz vectors
       double md = 0;
       for (int q = 0; q < n_states; q++) md = std::max(md, fabs(lowest[q] - prev[q]));
       if (md < tol) { converged = true; break; }
@@ -346,6 +381,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     }
   }
   // ---- results: evals + eigenvectors in caller order
+  PT.start();
   for (int q = 0; q < n_states; q++) evals[q] = lowest[q];
   for (int q = 0; q < n_states; q++) {
     if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, D.W + (int64_t)q * ld, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -354,6 +390,10 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     SQ_CUDA(cudaMemcpyAsync(evecs + (size_t)q * n, h->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     SQ_CUDA(cudaStreamSynchronize(s));
   }
+  PT.stop(5);  // eigenvector download
+  if (PT.on)
+    fprintf(stderr, "[sqmc_b200 davidson] n=%lld matvecs=%d  setup %.1f ms | residual+GS %.1f | H.v %.1f | krylov %.1f | ritz %.1f | download %.1f\n",
+            (long long)n, D.nmv, PT.acc[0] * 1e3, PT.acc[1] * 1e3, PT.acc[2] * 1e3, PT.acc[3] * 1e3, PT.acc[4] * 1e3, PT.acc[5] * 1e3);
   if (n_matvec_out) *n_matvec_out = D.nmv;
   if (n_ritz_logged) *n_ritz_logged = nlogged;
   return 0;
