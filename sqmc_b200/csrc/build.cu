@@ -13,7 +13,8 @@
 //      reference's alpha_m1 idea, chemistry.f90:9819, applied to unique strings,
 //      not to determinants): the run of a key lists every alpha string one
 //      excitation away.
-//   3. candidate generation is pure XOR/popcount work, one warp per row:
+//   3. candidate generation is pure XOR/popcount work, one CTA per tile of <= 256 rows of one alpha-group, the beta
+//      strings of each candidate group staged once in shared memory (connect_tile_kernel):
 //        same alpha-group      : popc(dn^dn') in {2,4}   (dn single / double)
 //        neighbour alpha-groups : popc(dn^dn') in {0,2}   (up single, up+dn double)
 //        same beta-group        : popc(up^up') == 4       (up double)
@@ -244,66 +245,129 @@ struct ConnView {
   int nel;
 };
 
-// One warp per row.  FILL=false: count candidates; FILL=true: write candidate rep indices.
-template <int NW, bool FILL>
-__global__ void __launch_bounds__(256) connect_kernel(ConnView V, int64_t row_begin, int64_t row_end, int32_t *counts /*[row-row_begin]*/,
-                                                      const int64_t *cand_ptr /*[row-row_begin]*/, int32_t *cand) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t p = row_begin + warp;
-  if (p >= row_end) return;
-  const unsigned full = 0xffffffffu;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int32_t t0 = V.rowE[p];
-  const Bits<NW> a = b_load<NW>(V.Ea, t0), b = b_load<NW>(V.Eb, t0);
-  const int32_t g = V.eA[t0];
-  int64_t base = FILL ? cand_ptr[warp] : 0;
-  int cnt = 0;
-  // diagonal
-  if (FILL && lane == 0) cand[base] = (int32_t)p;
-  cnt = 1;
-  auto emit = [&](bool hit, uint32_t rep) {
-    unsigned m = __ballot_sync(full, hit);
-    if (FILL && hit) cand[base + cnt + __popc(m & lt_mask)] = (int32_t)(rep & ~kSwapBit);
-    cnt += __popc(m);
-  };
-  // (a) own alpha group: dn single / double
-  {
-    int64_t lo = V.gA_off[g], hi = V.gA_off[g + 1];
-    for (int64_t tb = lo; tb < hi; tb += 32) {
-      int64_t t = tb + lane;
-      bool in = t < hi;
-      int pc = in ? b_popc_xor(b, b_load<NW>(V.Eb, t)) : 0;
-      emit(in && (pc == 2 || pc == 4), in ? V.Erep[t] : 0u);
+// Tiled candidate generation: one CTA per tile of <= 256 consecutive entries of ONE alpha-group, one thread per entry
+// (= row, when the entry is not a time-reversed partner).  All rows of the tile share their candidate alpha-groups
+// (own group + the groups of the strings one excitation away), so the beta strings of a candidate group are staged
+// ONCE in shared memory and every thread tests them against its own beta string with XOR/popcount (broadcast
+// shared-memory reads, no divergence in the test).  The same-beta up-doubles are found afterwards, one warp per row.
+// FILL=false counts, FILL=true writes candidate rep indices (order inside a row is arbitrary; rows are sorted later).
+struct TileDesc {
+  int64_t e0;   // first entry
+  int32_t n;    // entries (<= kConnTile)
+  int32_t g;    // alpha group
+};
+static const int kConnTile = 256;
+static const int kConnStage = 1024;  // beta strings staged per step
+
+// W32: norb <= 32 -> strings are compared as 32-bit words (POPC is a quarter-rate instruction: one instead of two per test)
+template <int NW, bool FILL, bool W32>
+__global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, const TileDesc *tiles, int64_t ntiles, int64_t row_begin,
+                                                                 int32_t *counts, const int64_t *cand_ptr, int32_t *cand) {
+  __shared__ uint64_t sEb[W32 ? 1 : kConnStage * NW];
+  __shared__ uint32_t sEb32[W32 ? kConnStage : 1];
+  __shared__ uint32_t sErep[FILL ? kConnStage : 1];
+  __shared__ int32_t s_cnt[kConnTile];
+  __shared__ int32_t s_row[kConnTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const TileDesc T = tiles[t];
+    const int64_t e = T.e0 + threadIdx.x;
+    const bool have = threadIdx.x < T.n;
+    const uint32_t rep = have ? V.Erep[e] : kSwapBit;
+    const bool active = have && !(rep & kSwapBit);  // rows are the unswapped entries
+    const int64_t p = active ? (int64_t)rep : -1;
+    Bits<NW> b = b_zero<NW>();
+    if (active) b = b_load<NW>(V.Eb, e);
+    int64_t base = 0;
+    if (FILL && active) base = cand_ptr[p - row_begin];
+    int cnt = 0;
+    if (active) {
+      if (FILL) cand[base] = (int32_t)p;  // diagonal
+      cnt = 1;
     }
-  }
-  // (c) neighbour alpha groups: same dn (up single) or dn single (up single x dn single)
-  for (int e = 0; e < V.nel; e++) {
-    int32_t rlo = V.run_lo[(int64_t)g * V.nel + e], rhi = V.run_hi[(int64_t)g * V.nel + e];
-    for (int32_t r = rlo; r < rhi; r++) {
-      int32_t g2 = V.K_grp[r];
-      if (g2 == g) continue;
-      int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
-      for (int64_t tb = lo; tb < hi; tb += 32) {
-        int64_t t = tb + lane;
-        bool in = t < hi;
-        int pc = in ? b_popc_xor(b, b_load<NW>(V.Eb, t)) : 1;
-        emit(in && (pc == 0 || pc == 2), in ? V.Erep[t] : 0u);
+    const int g = T.g;
+    // candidate groups: index -1 = own group, then the runs of the nel (N-1)-electron keys of the group's string
+    for (int ek = -1; ek < V.nel; ek++) {
+      int32_t rlo = 0, rhi = 1;
+      if (ek >= 0) { rlo = V.run_lo[(int64_t)g * V.nel + ek]; rhi = V.run_hi[(int64_t)g * V.nel + ek]; }
+      for (int32_t r = rlo; r < rhi; r++) {
+        const int32_t g2 = (ek < 0) ? g : V.K_grp[r];
+        if (ek >= 0 && g2 == g) continue;
+        const bool own = ek < 0;
+        const int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
+        for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
+          const int ns = (int)min((int64_t)kConnStage, hi - s0);
+          __syncthreads();  // previous stage fully consumed
+          for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+            if (W32) {
+              sEb32[i] = (uint32_t)V.Eb[s0 + i];
+            } else {
+#pragma unroll
+              for (int w = 0; w < NW; w++) sEb[i * NW + w] = V.Eb[(s0 + i) * NW + w];
+            }
+            if (FILL) sErep[i] = V.Erep[s0 + i];
+          }
+          __syncthreads();
+          if (active) {
+            const uint32_t b32 = (uint32_t)b.w[0];
+#pragma unroll 8
+            for (int i = 0; i < ns; i++) {
+              int pc = 0;
+              if (W32) {
+                pc = __popc(b32 ^ sEb32[i]);
+              } else {
+#pragma unroll
+                for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
+              }
+              const bool hit = own ? (pc == 2 || pc == 4) : (pc == 0 || pc == 2);
+              if (hit) {
+                if (FILL) cand[base + cnt] = (int32_t)(sErep[i] & ~kSwapBit);
+                cnt++;
+              }
+            }
+          }
+        }
       }
     }
-  }
-  // (b) own beta group: up double
-  {
-    int32_t gb = V.eB[t0];
-    int64_t lo = V.gB_off[gb], hi = V.gB_off[gb + 1];
-    for (int64_t tb = lo; tb < hi; tb += 32) {
-      int64_t t = tb + lane;
-      bool in = t < hi;
-      int pc = in ? b_popc_xor(a, b_load<NW>(V.EBa, t)) : 0;
-      emit(in && pc == 4, in ? V.EBrep[t] : 0u);
+    // same beta-group, up doubles: one warp per row (coalesced scan of the beta-major view)
+    __syncthreads();
+    s_cnt[threadIdx.x] = cnt;
+    s_row[threadIdx.x] = active ? (int32_t)threadIdx.x : -1;
+    __syncthreads();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int rr = warp; rr < T.n; rr += kConnTile / 32) {
+      if (s_row[rr] < 0) continue;
+      const int64_t e2 = T.e0 + rr;
+      const Bits<NW> a2 = b_load<NW>(V.Ea, e2);
+      const int64_t p2 = (int64_t)V.Erep[e2];
+      const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] : 0;
+      int c2 = s_cnt[rr];
+      const int32_t gb = V.eB[e2];
+      const int64_t lo = V.gB_off[gb], hi = V.gB_off[gb + 1];
+      for (int64_t tb = lo; tb < hi; tb += 32) {
+        const int64_t k = tb + lane;
+        const bool in = k < hi;
+        const int pc = in ? b_popc_xor(a2, b_load<NW>(V.EBa, k)) : 0;
+        const bool hit = in && pc == 4;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) cand[base2 + c2 + __popc(m & lt_mask)] = (int32_t)(V.EBrep[k] & ~kSwapBit);
+        c2 += __popc(m);
+      }
+      if (!FILL && lane == 0) counts[p2 - row_begin] = c2;
     }
+    __syncthreads();
   }
-  if (!FILL && lane == 0) counts[warp] = cnt;
+}
+
+// tiles covering the entries [e_lo, e_hi) (host; gA is the host copy of the alpha-group offsets)
+static void make_conn_tiles(const std::vector<int64_t> &gA, int64_t e_lo, int64_t e_hi, std::vector<TileDesc> &tiles) {
+  tiles.clear();
+  if (e_hi <= e_lo) return;
+  int64_t g = std::upper_bound(gA.begin(), gA.end(), e_lo) - gA.begin() - 1;
+  for (; g + 1 < (int64_t)gA.size() && gA[g] < e_hi; g++) {
+    int64_t a = std::max(gA[g], e_lo), b = std::min(gA[g + 1], e_hi);
+    for (int64_t x = a; x < b; x += kConnTile) tiles.push_back({x, (int32_t)std::min<int64_t>(kConnTile, b - x), (int32_t)g});
+  }
 }
 
 // ------------------------------------------------------------------ per-row sort of candidate columns
@@ -699,6 +763,17 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   K_keys.release();
 
   ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, run_lo.p, run_hi.p, K_grp.p, nel};
+  // host copies for the tile lists: alpha-group offsets and (time-reversal only) the row -> entry map
+  std::vector<int64_t> gA_host(nA + 1);
+  SQ_CUDA(cudaMemcpy(gA_host.data(), gA_off.p, (nA + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> rowE_host;
+  if (ts) {
+    rowE_host.resize(n);
+    SQ_CUDA(cudaMemcpy(rowE_host.data(), rowE_buf.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  auto row_entry = [&](int64_t p) -> int64_t { return ts ? (int64_t)rowE_host[p] : p; };
+  std::vector<TileDesc> fill_tiles;
+  DevBuf<TileDesc> fill_tiles_dev;
   cudaEventRecord(ev[1], s);
 
   // ---- P1: candidate counts.  Under sharding every rank counts an equal slice of rows,
@@ -710,8 +785,18 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     int64_t per = div_up(n, G.nranks);
     int64_t c0 = std::min<int64_t>(n, per * G.rank), c1 = std::min<int64_t>(n, c0 + per);
     if (c1 > c0) {
-      connect_kernel<NW, false><<<nblocks((c1 - c0) * 32), 256, 0, s>>>(V, c0, c1, cand_count.p + c0, nullptr, nullptr);
+      std::vector<TileDesc> tiles;
+      make_conn_tiles(gA_host, row_entry(c0), row_entry(c1 - 1) + 1, tiles);
+      DevBuf<TileDesc> dt;
+      SQ_CHECK(dt.alloc((int64_t)tiles.size()));
+      SQ_CUDA(cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+      const unsigned cgrid = (unsigned)std::min<int64_t>((int64_t)tiles.size(), G.sm_count * 16);
+      if (NW == 1 && T.norb <= 32)
+        connect_tile_kernel<NW, false, true><<<cgrid, kConnTile, 0, s>>>(V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr);
+      else
+        connect_tile_kernel<NW, false, false><<<cgrid, kConnTile, 0, s>>>(V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr);
       SQ_LAUNCH_CHECK();
+      SQ_CUDA(cudaStreamSynchronize(s));
     }
     if (G.nranks > 1) {
       // equal-sized padded slices so that a plain allgather works
@@ -785,8 +870,17 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     // chunk-local candidate offsets
     SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p + r, cptr.p, nr, s));
     // the scan above read cand_count[r+nr] as its spare slot; offsets beyond nr are unused
-    connect_kernel<NW, true><<<nblocks(nr * 32), 256, 0, s>>>(V, r, r_end, nullptr, cptr.p, cand_tmp.p);
-    SQ_LAUNCH_CHECK();
+    {
+      make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
+      if ((int64_t)fill_tiles.size() > fill_tiles_dev.n) SQ_CHECK(fill_tiles_dev.alloc((int64_t)fill_tiles.size() * 2));
+      SQ_CUDA(cudaMemcpyAsync(fill_tiles_dev.p, fill_tiles.data(), fill_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+      const unsigned cgrid = (unsigned)std::min<int64_t>((int64_t)fill_tiles.size(), G.sm_count * 16);
+      if (NW == 1 && T.norb <= 32)
+        connect_tile_kernel<NW, true, true><<<cgrid, kConnTile, 0, s>>>(V, fill_tiles_dev.p, (int64_t)fill_tiles.size(), r, nullptr, cptr.p, cand_tmp.p);
+      else
+        connect_tile_kernel<NW, true, false><<<cgrid, kConnTile, 0, s>>>(V, fill_tiles_dev.p, (int64_t)fill_tiles.size(), r, nullptr, cptr.p, cand_tmp.p);
+      SQ_LAUNCH_CHECK();
+    }
     sort_rows_warp_kernel<<<nblocks(nr, 8), 256, 0, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
     SQ_LAUNCH_CHECK();
     {
