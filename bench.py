@@ -171,6 +171,12 @@ def main():
     nnz_full = info["nnz_full"]
     nloc, nnz_loc = H.local_rows()
     bt = H.build_times()
+    if world > 1:
+        allnnz = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(allnnz, torch.tensor([nnz_loc], dtype=torch.int64, device="cuda"))
+        nnz_per_rank = [int(t.item()) for t in allnnz]
+    else:
+        nnz_per_rank = [nnz_loc]
     launches_before = L.sqmc_b200_launch_count()
 
     # ---- resident vectors (internal row order: the order Davidson keeps its Krylov vectors in)
@@ -269,6 +275,7 @@ def main():
         "clocks": clocks,
         "build": {"seconds_wall": t_build, "nnz_upper_per_s": nnz_upper / t_build, "phases_ms": bt, "space_seconds": t_space},
         "step_ms_min_max": [min(per), max(per)],
+        "nnz_per_rank_max_over_mean": max(nnz_per_rank) / (sum(nnz_per_rank) / len(nnz_per_rank)),
     }
     line.update(extra)
     if not args.no_cpu_baseline and world == 1:

@@ -67,6 +67,9 @@ int sqmc_b200_init(int device, int rank, int nranks, const void *id128) {
   G.nranks = nranks < 1 ? 1 : nranks;
   G.sm_count = prop.multiProcessorCount;
   SQ_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  SQ_CUDA(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
+  SQ_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
+  SQ_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
   if (G.nranks > 1) {
     if (!id128) { set_error("sqmc_b200_init: nranks>1 needs an ncclUniqueId"); return 1; }
     ncclUniqueId id;
@@ -84,6 +87,11 @@ int sqmc_b200_finalize(void) {
   G.comm = nullptr;
   if (G.stream) cudaStreamDestroy(G.stream);
   G.stream = nullptr;
+  if (G.comm_stream) cudaStreamDestroy(G.comm_stream);
+  G.comm_stream = nullptr;
+  if (G.ev_fork) cudaEventDestroy(G.ev_fork);
+  if (G.ev_join) cudaEventDestroy(G.ev_join);
+  G.ev_fork = G.ev_join = nullptr;
   G.inited = false;
   return 0;
 }
@@ -267,8 +275,7 @@ int sqmc_b200_matvec_dev(sqmc_b200_handle *h, double *x_dev, double *y_dev, void
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("matvec_dev: no matrix on this handle"); return 2; }
   cudaStream_t s = stream ? (cudaStream_t)stream : G.stream;
-  SQ_CHECK(allgather_rows(h, x_dev, s));  // no-op on one rank
-  return spmv_launch(h, x_dev, y_dev, s);
+  return spmv_gather_multiply(h, x_dev, y_dev, s);
 }
 int sqmc_b200_device_malloc(void **p, int64_t bytes) {
   SQ_CHECK(require_init());

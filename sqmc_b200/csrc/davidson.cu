@@ -209,8 +209,7 @@ struct Dav {
   // HVc = H * Vc (Vc is the local block; gathered into the handle's x buffer first)
   int apply_h(const double *Vc, double *HVc) {
     if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Vc, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SQ_CHECK(allgather_rows(h, h->d_x, s));
-    SQ_CHECK(spmv_launch(h, h->d_x, HVc, s));
+    SQ_CHECK(spmv_gather_multiply(h, h->d_x, HVc, s));
     nmv++;
     return 0;
   }

@@ -16,6 +16,8 @@ struct Global {
   int sm_count = 148;
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;  // all library work is issued on this stream unless a stream is passed in
+  cudaStream_t comm_stream = nullptr;  // NCCL all-gather of x overlapped with the local-column part of H.v
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 extern Global G;
 
@@ -114,6 +116,8 @@ struct sqmc_b200_handle {
   // ---- SpMV degree bins: row lists (local row ids) ----
   int32_t *d_bin_rows = nullptr;  // concatenated lists
   int64_t bin_off[sqmc::kNumBins + 1] = {0};
+  // nranks>1: per local row the sub-range [split_lo, split_hi) of its (ascending) entries whose columns this rank owns
+  int64_t *d_split_lo = nullptr, *d_split_hi = nullptr;
 
   // ---- group structure of the determinant list (kept for the WCSR layout; non-time-sym builds only) ----
   int64_t nA = 0, nB = 0;
@@ -155,6 +159,9 @@ int permute_scatter(const double *src, const int32_t *idx, double *dst, int64_t 
 int scale_array(double *a, int64_t n, double r, cudaStream_t s);
 int projector_epilogue(double *deltaw, const double *w, double c, int64_t n, cudaStream_t s);  // deltaw += c*w
 int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-place allgather of row blocks
+// all-gather x (own block valid on entry) and multiply; under nranks>1 the all-gather runs on the comm stream while the
+// local-column part of every row is multiplied, the remote-column part follows
+int spmv_gather_multiply(sqmc_b200_handle *h, double *x_full, double *y_dev, cudaStream_t s);
 // wcsr.cu
 int wcsr_convert(sqmc_b200_handle *h);      // CSR -> WCSR in place when the space is dense enough (or SQMC_WCSR=1)
 int wcsr_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
