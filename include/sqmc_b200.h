@@ -61,6 +61,18 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **h, int l_x, int l_y, const int3
                               double ubyn, int nup, int ndn);
 int sqmc_b200_free(sqmc_b200_handle *h);
 
+/* ---- heat-bath determinant selection (the step before the H build in every HCI iteration)
+ * Replaces get_next_det_list (hci.f90:865-1039): for the current list (n dets, caller order) with coefficients
+ * coeffs(i) = max_state |c_i| (hci.f90:369-382) generate every excitation with |H| |c_i| above eps_var
+ * (find_important_connected_dets_chem chemistry.f90:6819 / _heg heg.f90:2475), drop the ones already in the list and
+ * return the rest sorted by label: the reference appends exactly these after the old dets (hci.f90:945-991).
+ * min_H_already_done (n, in/out) follows hci.f90:1014-1016 for the old dets; the caller sets 9e99 for the new ones.
+ * chem needs the (reordered) orbital irreps first: orbital_symmetries(1:norb) of chemistry.f90:27. */
+int sqmc_b200_system_orbital_symmetries(sqmc_b200_handle *h, const int32_t *orbital_symmetries);
+int sqmc_b200_hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs,
+                         double *min_H_already_done, double eps_var, int64_t *n_new_out);
+int sqmc_b200_hci_new_dets(sqmc_b200_handle *h, void *new_up /* n_new x 16 B */, void *new_dn);
+
 /* ---- sparse H build --------------------------------------------------------
  * Replaces generate_sparse_ham_chem_upper_triangular (chemistry.f90:7639),
  * its _mpi twin (:8012), generate_sparse_ham_heg_upper_triangular

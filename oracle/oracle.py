@@ -57,6 +57,8 @@ def lib():
         L.orc_matvec_upper_mt.argtypes = [i64, vp, vp, vp, vp, vp, i32]
         L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
+        L.orc_select.restype = i64
+        L.orc_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, i64, vp, vp]
         L.orc_hci.argtypes = [vp, vp, i32, i32, i32]
         L.orc_hci_ndets.restype = i64
         L.orc_hci_ndets.argtypes = [vp]
@@ -185,6 +187,18 @@ class System:
         val = np.zeros(nnz)
         lib().orc_get_upper(self.h, _p(counts), _p(idx), _p(val))
         return counts, idx, val
+
+    def select(self, up, dn, coeffs, min_H, eps_var, cap=5_000_000):
+        """one get_next_det_list step -> (new_up, new_dn sorted by label and not in the old list, updated min_H)"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        mh = np.array(min_H, dtype=np.float64)
+        nu = np.zeros((cap, 2), dtype=np.uint64)
+        nd = np.zeros((cap, 2), dtype=np.uint64)
+        nn = lib().orc_select(self.h, len(up), _p(up), _p(dn), _p(c), _p(mh), float(eps_var), cap, _p(nu), _p(nd))
+        assert nn <= cap
+        return nu[:nn].copy(), nd[:nn].copy(), mh
 
     def hci(self, eps_var, eps_var_sched=(), n_states=1, max_iters=50, max_dets=0):
         sched = np.zeros(30)

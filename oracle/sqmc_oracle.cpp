@@ -1068,6 +1068,45 @@ static void important_connected_heg(System &S, det_t det_up, det_t det_dn, doubl
     }
 }
 
+// One selection step = get_next_det_list (hci.f90:865-1039) + find_doubly_excited (semistoch.f90:1579-2231):
+// new list = old dets in their order, then the not-yet-present selected dets sorted by label; min_H_already_done
+// updated (hci.f90:1014-1016).
+static void select_step(System &S, const std::vector<det_t> &old_up, const std::vector<det_t> &old_dn, const std::vector<double> &coeffs,
+                        std::vector<double> &min_H_done, double eps_var, std::vector<det_t> &new_up, std::vector<det_t> &new_dn) {
+  const i8b ndets_old = (i8b)old_up.size();
+  std::vector<det_t> tu, td;
+  for (i8b i = 0; i < ndets_old; i++) {
+    if (std::fabs(coeffs[i]) * min_H_done[i] > eps_var) {  // semistoch.f90:1825 / :1876
+      if (S.model == 0) important_connected_chem(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), min_H_done[i], tu, td);
+      else important_connected_heg(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), tu, td);
+    } else {
+      tu.push_back(old_up[i]); td.push_back(old_dn[i]);
+    }
+  }
+  std::vector<size_t> ord(tu.size());
+  for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return tu[a] < tu[b] || (tu[a] == tu[b] && td[a] < td[b]); });
+  std::vector<det_t> su, sd;
+  for (size_t k = 0; k < ord.size(); k++) {
+    size_t i = ord[k];
+    if (!su.empty() && su.back() == tu[i] && sd.back() == td[i]) continue;
+    su.push_back(tu[i]); sd.push_back(td[i]);
+  }
+  std::vector<size_t> oord(ndets_old);
+  for (i8b i = 0; i < ndets_old; i++) oord[i] = i;
+  std::sort(oord.begin(), oord.end(), [&](size_t a, size_t b) { return old_up[a] < old_up[b] || (old_up[a] == old_up[b] && old_dn[a] < old_dn[b]); });
+  new_up = old_up; new_dn = old_dn;
+  size_t o = 0;
+  for (size_t i = 0; i < su.size(); i++) {
+    while (o < oord.size() && (old_up[oord[o]] < su[i] || (old_up[oord[o]] == su[i] && old_dn[oord[o]] < sd[i]))) o++;
+    bool present = o < oord.size() && old_up[oord[o]] == su[i] && old_dn[oord[o]] == sd[i];
+    if (!present) { new_up.push_back(su[i]); new_dn.push_back(sd[i]); }
+  }
+  std::vector<double> mh(new_up.size(), 9.e99);
+  for (i8b i = 0; i < ndets_old; i++) mh[i] = std::min(min_H_done[i], (eps_var / std::fabs(coeffs[i]) - 1.e-14));
+  min_H_done.swap(mh);
+}
+
 // hci.f90:66-862 perform_hci (variational stage only), :865-1039 get_next_det_list,
 // :1042-1097 iterative_diagonalize
 static int perform_hci(System &S, const double *eps_var_sched /*30*/, int n_states, int max_iters, int max_dets) {
@@ -1097,44 +1136,9 @@ static int perform_hci(System &S, const double *eps_var_sched /*30*/, int n_stat
     } else {
       for (i8b i = 0; i < ndets_old; i++) coeffs[i] = old_wts[i];
     }
-    // find_doubly_excited (semistoch.f90:1825-1850 chem / :1876-1888 heg)
-    std::vector<det_t> tu, td;
-    for (i8b i = 0; i < ndets_old; i++) {
-      if (std::fabs(coeffs[i]) * min_H_done[i] > eps_var) {
-        if (S.model == 0) important_connected_chem(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), min_H_done[i], tu, td);
-        else important_connected_heg(S, old_up[i], old_dn[i], eps_var / std::fabs(coeffs[i]), tu, td);
-      } else {
-        tu.push_back(old_up[i]); td.push_back(old_dn[i]);
-      }
-    }
-    std::vector<size_t> ord(tu.size());
-    for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
-    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return tu[a] < tu[b] || (tu[a] == tu[b] && td[a] < td[b]); });
-    std::vector<det_t> su, sd;
-    for (size_t k = 0; k < ord.size(); k++) {
-      size_t i = ord[k];
-      if (!su.empty() && su.back() == tu[i] && sd.back() == td[i]) continue;
-      su.push_back(tu[i]); sd.push_back(td[i]);
-    }
-    i8b ndets_new = (i8b)su.size();
-    // new list = old dets in old order, then not-yet-present dets sorted by label (hci.f90:945-991)
-    std::vector<size_t> oord(ndets_old);
-    for (i8b i = 0; i < ndets_old; i++) oord[i] = i;
-    std::sort(oord.begin(), oord.end(), [&](size_t a, size_t b) { return old_up[a] < old_up[b] || (old_up[a] == old_up[b] && old_dn[a] < old_dn[b]); });
-    std::vector<det_t> new_up(old_up), new_dn(old_dn);
-    {
-      size_t o = 0;
-      for (i8b i = 0; i < ndets_new; i++) {
-        while (o < oord.size() && (old_up[oord[o]] < su[i] || (old_up[oord[o]] == su[i] && old_dn[oord[o]] < sd[i]))) o++;
-        bool present = o < oord.size() && old_up[oord[o]] == su[i] && old_dn[oord[o]] == sd[i];
-        if (!present) { new_up.push_back(su[i]); new_dn.push_back(sd[i]); }
-      }
-    }
-    if ((i8b)new_up.size() != ndets_new) { /* every old det is regenerated as ref => sizes agree */ ndets_new = (i8b)new_up.size(); }
-    // hci.f90:1014-1016
-    std::vector<double> mh(ndets_new, 9.e99);
-    for (i8b i = 0; i < ndets_old; i++) mh[i] = std::min(min_H_done[i], (eps_var / std::fabs(coeffs[i]) - 1.e-14));
-    min_H_done.swap(mh);
+    std::vector<det_t> new_up, new_dn;
+    select_step(S, old_up, old_dn, coeffs, min_H_done, eps_var, new_up, new_dn);
+    i8b ndets_new = (i8b)new_up.size();
     if (ndets_new == ndets_old) continue;  // hci.f90:413-417
     if (ndets_new <= (i8b)(1.00001 * ndets_old) && eps_var == eps_last) break;  // :420
     if (max_dets > 0 && ndets_new > max_dets) break;
@@ -1369,6 +1373,20 @@ void orc_projector_step(long long n, const i8b *indices, const i8b *counts, cons
   for (long long i = 0; i < n; i++) w[i] = w[i] + deltaw[i];
 }
 
+// single selection step for tests of the GPU selection kernel: returns the number of NEW dets (sorted by label) written to
+// new_up/new_dn (capacity cap); min_H (n entries) is updated in place for the old dets
+long long orc_select(void *h, long long n, const det_t *up, const det_t *dn, const double *coeffs, double *min_H, double eps_var, long long cap,
+                     det_t *new_up, det_t *new_dn) {
+  System *S = (System *)h;
+  if (S->model == 0) chem_max_double(*S); else if (S->model == 1) heg_max_double(*S);
+  std::vector<det_t> ou(up, up + n), od(dn, dn + n), nu, nd;
+  std::vector<double> c(coeffs, coeffs + n), mh(min_H, min_H + n);
+  select_step(*S, ou, od, c, mh, eps_var, nu, nd);
+  for (long long i = 0; i < n; i++) min_H[i] = mh[i];
+  long long nn = (long long)nu.size() - n;
+  for (long long i = 0; i < nn && i < cap; i++) { new_up[i] = nu[n + i]; new_dn[i] = nd[n + i]; }
+  return nn;
+}
 int orc_hci(void *h, const double *eps_var_sched30, int n_states, int max_iters, int max_dets) {
   return perform_hci(*(System *)h, eps_var_sched30, n_states, max_iters, max_dets);
 }

@@ -18,7 +18,8 @@ SYMBOLS = [
     "sqmc_b200_local_rows", "sqmc_b200_diagonal", "sqmc_b200_matvec", "sqmc_b200_projector",
     "sqmc_b200_scale_values", "sqmc_b200_davidson", "sqmc_b200_matvec_dev", "sqmc_b200_device_malloc",
     "sqmc_b200_device_free", "sqmc_b200_memcpy_h2d", "sqmc_b200_memcpy_d2h", "sqmc_b200_device_sync",
-    "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row",
+    "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
+    "sqmc_b200_hci_new_dets",
 ]
 
 
@@ -65,6 +66,9 @@ def load():
     L.sqmc_b200_build_times.argtypes = [vp, vp]
     L.sqmc_b200_partition_rows.argtypes = [vp, i64, i32, vp]
     L.sqmc_b200_get_row.argtypes = [vp, i64, i64, vp, vp, vp]
+    L.sqmc_b200_system_orbital_symmetries.argtypes = [vp, vp]
+    L.sqmc_b200_hci_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, vp]
+    L.sqmc_b200_hci_new_dets.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

@@ -56,6 +56,8 @@ class SparseHamiltonian:
             c2 = np.asfortranarray(system.combine_2, dtype=np.int32)
             check(L.sqmc_b200_system_chem(C.byref(self._h), system.norb, system.nup, system.ndn, _p(integrals), len(integrals),
                                           c2.ctypes.data_as(C.c_void_p), int(system.time_sym), int(system.z)))
+            sym = np.ascontiguousarray(system.orbital_symmetries, dtype=np.int32)
+            check(L.sqmc_b200_system_orbital_symmetries(self._h, _p(sym)))
         elif isinstance(system, systems.HegSystem):
             kv = np.ascontiguousarray(system.k_vectors, dtype=np.float64)
             check(L.sqmc_b200_system_heg(C.byref(self._h), system.norb, system.n_dim, _p(kv), float(system.length_cell),
@@ -78,6 +80,20 @@ class SparseHamiltonian:
             self.close()
         except Exception:
             pass
+
+    # ---- selection -----------------------------------------------------
+    def get_next_det_list(self, dets_up, dets_dn, coeffs, min_H_already_done, eps_var):
+        """hci.f90:865 get_next_det_list: returns (new_up, new_dn) = the determinants to append (sorted by label, not yet in
+        the list) and the updated min_H_already_done of the old determinants."""
+        up, dn = dets_to_u64(dets_up), dets_to_u64(dets_dn)
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        mh = np.array(min_H_already_done, dtype=np.float64)
+        nn = C.c_int64()
+        check(self._L.sqmc_b200_hci_select(self._h, len(up), _p(up), _p(dn), _p(c), _p(mh), float(eps_var), C.byref(nn)))
+        nu = np.zeros((nn.value, 2), dtype=np.uint64)
+        nd = np.zeros((nn.value, 2), dtype=np.uint64)
+        check(self._L.sqmc_b200_hci_new_dets(self._h, _p(nu), _p(nd)))
+        return nu, nd, mh
 
     # ---- build ---------------------------------------------------------
     def generate_sparse_ham_upper_triangular(self, dets_up, dets_dn, ndet_old=0):

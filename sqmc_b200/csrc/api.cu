@@ -173,6 +173,7 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const in
 int sqmc_b200_free(sqmc_b200_handle *h) {
   if (!h) return 0;
   free_matrix(h);
+  if (h->d_orbsym) cudaFree(h->d_orbsym);
   if (h->d_integrals) cudaFree(h->d_integrals);
   if (h->d_combine_2) cudaFree(h->d_combine_2);
   if (h->d_kvec) cudaFree(h->d_kvec);
@@ -182,6 +183,27 @@ int sqmc_b200_free(sqmc_b200_handle *h) {
   return 0;
 }
 
+int sqmc_b200_system_orbital_symmetries(sqmc_b200_handle *h, const int32_t *orbital_symmetries) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("orbital_symmetries: null handle"); return 2; }
+  if (!h->d_orbsym) SQ_CUDA(cudaMalloc(&h->d_orbsym, h->T.norb * sizeof(int32_t)));
+  SQ_CUDA(cudaMemcpy(h->d_orbsym, orbital_symmetries, h->T.norb * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+int sqmc_b200_hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H_already_done,
+                         double eps_var, int64_t *n_new_out) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("hci_select: null handle"); return 2; }
+  return hci_select(h, n, dets_up, dets_dn, coeffs, min_H_already_done, eps_var, n_new_out);
+}
+int sqmc_b200_hci_new_dets(sqmc_b200_handle *h, void *new_up, void *new_dn) {
+  if (!h) { set_error("hci_new_dets: null handle"); return 2; }
+  if (!h->sel_new_up.empty()) {
+    memcpy(new_up, h->sel_new_up.data(), h->sel_new_up.size() * sizeof(uint64_t));
+    memcpy(new_dn, h->sel_new_dn.data(), h->sel_new_dn.size() * sizeof(uint64_t));
+  }
+  return 0;
+}
 int sqmc_b200_build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t ndet_old,
                       int64_t *nnz_upper_out) {
   SQ_CHECK(require_init());

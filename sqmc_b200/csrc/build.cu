@@ -529,6 +529,46 @@ static int exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n,
   return 0;
 }
 
+// ---- helpers shared with select.cu
+// upload n 16-byte determinants (host) and split them into NW-word strings (device, caller allocates n*NW words)
+int upload_dets(int NW, int norb, const void *host16, uint64_t *out, int64_t n, cudaStream_t s) {
+  DevBuf<uint64_t> raw;
+  DevBuf<int> bad;
+  SQ_CHECK(raw.alloc(2 * n));
+  SQ_CHECK(bad.alloc(1));
+  SQ_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  uint64_t m0 = 0, m1 = 0;
+  if (norb < 64) { m0 = ~((1ull << norb) - 1ull); m1 = ~0ull; }
+  else if (norb == 64) { m0 = 0; m1 = ~0ull; }
+  else { m0 = 0; m1 = (norb >= 128) ? 0ull : ~((1ull << (norb - 64)) - 1ull); }
+  SQ_CUDA(cudaMemcpyAsync(raw.p, host16, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+  if (NW == 1) split_dets_kernel<1><<<nblocks(n), kThreads, 0, s>>>(raw.p, out, n, bad.p, m0, m1);
+  else split_dets_kernel<2><<<nblocks(n), kThreads, 0, s>>>(raw.p, out, n, bad.p, m0, m1);
+  SQ_LAUNCH_CHECK();
+  int hbad = 0;
+  SQ_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  if (hbad) { set_error("a determinant occupies an orbital beyond norb=%d", norb); return 2; }
+  return 0;
+}
+// idx (device, n entries, initialised here) := permutation sorting the pairs (a, b) ascending, a most significant
+int sort_pairs_index(int NW, int norb, const uint64_t *a, const uint64_t *b, int32_t *idx, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  iota_kernel<<<nblocks(n), kThreads, 0, s>>>(idx, n);
+  SQ_LAUNCH_CHECK();
+  std::vector<KeyWord> words;
+  for (int w = 0; w < NW; w++) words.push_back({b, NW, w, std::min(64, norb - 64 * w)});
+  for (int w = 0; w < NW; w++) words.push_back({a, NW, w, std::min(64, norb - 64 * w)});
+  return sort_by_words(words, idx, n, s);
+}
+int gather_strings(int NW, const uint64_t *src, const int32_t *idx, uint64_t *out, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (NW == 1) gather_bits_kernel<1><<<nblocks(n), kThreads, 0, s>>>(src, idx, out, n);
+  else gather_bits_kernel<2><<<nblocks(n), kThreads, 0, s>>>(src, idx, out, n);
+  SQ_LAUNCH_CHECK();
+  return 0;
+}
+
 void free_matrix(sqmc_b200_handle *h) {
   auto F = [](auto *&p) {
     if (p) cudaFree(p);

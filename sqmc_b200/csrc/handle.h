@@ -140,6 +140,9 @@ struct sqmc_b200_handle {
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
   double *d_tmp = nullptr; // n (caller order staging)
+  // ---- heat-bath selection (select.cu) ----
+  int32_t *d_orbsym = nullptr;        // [norb] orbital irreps (chem), set by sqmc_b200_system_orbital_symmetries
+  std::vector<uint64_t> sel_new_up, sel_new_dn;  // result of the last hci_select (host, 16 B per det)
   double build_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [5] candidates (local) [6] alpha groups [7] beta groups
 };
 
@@ -151,6 +154,12 @@ int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double 
 int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
 void free_matrix(sqmc_b200_handle *h);
 void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *starts);
+int upload_dets(int NW, int norb, const void *host16, uint64_t *out, int64_t n, cudaStream_t s);
+int sort_pairs_index(int NW, int norb, const uint64_t *a, const uint64_t *b, int32_t *idx, int64_t n, cudaStream_t s);
+int gather_strings(int NW, const uint64_t *src, const int32_t *idx, uint64_t *out, int64_t n, cudaStream_t s);
+// select.cu
+int hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,
+               int64_t *n_new_out);
 // spmv.cu
 int spmv_setup_bins(sqmc_b200_handle *h);
 int spmv_launch(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);

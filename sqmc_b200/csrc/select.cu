@@ -1,0 +1,355 @@
+// select.cu -- heat-bath determinant selection on the device: SURVEY.md section 8(f) item 1, the step
+// immediately before the H build in every HCI iteration.
+//
+// Replaces get_next_det_list (hci.f90:865-1039) + find_doubly_excited (semistoch.f90:1579-2231) with
+// find_important_connected_dets_chem (chemistry.f90:6819-7159) / find_important_connected_dets_heg
+// (heg.f90:2475-2727).  For every determinant i of the current list with coefficient c_i and
+// |c_i| * min_H_already_done(i) > eps_var the excitations with |H| * |c_i| above eps_var are generated:
+//   chem singles  (same irrep only): eps' <= |H| <= min_H_already_done(i)       (:6956-6959)
+//   chem doubles                   : eps' <  |H| <= min_H_already_done(i)       (:7042-7046)
+//   heg  doubles (momentum conserving): eps' < |H|                              (heg.f90:2609,2625)
+// with eps' = eps_var/|c_i|; the reference walks per-pair tables sorted by |H| (dtm_hb) only to prune the
+// search -- the selected set is defined by these inequalities, so the kernel enumerates all excitations of a
+// determinant (one warp per determinant) and evaluates the same element arithmetic (elements.cuh, no FMA).
+// Time-reversal symmetry: new_up == new_dn dropped for z<0, the time-reversed partner of det i dropped, results
+// mapped to the representative up <= dn (:6949-6952,6966-6971,7110-7132).
+// The generated determinants are sorted by label, made unique, and those already in the list removed: what
+// remains is exactly the tail the reference appends to its list (hci.f90:945-991).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "handle.h"
+
+namespace sqmc {
+
+static const int kSelMaxOrb = 128;
+
+template <int NW>
+struct SelCtx {
+  ModelTables T;
+  const int32_t *orbsym;
+  const uint64_t *up, *dn;
+  const double *coeffs, *min_H;
+  double eps_var;
+  int64_t n;
+};
+
+__device__ __forceinline__ int nth_set(const uint8_t *list, int k) { return list[k]; }
+
+// one warp per determinant; FILL=false counts, FILL=true writes (up,dn) of the selected determinants at out_ptr[i]
+template <int NW, bool FILL>
+__global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_begin, int64_t i_end, int32_t *counts, const int64_t *out_ptr,
+                                                     uint64_t *out_up, uint64_t *out_dn) {
+  __shared__ uint8_t s_occ[4][2][kSelMaxOrb], s_virt[4][2][kSelMaxOrb];
+  extern __shared__ int32_t c2s[];
+  const ModelTables &T = S.T;
+  const int32_t *c2 = T.combine_2;
+  if (T.model == MODEL_CHEM) {
+    const int n1 = T.norb + 1;
+    for (int k = threadIdx.x; k < n1 * n1; k += blockDim.x) c2s[k] = T.combine_2[k];
+    __syncthreads();
+    c2 = c2s;
+  }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t i = i_begin + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (i >= i_end) return;
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  const Bits<NW> u = b_load<NW>(S.up, i), d = b_load<NW>(S.dn, i);
+  const double c = fabs(S.coeffs[i]), minH = S.min_H[i];
+  const int norb = T.norb;
+  const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
+  int64_t base = FILL ? out_ptr[i - i_begin] : 0;
+  int cnt = 0;
+  auto emit = [&](bool keep, Bits<NW> nu, Bits<NW> nd) {
+    if (keep && ts && b_lt(nd, nu)) { Bits<NW> t = nu; nu = nd; nd = t; }  // representative up <= dn
+    unsigned m = __ballot_sync(full, keep);
+    if (FILL && keep) {
+      int64_t q = base + cnt + __popc(m & lt);
+      b_store<NW>(out_up, q, nu);
+      b_store<NW>(out_dn, q, nd);
+    }
+    cnt += __popc(m);
+  };
+  emit(lane == 0, u, d);  // the determinant itself comes first (chemistry.f90:6893-6895)
+  const bool expand = c * minH > S.eps_var;  // semistoch.f90:1825
+  if (expand) {  // warp-uniform
+    const double eps = S.eps_var / c;
+    // occupied / virtual orbital lists of both spins (lane 0 of the warp fills them)
+    uint8_t *occ_u = s_occ[wib][0], *occ_d = s_occ[wib][1], *vir_u = s_virt[wib][0], *vir_d = s_virt[wib][1];
+    int nu_ = 0, nd_ = 0, nvu = 0, nvd = 0;
+    if (lane == 0) {
+      for (int o = 0; o < norb; o++) {
+        if (b_test(u, o)) occ_u[nu_++] = (uint8_t)o; else vir_u[nvu++] = (uint8_t)o;
+        if (b_test(d, o)) occ_d[nd_++] = (uint8_t)o; else vir_d[nvd++] = (uint8_t)o;
+      }
+    }
+    nu_ = __shfl_sync(full, nu_, 0); nd_ = __shfl_sync(full, nd_, 0); nvu = __shfl_sync(full, nvu, 0); nvd = __shfl_sync(full, nvd, 0);
+    __syncwarp();
+    ChemCtx C{T.integrals, c2, T.norb + 1, T.enuc, T.sqrt2, T.sqrt2inv, T.z};
+    HegCtx Hg{T.k_vectors, T.n_dim, T.length_cell};
+    auto ts_excluded = [&](const Bits<NW> &nu, const Bits<NW> &nd) {
+      if (!ts) return false;
+      if (b_eq(nu, nd) && T.z < 0) return true;
+      return b_eq(u, nd) && b_eq(d, nu);
+    };
+    // ---- singles (chem only)
+    if (T.model == MODEL_CHEM) {
+      for (int spin = 0; spin < 2; spin++) {
+        const uint8_t *occ = spin == 0 ? occ_u : occ_d, *vir = spin == 0 ? vir_u : vir_d;
+        const int no = spin == 0 ? nu_ : nd_, nv = spin == 0 ? nvu : nvd;
+        const int tot = no * nv;
+        for (int b0 = 0; b0 < tot; b0 += 32) {
+          const int f = b0 + lane;
+          bool keep = false;
+          Bits<NW> nu = u, nd = d;
+          if (f < tot) {
+            const int p = occ[f / nv], r = vir[f % nv];
+            if (S.orbsym[p] == S.orbsym[r]) {
+              if (spin == 0) { b_clear(nu, p); b_set(nu, r); } else { b_clear(nd, p); b_set(nd, r); }
+              if (!ts_excluded(nu, nd)) {
+                const double me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 1));
+                keep = !(me < eps) && !(me > minH);
+              }
+            }
+          }
+          emit(keep, nu, nd);
+        }
+      }
+    }
+    // ---- same-spin doubles
+    for (int spin = 0; spin < 2; spin++) {
+      const uint8_t *occ = spin == 0 ? occ_u : occ_d, *vir = spin == 0 ? vir_u : vir_d;
+      const int no = spin == 0 ? nu_ : nd_, nv = spin == 0 ? nvu : nvd;
+      const int npo = no * (no - 1) / 2, npv = nv * (nv - 1) / 2;
+      const int tot = npo * npv;
+      for (int b0 = 0; b0 < tot; b0 += 32) {
+        const int f = b0 + lane;
+        bool keep = false;
+        Bits<NW> nu = u, nd = d;
+        if (f < tot) {
+          int po = f / npv, pv = f % npv;
+          // unrank pairs (a<b): pair index -> (a,b)
+          int a = 0;
+          while (po >= no - 1 - a) { po -= no - 1 - a; a++; }
+          const int bq = a + 1 + po;
+          int r = 0;
+          while (pv >= nv - 1 - r) { pv -= nv - 1 - r; r++; }
+          const int sq = r + 1 + pv;
+          Bits<NW> &tgt = spin == 0 ? nu : nd;
+          b_clear(tgt, occ[a]); b_clear(tgt, occ[bq]); b_set(tgt, vir[r]); b_set(tgt, vir[sq]);
+          if (!ts_excluded(nu, nd)) {
+            double me;
+            if (T.model == MODEL_CHEM) me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 2));
+            else me = fabs(heg_hamiltonian(Hg, u, d, nu, nd));
+            keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
+          }
+        }
+        emit(keep, nu, nd);
+      }
+    }
+    // ---- opposite-spin doubles
+    {
+      const int tu = nu_ * nvu, td = nd_ * nvd;
+      const int64_t tot = (int64_t)tu * td;
+      for (int64_t b0 = 0; b0 < tot; b0 += 32) {
+        const int64_t f = b0 + lane;
+        bool keep = false;
+        Bits<NW> nu = u, nd = d;
+        if (f < tot) {
+          const int fu = (int)(f / td), fd = (int)(f % td);
+          b_clear(nu, occ_u[fu / nvu]); b_set(nu, vir_u[fu % nvu]);
+          b_clear(nd, occ_d[fd / nvd]); b_set(nd, vir_d[fd % nvd]);
+          if (!ts_excluded(nu, nd)) {
+            double me;
+            if (T.model == MODEL_CHEM) me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 2));
+            else me = fabs(heg_hamiltonian(Hg, u, d, nu, nd));
+            keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
+          }
+        }
+        emit(keep, nu, nd);
+      }
+    }
+  }
+  if (!FILL && lane == 0) counts[i - i_begin] = cnt;
+}
+
+template <int NW>
+__global__ void uniq_flag_kernel(const uint64_t *a, const uint64_t *b, int32_t *flag, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  flag[t] = (t == 0) ? 1 : ((b_eq(b_load<NW>(a, t), b_load<NW>(a, t - 1)) && b_eq(b_load<NW>(b, t), b_load<NW>(b, t - 1))) ? 0 : 1);
+}
+// flag[t] &= (a[t], b[t]) not in the sorted list (oa, ob)
+template <int NW>
+__global__ void not_in_list_kernel(const uint64_t *a, const uint64_t *b, const uint64_t *oa, const uint64_t *ob, int64_t nold, int32_t *flag, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m || !flag[t]) return;
+  const Bits<NW> x = b_load<NW>(a, t), y = b_load<NW>(b, t);
+  int64_t lo = 0, hi = nold;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    const Bits<NW> ma = b_load<NW>(oa, mid), mb = b_load<NW>(ob, mid);
+    const bool less = b_lt(ma, x) || (b_eq(ma, x) && b_lt(mb, y));
+    if (less) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo < nold && b_eq(b_load<NW>(oa, lo), x) && b_eq(b_load<NW>(ob, lo), y)) flag[t] = 0;
+}
+
+// sort (a,b) pairs by label, keep the unique ones that are not in the sorted old list; returns them compacted in (ra, rb)
+template <int NW>
+static int sort_unique_new(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, int64_t m, const uint64_t *oa, const uint64_t *ob, int64_t nold,
+                           DevBuf<uint64_t> &ra, DevBuf<uint64_t> &rb, int64_t &mout, cudaStream_t s) {
+  mout = 0;
+  if (m == 0) return 0;
+  DevBuf<int32_t> idx, flag, sel;
+  DevBuf<uint64_t> sa, sb;
+  SQ_CHECK(idx.alloc(m));
+  SQ_CHECK(sort_pairs_index(NW, norb, a.p, b.p, idx.p, m, s));
+  SQ_CHECK(sa.alloc(m * NW));
+  SQ_CHECK(sb.alloc(m * NW));
+  SQ_CHECK(gather_strings(NW, a.p, idx.p, sa.p, m, s));
+  SQ_CHECK(gather_strings(NW, b.p, idx.p, sb.p, m, s));
+  SQ_CHECK(flag.alloc(m));
+  const unsigned g = (unsigned)div_up(m, 256);
+  uniq_flag_kernel<NW><<<g, 256, 0, s>>>(sa.p, sb.p, flag.p, m);
+  SQ_LAUNCH_CHECK();
+  if (nold > 0) {
+    not_in_list_kernel<NW><<<g, 256, 0, s>>>(sa.p, sb.p, oa, ob, nold, flag.p, m);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CHECK(sel.alloc(m));
+  DevBuf<int32_t> num;
+  SQ_CHECK(num.alloc(1));
+  cub::CountingInputIterator<int32_t> it(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, it, flag.p, sel.p, num.p, (int)m, s);
+  DevBuf<char> tmp;
+  SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+  SQ_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, it, flag.p, sel.p, num.p, (int)m, s));
+  g_launch_count += 2;
+  int32_t k = 0;
+  SQ_CUDA(cudaMemcpyAsync(&k, num.p, 4, cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  mout = k;
+  SQ_CHECK(ra.alloc(std::max<int64_t>(mout, 1) * NW));
+  SQ_CHECK(rb.alloc(std::max<int64_t>(mout, 1) * NW));
+  SQ_CHECK(gather_strings(NW, sa.p, sel.p, ra.p, mout, s));
+  SQ_CHECK(gather_strings(NW, sb.p, sel.p, rb.p, mout, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <int NW>
+static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,
+                       int64_t *n_new_out) {
+  cudaStream_t s = G.stream;
+  const ModelTables &T = h->T;
+  DevBuf<uint64_t> up, dn, sup, sdn;
+  DevBuf<double> dc, dm;
+  SQ_CHECK(up.alloc(n * NW));
+  SQ_CHECK(dn.alloc(n * NW));
+  SQ_CHECK(upload_dets(NW, T.norb, dets_up, up.p, n, s));
+  SQ_CHECK(upload_dets(NW, T.norb, dets_dn, dn.p, n, s));
+  SQ_CHECK(dc.alloc(n));
+  SQ_CHECK(dm.alloc(n));
+  SQ_CUDA(cudaMemcpyAsync(dc.p, coeffs, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  SQ_CUDA(cudaMemcpyAsync(dm.p, min_H, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  // sorted copy of the current list for the membership test
+  {
+    DevBuf<int32_t> idx;
+    SQ_CHECK(idx.alloc(n));
+    SQ_CHECK(sort_pairs_index(NW, T.norb, up.p, dn.p, idx.p, n, s));
+    SQ_CHECK(sup.alloc(n * NW));
+    SQ_CHECK(sdn.alloc(n * NW));
+    SQ_CHECK(gather_strings(NW, up.p, idx.p, sup.p, n, s));
+    SQ_CHECK(gather_strings(NW, dn.p, idx.p, sdn.p, n, s));
+  }
+  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_var, n};
+  const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
+  // count pass over all determinants
+  DevBuf<int32_t> counts;
+  SQ_CHECK(counts.alloc(n + 1));
+  SQ_CUDA(cudaMemsetAsync(counts.p, 0, (n + 1) * sizeof(int32_t), s));
+  select_kernel<NW, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr);
+  SQ_LAUNCH_CHECK();
+  std::vector<int32_t> hc(n + 1);
+  SQ_CUDA(cudaMemcpyAsync(hc.data(), counts.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  std::vector<int64_t> prefix(n + 1, 0);
+  for (int64_t i = 0; i < n; i++) prefix[i + 1] = prefix[i] + hc[i];
+  // chunks of determinants bounded by generated candidates; per chunk: fill, sort, unique, drop members of the list
+  const int64_t kChunk = 1ll << 27;
+  DevBuf<uint64_t> acc_a, acc_b;  // unique new determinants found so far (unsorted union of the chunk results)
+  int64_t acc_n = 0;
+  int64_t i0 = 0;
+  while (i0 < n) {
+    int64_t i1 = std::upper_bound(prefix.begin() + i0 + 1, prefix.end(), prefix[i0] + kChunk) - prefix.begin() - 1;
+    if (i1 <= i0) i1 = i0 + 1;
+    if (i1 > n) i1 = n;
+    const int64_t m = prefix[i1] - prefix[i0];
+    if (m >= (1ll << 31)) { set_error("hci_select: one determinant generates too many connections"); return 2; }
+    DevBuf<uint64_t> ca, cb, ra, rb;
+    DevBuf<int64_t> optr;
+    SQ_CHECK(ca.alloc(std::max<int64_t>(m, 1) * NW));
+    SQ_CHECK(cb.alloc(std::max<int64_t>(m, 1) * NW));
+    SQ_CHECK(optr.alloc(i1 - i0 + 1));
+    std::vector<int64_t> hp(prefix.begin() + i0, prefix.begin() + i1 + 1);
+    for (auto &v : hp) v -= prefix[i0];
+    SQ_CUDA(cudaMemcpyAsync(optr.p, hp.data(), hp.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    select_kernel<NW, true><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaStreamSynchronize(s));
+    int64_t mu = 0;
+    SQ_CHECK(sort_unique_new<NW>(T.norb, ca, cb, m, sup.p, sdn.p, n, ra, rb, mu, s));
+    if (mu > 0) {  // append to the accumulator
+      DevBuf<uint64_t> na, nb;
+      SQ_CHECK(na.alloc((acc_n + mu) * NW));
+      SQ_CHECK(nb.alloc((acc_n + mu) * NW));
+      if (acc_n) {
+        SQ_CUDA(cudaMemcpyAsync(na.p, acc_a.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(nb.p, acc_b.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+      }
+      SQ_CUDA(cudaMemcpyAsync(na.p + acc_n * NW, ra.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaMemcpyAsync(nb.p + acc_n * NW, rb.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaStreamSynchronize(s));
+      acc_a.release(); acc_b.release();
+      acc_a.p = na.take(); acc_b.p = nb.take();
+      acc_n += mu;
+    }
+    i0 = i1;
+  }
+  // final sort + unique across chunks (members of the list are already gone)
+  DevBuf<uint64_t> fa, fb;
+  int64_t nf = 0;
+  SQ_CHECK(sort_unique_new<NW>(T.norb, acc_a, acc_b, acc_n, nullptr, nullptr, 0, fa, fb, nf, s));
+  h->sel_new_up.assign((size_t)nf * 2, 0);
+  h->sel_new_dn.assign((size_t)nf * 2, 0);
+  if (nf > 0) {
+    std::vector<uint64_t> ha(nf * NW), hb(nf * NW);
+    SQ_CUDA(cudaMemcpy(ha.data(), fa.p, nf * NW * 8, cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(hb.data(), fb.p, nf * NW * 8, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < nf; k++)
+      for (int w = 0; w < NW; w++) {
+        h->sel_new_up[2 * k + w] = ha[k * NW + w];
+        h->sel_new_dn[2 * k + w] = hb[k * NW + w];
+      }
+  }
+  // min_H_already_done of the current dets (hci.f90:1015); new dets start at 9e99 on the caller's side (:1016)
+  for (int64_t i = 0; i < n; i++) min_H[i] = std::min(min_H[i], eps_var / fabs(coeffs[i]) - 1.e-14);
+  *n_new_out = nf;
+  return 0;
+}
+
+int hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,
+               int64_t *n_new_out) {
+  if (n <= 0) { set_error("hci_select: n must be positive"); return 2; }
+  if (h->T.model == MODEL_HUBBARDK) { set_error("hci_select: only chem and heg (hci.f90:1073-1075)"); return 2; }
+  if (h->T.model == MODEL_CHEM && !h->d_orbsym) { set_error("hci_select: call sqmc_b200_system_orbital_symmetries first"); return 2; }
+  if (!(eps_var >= 0.0)) { set_error("hci_select: eps_var must be >= 0 (hci.f90:932)"); return 2; }
+  return h->NW == 1 ? select_impl<1>(h, n, dets_up, dets_dn, coeffs, min_H, eps_var, n_new_out)
+                    : select_impl<2>(h, n, dets_up, dets_dn, coeffs, min_H, eps_var, n_new_out);
+}
+
+}  // namespace sqmc
