@@ -1,0 +1,148 @@
+// sqmc_b200_host.hpp -- C++ host-side mirror of the reference's Fortran interface for the hot path, written above the
+// C ABI of libsqmc_b200.so (include/sqmc_b200.h).  The reference is compiled Fortran and this image has no Fortran
+// compiler, so this header plays the role of fortran/sqmc_b200_iface.f90 for compiled callers: the routines keep the
+// reference's names, argument order and meaning (allocatable intent(out) arrays become std::vector&), and errors throw
+// (the reference `stop`s).  One `model_system` object stands for the module globals the Fortran routines read.
+//
+//   generate_sparse_ham_chem_upper_triangular      chemistry.f90:7639
+//   generate_sparse_ham_heg_upper_triangular       heg.f90:3553
+//   generate_sparse_ham_hubbardk_upper_triangular  hubbard.f90:9435
+//   fast_sparse_matrix_multiply_upper_triangular   more_tools.f90:3622
+//   davidson_sparse                                more_tools.f90:2018
+//   deterministic projector step                   do_walk.f90:2255-2325
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/sqmc_b200.h"
+
+namespace sqmc_b200_host {
+
+typedef unsigned __int128 ik;  // integer(ik), types.f90:26
+typedef int64_t i8b;           // types.f90:18
+typedef double rk;             // types.f90:27
+
+inline void check(int rc) {
+  if (rc != 0) throw std::runtime_error(std::string("sqmc_b200: ") + sqmc_b200_last_error());
+}
+
+// sparse_mat of commons/common_selected_ci.f90:26-31: only ndet is consulted (rows already built)
+struct sparse_mat {
+  i8b ndet = 0;
+};
+
+// stands for the module globals of chemistry.f90 / heg.f90 / hubbard.f90 that the builders read
+class model_system {
+ public:
+  sqmc_b200_handle *h = nullptr;
+  i8b n = 0;
+  static void init(int device = 0) {
+    static bool done = false;
+    if (!done) check(sqmc_b200_init(device, 0, 1, nullptr));
+    done = true;
+  }
+  static model_system chem(int norb, int nup, int ndn, const std::vector<rk> &integrals, const std::vector<int32_t> &combine_2, bool time_sym, int z) {
+    model_system s;
+    init();
+    check(sqmc_b200_system_chem(&s.h, norb, nup, ndn, integrals.data(), (i8b)integrals.size(), combine_2.data(), time_sym ? 1 : 0, z));
+    return s;
+  }
+  static model_system heg(int norb, int n_dim, const std::vector<rk> &k_vectors, rk length_cell, int nup, int ndn) {
+    model_system s;
+    init();
+    check(sqmc_b200_system_heg(&s.h, norb, n_dim, k_vectors.data(), length_cell, nup, ndn));
+    return s;
+  }
+  static model_system hubbardk(int l_x, int l_y, const std::vector<int32_t> &k_vectors, const std::vector<rk> &k_energies, rk ubyn, int nup, int ndn) {
+    model_system s;
+    init();
+    check(sqmc_b200_system_hubbardk(&s.h, l_x, l_y, k_vectors.data(), k_energies.data(), ubyn, nup, ndn));
+    return s;
+  }
+  model_system() = default;
+  model_system(model_system &&o) noexcept : h(o.h), n(o.n) { o.h = nullptr; }
+  model_system &operator=(model_system &&o) noexcept {
+    if (this != &o) { release(); h = o.h; n = o.n; o.h = nullptr; }
+    return *this;
+  }
+  model_system(const model_system &) = delete;
+  model_system &operator=(const model_system &) = delete;
+  ~model_system() { release(); }
+
+ private:
+  void release() {
+    if (h) sqmc_b200_free(h);
+    h = nullptr;
+  }
+};
+
+namespace detail {
+inline void build(model_system &S, const std::vector<ik> &dets_up, const std::vector<ik> &dets_dn, std::vector<i8b> &H_indices,
+                  std::vector<i8b> &H_nonzero_elements, std::vector<rk> &H_values, bool hf_to_psit, sparse_mat *sparse_ham, rk *average_connections) {
+  if (dets_up.size() != dets_dn.size() || dets_up.empty()) throw std::runtime_error("sqmc_b200: bad determinant list");
+  const i8b n = (i8b)dets_up.size();
+  i8b nnz = 0;
+  check(sqmc_b200_set_hf_to_psit(S.h, hf_to_psit ? 1 : 0));
+  check(sqmc_b200_build_h(S.h, n, dets_up.data(), dets_dn.data(), sparse_ham ? sparse_ham->ndet : 0, &nnz));
+  S.n = n;
+  H_nonzero_elements.assign(n, 0);
+  H_indices.assign(nnz, 0);
+  H_values.assign(nnz, 0.0);
+  check(sqmc_b200_export_upper(S.h, H_nonzero_elements.data(), H_indices.data(), H_values.data()));
+  if (sparse_ham) sparse_ham->ndet = n;                       // chemistry.f90:7989
+  if (average_connections) *average_connections = (rk)nnz / n;  // chemistry.f90:8006
+}
+}  // namespace detail
+
+// chemistry.f90:7639.  time_sym_on is carried by the model_system (module variable time_sym); hf_to_psit is ignored by the
+// reference's partial-connection branch (:7721) and therefore here.
+inline void generate_sparse_ham_chem_upper_triangular(model_system &S, const std::vector<ik> &dets_up, const std::vector<ik> &dets_dn,
+                                                      std::vector<i8b> &H_indices, std::vector<i8b> &H_nonzero_elements, std::vector<rk> &H_values,
+                                                      bool /*time_sym_on*/, bool /*hf_to_psit*/, sparse_mat *sparse_ham = nullptr,
+                                                      rk *average_connections = nullptr) {
+  detail::build(S, dets_up, dets_dn, H_indices, H_nonzero_elements, H_values, false, sparse_ham, average_connections);
+}
+// heg.f90:3553
+inline void generate_sparse_ham_heg_upper_triangular(model_system &S, const std::vector<ik> &dets_up, const std::vector<ik> &dets_dn,
+                                                     std::vector<i8b> &H_indices, std::vector<i8b> &H_nonzero_elements, std::vector<rk> &H_values,
+                                                     bool /*time_sym_on*/, bool /*hf_to_psit*/, sparse_mat *sparse_ham = nullptr) {
+  detail::build(S, dets_up, dets_dn, H_indices, H_nonzero_elements, H_values, false, sparse_ham, nullptr);
+}
+// hubbard.f90:9435 (hf_to_psit honoured: row 1 = single zero diagonal entry, :9636-9643)
+inline void generate_sparse_ham_hubbardk_upper_triangular(model_system &S, const std::vector<ik> &dets_up, const std::vector<ik> &dets_dn,
+                                                          std::vector<i8b> &H_indices, std::vector<i8b> &H_nonzero_elements,
+                                                          std::vector<rk> &H_values, bool hf_to_psit) {
+  detail::build(S, dets_up, dets_dn, H_indices, H_nonzero_elements, H_values, hf_to_psit, nullptr, nullptr);
+}
+
+// more_tools.f90:3622: answer = H . vector with the matrix the last generate_sparse_ham_* left resident on the device
+// (the reference passes matrix_indices / nelem_nonzero / matrix_values explicitly; they are the arrays returned above)
+inline void fast_sparse_matrix_multiply_upper_triangular(model_system &S, int n, const std::vector<rk> &vector, std::vector<rk> &answer) {
+  if ((i8b)n != S.n || (i8b)vector.size() < S.n) throw std::runtime_error("sqmc_b200: matvec size mismatch");
+  answer.assign(n, 0.0);
+  check(sqmc_b200_matvec(S.h, vector.data(), answer.data(), 1, n));
+}
+
+// more_tools.f90:2018: final_vector(n, n_states) column-major, lowest_eigenvalues(n_states); initial_vector optional
+inline void davidson_sparse(model_system &S, int n, int n_states, std::vector<rk> &final_vector, std::vector<rk> &lowest_eigenvalues,
+                            const std::vector<rk> *initial_vector = nullptr, std::vector<rk> *iteration_eigenvalues = nullptr) {
+  if ((i8b)n != S.n) throw std::runtime_error("sqmc_b200: davidson size mismatch");
+  final_vector.assign((size_t)n * n_states, 0.0);
+  lowest_eigenvalues.assign(n_states, 0.0);
+  std::vector<rk> log(1024 * (size_t)n_states);
+  int nmv = 0, nlog = 0;
+  check(sqmc_b200_davidson(S.h, n_states, initial_vector ? initial_vector->data() : nullptr, final_vector.data(), lowest_eigenvalues.data(), 1.e-10,
+                           50, &nmv, log.data(), 1024, &nlog));
+  if (iteration_eigenvalues) iteration_eigenvalues->assign(log.begin(), log.begin() + (size_t)std::min(nlog, 1024) * n_states);
+}
+
+// do_walk.f90:2259-2290 with the stored matrix already scaled by -tau (semistoch.f90:657,880)
+inline void scale_values(model_system &S, rk ratio) { check(sqmc_b200_scale_values(S.h, ratio)); }
+inline void deterministic_projector_step(model_system &S, rk tau, rk e_trial, const std::vector<rk> &imp_wt, std::vector<rk> &deltaw) {
+  deltaw.assign(S.n, 0.0);
+  check(sqmc_b200_projector(S.h, tau, e_trial, imp_wt.data(), deltaw.data()));
+}
+
+}  // namespace sqmc_b200_host

@@ -59,6 +59,10 @@ int sqmc_b200_system_heg(sqmc_b200_handle **h, int norb, int n_dim, const double
  * (hubbard.f90:2179-2324); l_x,l_y give the momentum period. */
 int sqmc_b200_system_hubbardk(sqmc_b200_handle **h, int l_x, int l_y, const int32_t *k_vectors, const double *k_energies,
                               double ubyn, int nup, int ndn);
+/* hf_to_psit argument of generate_sparse_ham_hubbardk_upper_triangular (hubbard.f90:9435,9636-9643): when set, the next
+ * builds store row 1 as a single zero diagonal entry and no other row links to column 1.  Ignored for chem / heg, whose
+ * partial-connection builders ignore the flag too (chemistry.f90:7721). */
+int sqmc_b200_set_hf_to_psit(sqmc_b200_handle *h, int flag);
 int sqmc_b200_free(sqmc_b200_handle *h);
 
 /* ---- heat-bath determinant selection (the step before the H build in every HCI iteration)

@@ -41,6 +41,7 @@ def lib():
         L.orc_hubbardk_new.restype = vp
         L.orc_hubbardk_new.argtypes = [i32, i32, dbl, dbl, i32, i32]
         L.orc_free.argtypes = [vp]
+        L.orc_set_hf_to_psit.argtypes = [vp, i32]
         L.orc_norb.argtypes = [vp]
         L.orc_nint.restype = i64
         L.orc_nint.argtypes = [vp]
@@ -176,11 +177,12 @@ class System:
         assert k <= cap
         return cols[:k].copy(), vals[:k].copy()
 
-    def build_upper(self, up, dn, incremental=False):
+    def build_upper(self, up, dn, incremental=False, hf_to_psit=False):
         """-> (counts int64[n], indices int64[nnz] 1-based, values f64[nnz]) : reference layout."""
         up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
         dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
         n = len(up)
+        lib().orc_set_hf_to_psit(self.h, int(bool(hf_to_psit)))
         nnz = lib().orc_build_upper(self.h, n, _p(up), _p(dn), int(incremental))
         counts = np.zeros(n, dtype=np.int64)
         idx = np.zeros(nnz, dtype=np.int64)

@@ -164,6 +164,7 @@ struct System {
   // --- hubbard k-space (hubbard.f90)
   int l_x = 0, l_y = 0;
   double hub_t = 1, hub_U = 0, ubyn = 0;
+  bool hf_to_psit = false;         // hubbard.f90:9636-9643
   std::vector<int> hk_vectors;     // (2,nsites)
   std::vector<double> k_energies;
   // stored sparse H (sparse_mat, commons/common_selected_ci.f90:26-31)
@@ -746,7 +747,9 @@ static void build_upper(System &S, i8b n_det, const det_t *dets_up, const det_t 
         if (std::fabs(elem) > thresh) { conn.push_back({j, elem}); is_included[j] = 1; }
       }
     };
-    if (S.model == 2) {
+    if (S.model == 2 && S.hf_to_psit && i == 1) {
+      conn[0].second = 0.0;  // first row = single zero diagonal entry (hubbard.f90:9636-9643)
+    } else if (S.model == 2) {
       // Hubbard: every connected j>i, no threshold (hubbard.f90:9640-9668)
       size_t lo, hi;
       det_t t = up;
@@ -1253,6 +1256,7 @@ void *orc_hubbardk_new(int l_x, int l_y, double t, double U, int nup, int ndn) {
 }
 
 void orc_free(void *h) { delete (System *)h; }
+void orc_set_hf_to_psit(void *h, int flag) { ((System *)h)->hf_to_psit = flag != 0; }
 
 int orc_norb(void *h) { return ((System *)h)->norb; }
 long long orc_nint(void *h) { return (long long)((System *)h)->integrals.size(); }

@@ -19,7 +19,7 @@ SYMBOLS = [
     "sqmc_b200_scale_values", "sqmc_b200_davidson", "sqmc_b200_matvec_dev", "sqmc_b200_device_malloc",
     "sqmc_b200_device_free", "sqmc_b200_memcpy_h2d", "sqmc_b200_memcpy_d2h", "sqmc_b200_device_sync",
     "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
-    "sqmc_b200_hci_new_dets",
+    "sqmc_b200_hci_new_dets", "sqmc_b200_set_hf_to_psit",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     L.sqmc_b200_system_orbital_symmetries.argtypes = [vp, vp]
     L.sqmc_b200_hci_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, vp]
     L.sqmc_b200_hci_new_dets.argtypes = [vp, vp, vp]
+    L.sqmc_b200_set_hf_to_psit.argtypes = [vp, i32]
     _lib = L
     return L
 

@@ -96,12 +96,13 @@ class SparseHamiltonian:
         return nu, nd, mh
 
     # ---- build ---------------------------------------------------------
-    def generate_sparse_ham_upper_triangular(self, dets_up, dets_dn, ndet_old=0):
+    def generate_sparse_ham_upper_triangular(self, dets_up, dets_dn, ndet_old=0, hf_to_psit=False):
         """Build H over the determinant list (caller order). Returns nnz of the
         reference's upper-triangular format (its "# of nonzero elem in H")."""
         up, dn = dets_to_u64(dets_up), dets_to_u64(dets_dn)
         if len(up) != len(dn):
             raise SqmcError("dets_up / dets_dn length mismatch")
+        check(self._L.sqmc_b200_set_hf_to_psit(self._h, int(bool(hf_to_psit))))
         nnz = C.c_int64()
         check(self._L.sqmc_b200_build_h(self._h, len(up), _p(up), _p(dn), int(ndet_old), C.byref(nnz)))
         self.n = len(up)

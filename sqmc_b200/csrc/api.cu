@@ -183,6 +183,12 @@ int sqmc_b200_free(sqmc_b200_handle *h) {
   return 0;
 }
 
+int sqmc_b200_set_hf_to_psit(sqmc_b200_handle *h, int flag) {
+  if (!h) { set_error("set_hf_to_psit: null handle"); return 2; }
+  // honoured by the Hubbard builder only: the chem/heg partial-connection builders ignore it (chemistry.f90:7721,7885)
+  h->T.hf_to_psit = (flag && h->T.model == MODEL_HUBBARDK) ? 1 : 0;
+  return 0;
+}
 int sqmc_b200_system_orbital_symmetries(sqmc_b200_handle *h, const int32_t *orbital_symmetries) {
   SQ_CHECK(require_init());
   if (!h) { set_error("orbital_symmetries: null handle"); return 2; }

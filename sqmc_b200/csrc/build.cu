@@ -469,10 +469,13 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
       } else {
         Bits<NW> ju = b_load<NW>(up, j), jd = b_load<NW>(dn, j);
         // the reference stores H(i,j) for caller index i<j with det_i as bra
-        if (cp < perm[j]) v = model_hamiltonian<NW>(T, c2, pu, pd, ju, jd);
+        const int32_t cj = perm[j];
+        if (cp < cj) v = model_hamiltonian<NW>(T, c2, pu, pd, ju, jd);
         else v = model_hamiltonian<NW>(T, c2, ju, jd, pu, pd);
         keep = fabs(v) > 1.e-12;
+        if (T.hf_to_psit && (cp == 0 || cj == 0)) keep = false;  // no row links to the first state
       }
+      if (T.hf_to_psit && cp == 0 && j == (int32_t)p) v = 0.0;   // first row = single zero diagonal entry
     }
     __syncwarp();
     unsigned m = __ballot_sync(full, keep);

@@ -23,6 +23,7 @@ struct ModelTables {
   int model;
   int norb, nup, ndn;
   int time_sym, z;
+  int hf_to_psit;  // Hubbard builder: row/column 1 reduced to a zero diagonal (hubbard.f90:9636-9643)
   // chem
   const double *integrals;   // device; Fortran integrals(1:nint) stored 0-based
   const int32_t *combine_2;  // device; (norb+1)x(norb+1) column-major, values as in Fortran
