@@ -1028,14 +1028,21 @@ static void important_connected_chem(System &S, det_t det_up, det_t det_dn, doub
       try_double((det_up & ~bit(p)) | bit(r), (det_dn & ~bit(q)) | bit(s));
 }
 static void heg_max_double(System &S) {
+  // largest |double excitation element| over momentum-conserving (p,q)->(r,s) (heg.f90:288-397 max_double); s follows from p,q,r
   int norb = S.norb;
   double mx = 0;
-  for (int p = 0; p < norb; p++) for (int q = p + 1; q < norb; q++) for (int r = 0; r < norb; r++) for (int s = r + 1; s < norb; s++) {
-    if (p == r || q == s || p == s || q == r) continue;
+  auto sidx = [&](int p, int q, int r) {
+    return find_orb_id(S, S.k_rel[p * 3] + S.k_rel[q * 3] - S.k_rel[r * 3], S.k_rel[p * 3 + 1] + S.k_rel[q * 3 + 1] - S.k_rel[r * 3 + 1],
+                       S.k_rel[p * 3 + 2] + S.k_rel[q * 3 + 2] - S.k_rel[r * 3 + 2]) - 1;
+  };
+  for (int p = 0; p < norb; p++) for (int q = p + 1; q < norb; q++) for (int r = 0; r < norb; r++) {
+    int s = sidx(p, q, r);
+    if (s < 0 || s <= r || p == r || q == s || p == s || q == r) continue;
     mx = std::max(mx, std::fabs(hamiltonian_heg(S, bit(p) | bit(q), 0, bit(r) | bit(s), 0, true)));
   }
-  for (int p = 0; p < norb; p++) for (int q = 0; q < norb; q++) for (int r = 0; r < norb; r++) for (int s = 0; s < norb; s++) {
-    if (p == r || q == s) continue;
+  for (int p = 0; p < norb; p++) for (int q = 0; q < norb; q++) for (int r = 0; r < norb; r++) {
+    int s = sidx(p, q, r);
+    if (s < 0 || p == r || q == s) continue;
     mx = std::max(mx, std::fabs(hamiltonian_heg(S, bit(p), bit(q), bit(r), bit(s), true)));
   }
   S.max_double = mx;
