@@ -1076,21 +1076,14 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
 // ------------------------------------------------------------------ export / import (compatibility paths, host side)
 int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
   if (!h->d_rowptr) { set_error("export_upper: no matrix"); return 2; }
+  if (!h->wcsr) return export_upper_device(h, counts, indices, values);
+  // opt-in window-staged layout: decoded on the host (inspection path of an experimental layout)
   const int64_t nloc = h->row1 - h->row0;
   std::vector<int64_t> rowptr(nloc + 1);
   std::vector<int32_t> cols, perm(h->n);
   std::vector<double> vals;
-  if (h->wcsr) {
-    SQ_CHECK(wcsr_decode_host(h, rowptr, cols, vals));
-  } else {
-    cols.resize(h->nnz_local);
-    vals.resize(h->nnz_local);
-    SQ_CUDA(cudaMemcpy(rowptr.data(), h->d_rowptr, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
-    SQ_CUDA(cudaMemcpy(cols.data(), h->d_cols, h->nnz_local * 4, cudaMemcpyDeviceToHost));
-    SQ_CUDA(cudaMemcpy(vals.data(), h->d_vals, h->nnz_local * 8, cudaMemcpyDeviceToHost));
-  }
+  SQ_CHECK(wcsr_decode_host(h, rowptr, cols, vals));
   SQ_CUDA(cudaMemcpy(perm.data(), h->d_perm, h->n * 4, cudaMemcpyDeviceToHost));
-  // caller rows owned by this rank, ascending caller index
   std::vector<std::pair<int32_t, int64_t>> rows(nloc);
   for (int64_t q = 0; q < nloc; q++) rows[q] = {perm[h->row0 + q], q};
   std::sort(rows.begin(), rows.end());
@@ -1117,70 +1110,20 @@ int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double 
 
 int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values) {
   if (G.nranks != 1) { set_error("import_upper: single-rank handles only"); return 2; }
+  if (n <= 0 || n >= (1ll << 31) - 2) { set_error("import_upper: bad n"); return 2; }
   free_matrix(h);
-  std::vector<int64_t> deg(n, 0);
-  int64_t k = 0, nnzu = 0;
-  for (int64_t i = 0; i < n; i++)
-    for (int64_t j = 0; j < counts[i]; j++, k++) {
-      int64_t c = indices[k] - 1;
-      if (c < 0 || c >= n) { set_error("import_upper: column out of range"); return 2; }
-      deg[i]++;
-      if (c != i) deg[c]++;
-    }
-  nnzu = k;
-  std::vector<int64_t> rowptr(n + 1, 0);
-  for (int64_t i = 0; i < n; i++) rowptr[i + 1] = rowptr[i] + deg[i];
-  std::vector<int32_t> cols(rowptr[n]);
-  std::vector<double> vals(rowptr[n]);
-  std::vector<int64_t> cur(rowptr.begin(), rowptr.end() - 1);
-  k = 0;
-  // lower part first (columns < row arrive in increasing source-row order), then the stored upper part
-  for (int64_t i = 0; i < n; i++) {
-    int64_t k0 = k;
-    for (int64_t j = 0; j < counts[i]; j++, k++) {
-      int64_t c = indices[k] - 1;
-      if (c != i) { cols[cur[c]] = (int32_t)i; vals[cur[c]] = values[k]; cur[c]++; }
-    }
-    (void)k0;
-  }
-  // rows now hold their lower entries; append upper entries (in stored order) -- but lower entries of row c
-  // were appended while scanning rows i<c only, so appending row c's own entries afterwards keeps columns ascending.
-  // Do it in a second pass to keep the code simple: rebuild per row.
-  {
-    std::vector<int64_t> lowcnt(n);
-    for (int64_t i = 0; i < n; i++) lowcnt[i] = cur[i] - rowptr[i];
-    k = 0;
-    for (int64_t i = 0; i < n; i++) {
-      int64_t w = rowptr[i] + lowcnt[i];
-      for (int64_t j = 0; j < counts[i]; j++, k++) {
-        cols[w] = (int32_t)(indices[k] - 1);
-        vals[w] = values[k];
-        w++;
-      }
-    }
-  }
+  cudaStream_t s = G.stream;
   h->n = n;
   h->row_starts = {0, n};
   h->row0 = 0;
   h->row1 = n;
-  h->nnz_local = rowptr[n];
-  h->nnz_full = rowptr[n];
-  h->nnz_upper = nnzu;
-  h->capacity = std::max<int64_t>(rowptr[n], 1);
-  cudaStream_t s = G.stream;
   SQ_CUDA(cudaMalloc(&h->d_perm, n * 4));
   SQ_CUDA(cudaMalloc(&h->d_iperm, n * 4));
   iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, n);
   SQ_LAUNCH_CHECK();
   iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_iperm, n);
   SQ_LAUNCH_CHECK();
-  SQ_CUDA(cudaMalloc(&h->d_rowptr, (n + 1) * 8));
-  SQ_CUDA(cudaMalloc(&h->d_cols, h->capacity * 4));
-  SQ_CUDA(cudaMalloc(&h->d_vals, h->capacity * 8));
-  SQ_CUDA(cudaMemcpyAsync(h->d_rowptr, rowptr.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
-  SQ_CUDA(cudaMemcpyAsync(h->d_cols, cols.data(), rowptr[n] * 4, cudaMemcpyHostToDevice, s));
-  SQ_CUDA(cudaMemcpyAsync(h->d_vals, vals.data(), rowptr[n] * 8, cudaMemcpyHostToDevice, s));
-  SQ_CUDA(cudaStreamSynchronize(s));
+  SQ_CHECK(import_upper_device(h, n, counts, indices, values));
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
   return 0;

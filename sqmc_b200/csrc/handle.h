@@ -171,6 +171,9 @@ int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-
 // all-gather x (own block valid on entry) and multiply; under nranks>1 the all-gather runs on the comm stream while the
 // local-column part of every row is multiplied, the remote-column part follows
 int spmv_gather_multiply(sqmc_b200_handle *h, double *x_full, double *y_dev, cudaStream_t s);
+// convert.cu
+int export_upper_device(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values);
+int import_upper_device(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
 // wcsr.cu
 int wcsr_convert(sqmc_b200_handle *h);      // CSR -> WCSR in place when the space is dense enough (or SQMC_WCSR=1)
 int wcsr_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
