@@ -81,21 +81,49 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+CPU_SAMPLE_SCHED = (1e-3, 3e-4, 1e-4)
+
+
+def cpu_sample(args):
+    """The bounded CPU sample of the workload, built with the oracle only: for --space hci the same HCI run stopped at
+    eps_var = 1e-4 (171,060 determinants; tests/golden/c2_hci_sched.json), for --space lowest the cpu_sample_dets
+    lowest-energy determinants.  -> (counts, idx, val, description, seconds to obtain the sample matrix)"""
+    import sqmc_b200 as sq
+    from sqmc_b200 import spaces
+    from oracle import oracle as O
+    chem = sq.ChemSystem(FCIDUMP)
+    S = O.System.chem(FCIDUMP, chem.norb, chem.nelec, chem.nup, chem.orbital_symmetries_fcidump)
+    t0 = time.perf_counter()
+    if args.space == "hci":
+        r = S.hci(CPU_SAMPLE_SCHED[-1], eps_var_sched=CPU_SAMPLE_SCHED, max_iters=len(CPU_SAMPLE_SCHED))
+        up, dn = r["up"], r["dn"]
+        desc = "the same HCI run stopped at eps_var=1e-4 (oracle perform_hci, %d dets)" % len(up)
+    else:
+        up, dn, _ = spaces.c2_lowest_energy_space(chem, args.cpu_sample_dets)
+        desc = "the %d lowest-energy A_g dets" % len(up)
+    t_space = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cnt, idx, val = S.build_upper(up, dn)
+    t_build = time.perf_counter() - t0
+    return cnt, idx, val, desc, t_space, t_build
+
+
+def workload_name(args, n, space_desc=None):
+    if args.space == "hci":
+        d = space_desc or "HCI space (heat-bath selection + build + Davidson per iteration, eps_var lowered 1e-3 -> 5e-7)"
+    else:
+        d = space_desc or "lowest-diagonal-energy A_g determinants"
+    return "C2 cc-pVDZ r1.24253 (FCIDUMP), time_sym=f, %d determinants: %s; step = one H.v" % (n, d)
+
+
 def run_reference(args):
     """CPU arm: the oracle's restatement of fast_sparse_matrix_multiply_upper_triangular on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import sqmc_b200 as sq
     from sqmc_b200 import spaces
     from oracle import oracle as O
-    n_s = args.cpu_sample_dets
-    chem = sq.ChemSystem(FCIDUMP)
-    up, dn, _ = spaces.c2_lowest_energy_space(chem, n_s)
-    S = O.System.chem(FCIDUMP, chem.norb, chem.nelec, chem.nup, chem.orbital_symmetries_fcidump)
-    t0 = time.perf_counter()
-    cnt, idx, val = S.build_upper(up, dn)
-    t_build = time.perf_counter() - t0
+    cnt, idx, val, desc, t_space, t_build = cpu_sample(args)
     n = len(cnt)
     nnz_full = 2 * len(idx) - n
     cores = os.cpu_count() or 1
@@ -107,11 +135,11 @@ def run_reference(args):
         O.matvec_upper_mt(cnt, idx, val, x, cores)
     t = (time.perf_counter() - t0) / args.steps
     v = nnz_full / t
-    sample = "C2 cc-pVDZ r1.24253 time_sym=f, %d lowest-energy A_g dets (nnz_full=%d); %d threads, rows dealt round-robin, private y + reduction" % (n, nnz_full, cores)
+    sample = "C2 cc-pVDZ r1.24253 time_sym=f, %s (nnz_full=%d); %d threads, rows dealt round-robin, private y + reduction" % (desc, nnz_full, cores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 cc-pVDZ r1.24253 (FCIDUMP), time_sym=f, %d lowest-diagonal-energy A_g determinants; step = one H.v"
-                                   % args.n_dets, "n_dets": args.n_dets, "sample_n_dets": n, "sample_nnz_full": nnz_full,
+            "config": {"workload": workload_name(args, args.n_dets), "space": args.space, "n_dets": args.n_dets,
+                       "sample_n_dets": n, "sample_nnz_full": nnz_full,
                        "note": "each step is one CPU H.v on the bounded sample described in cpu_baseline.sample"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "build_nnz_upper_per_s_1core": len(idx) / t_build},
@@ -126,6 +154,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-dets", type=int, default=int(os.environ.get("SQMC_BENCH_NDETS", 10_000_000)))
+    ap.add_argument("--space", default=os.environ.get("SQMC_BENCH_SPACE", "hci"), choices=["hci", "lowest"],
+                    help="hci (BASELINE.json configs[3] recipe): an HCI run on the GPU (selection + build + Davidson through the "
+                         "library) with eps_var lowered until N determinants; lowest: the N lowest-diagonal-energy A_g "
+                         "determinants (host generated, SURVEY.md S4 fallback)")
     ap.add_argument("--cpu-sample-dets", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--davidson", action="store_true", help="also run a full device Davidson and report it in extra")
@@ -160,12 +192,20 @@ def main():
     # ---- workload (host, untimed)
     t0 = time.perf_counter()
     chem = sq.ChemSystem(FCIDUMP)
-    up, dn, sector = spaces.c2_lowest_energy_space(chem, args.n_dets)
+    H = sq.SparseHamiltonian(chem, device=local_rank)
+    hci_log = []
+    if args.space == "hci":
+        up, dn, _, e_var = spaces.hci_space(H, chem, args.n_dets, log=hci_log)
+        sector = 27944940
+        space_desc = "HCI space grown on the GPU (heat-bath selection + build + Davidson), eps_var lowered to %.0e, E_var = %.9f Ha" % (
+            hci_log[-1]["eps_var"], e_var)
+    else:
+        up, dn, sector = spaces.c2_lowest_energy_space(chem, args.n_dets)
+        space_desc = "%d lowest-diagonal-energy A_g determinants of %d" % (len(up), sector)
     n = len(up)
     t_space = time.perf_counter() - t0
-    H = sq.SparseHamiltonian(chem, device=local_rank)
     t0 = time.perf_counter()
-    nnz_upper = H.generate_sparse_ham_upper_triangular(up, dn)
+    nnz_upper = H.generate_sparse_ham_upper_triangular(up, dn)   # timed from-scratch build of the final space
     t_build = time.perf_counter() - t0
     info = H.nnz()
     nnz_full = info["nnz_full"]
@@ -198,6 +238,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    prof_range = os.environ.get("SQMC_BENCH_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: only warm-up + timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -210,6 +253,8 @@ def main():
         ev[k + 1].record(stream)
     barrier()
     l1 = L.sqmc_b200_launch_count()
+    if prof_range:
+        torch.cuda.profiler.stop()
     per = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     ms_total = ev[0].elapsed_time(ev[args.steps])
     if world > 1:
@@ -257,16 +302,17 @@ def main():
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmv_dram_bytes_per_launch.json")
-    if os.path.exists(tp) and world == 1 and n == 10_000_000:  # the committed ncu capture is of this exact launch
+    if os.path.exists(tp) and world == 1:  # only when the committed ncu capture is of this exact matrix
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if int(tj.get("nnz_full", -1)) == int(nnz_full):
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     line = {
         "metric": METRIC, "value": nnz_full / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 cc-pVDZ r1.24253 (FCIDUMP), time_sym=f, %d lowest-diagonal-energy A_g determinants of %d; H built on GPU; step = one H.v"
-                               % (n, sector), "n_dets": n, "nnz_upper": nnz_upper, "nnz_full": nnz_full, "parallelism": "rows x%d" % world,
+        "config": {"workload": workload_name(args, n), "space": args.space, "space_detail": space_desc, "n_dets": n, "nnz_upper": nnz_upper, "nnz_full": nnz_full, "parallelism": "rows x%d" % world,
                    "l2": "inputs larger than L2 (matrix %.1f GB streamed per step)" % (12.0 * nnz_full / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
@@ -277,6 +323,8 @@ def main():
         "step_ms_min_max": [min(per), max(per)],
         "nnz_per_rank_max_over_mean": max(nnz_per_rank) / (sum(nnz_per_rank) / len(nnz_per_rank)),
     }
+    if hci_log:
+        line["hci_iterations"] = hci_log
     line.update(extra)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
@@ -287,15 +335,9 @@ def main():
 
 def cpu_baseline(args):
     """oracle (port of the reference algorithm) on a bounded sample, 1 core: ~10-30 s of CPU work."""
-    import sqmc_b200 as sq
     from sqmc_b200 import spaces
     from oracle import oracle as O
-    chem = sq.ChemSystem(FCIDUMP)
-    up, dn, _ = spaces.c2_lowest_energy_space(chem, args.cpu_sample_dets)
-    S = O.System.chem(FCIDUMP, chem.norb, chem.nelec, chem.nup, chem.orbital_symmetries_fcidump)
-    t0 = time.perf_counter()
-    cnt, idx, val = S.build_upper(up, dn)
-    t_build = time.perf_counter() - t0
+    cnt, idx, val, desc, t_space, t_build = cpu_sample(args)
     n = len(cnt)
     nnz_full = 2 * len(idx) - n
     x = spaces.splitmix_vector(n)
@@ -306,8 +348,8 @@ def cpu_baseline(args):
         reps += 1
     t = (time.perf_counter() - t0) / reps
     return {"value": nnz_full / t, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle fast_sparse_matrix_multiply_upper_triangular on the %d lowest-energy A_g dets of the same C2 workload (nnz_full=%d), %d reps; oracle H build of that sample %.1f s"
-                      % (n, nnz_full, reps, t_build),
+            "sample": "oracle fast_sparse_matrix_multiply_upper_triangular on %s of the same C2 workload (nnz_full=%d), %d reps; "
+                      "obtaining the sample's space took the oracle %.1f s, its from-scratch H build %.1f s" % (desc, nnz_full, reps, t_space, t_build),
             "build_nnz_upper_per_s": len(idx) / t_build}
 
 

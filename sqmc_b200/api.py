@@ -178,6 +178,10 @@ class SparseHamiltonian:
     def scale_values(self, ratio):
         check(self._L.sqmc_b200_scale_values(self._h, float(ratio)))
 
+    def set_row_bundle(self, rows_per_bundle):
+        """storage-order hint for H.v: 0 = plain CSR rows, 2/4/8 = column-merged bundles of that many rows (csrc/bundle.cu)."""
+        check(self._L.sqmc_b200_set_row_bundle(self._h, int(rows_per_bundle)))
+
     def projector_step(self, tau, e_trial, w):
         """deltaw = Hstored.w + e_trial*tau*w (do_walk.f90:2259-2290)."""
         w = np.ascontiguousarray(w, dtype=np.float64)

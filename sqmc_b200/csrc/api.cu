@@ -293,6 +293,19 @@ int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio) {
   return 0;
 }
 
+int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("set_row_bundle: no matrix on this handle"); return 2; }
+  if (rows_per_bundle != 0 && rows_per_bundle != 2 && rows_per_bundle != 4 && rows_per_bundle != 8) {
+    set_error("set_row_bundle: rows_per_bundle must be 0, 2, 4 or 8");
+    return 2;
+  }
+  SQ_CHECK(bundle_decode(h));
+  if (rows_per_bundle) SQ_CHECK(bundle_encode_r(h, rows_per_bundle));
+  SQ_CUDA(cudaStreamSynchronize(G.stream));
+  return 0;
+}
+
 int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());
@@ -347,6 +360,9 @@ int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int6
   int64_t L = 0;
   if (h->wcsr) {
     SQ_CHECK(wcsr_get_row(h, p, c, v));
+    L = (int64_t)c.size();
+  } else if (h->bundle_R) {
+    SQ_CHECK(bundle_get_row(h, p, c, v));
     L = (int64_t)c.size();
   } else {
     int64_t rp[2];

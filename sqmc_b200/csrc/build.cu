@@ -581,6 +581,7 @@ void free_matrix(sqmc_b200_handle *h) {
   F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_split_lo); F(h->d_split_hi);
   F(h->d_gA_off); F(h->d_eA); F(h->d_gB_off); F(h->d_eBpos); F(h->d_bidx); F(h->d_binv);
   wcsr_free(h);
+  h->bundle_R = 0;
   h->nA = h->nB = 0;
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
   h->row_starts.clear();
@@ -1021,6 +1022,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
   SQ_CHECK(wcsr_convert(h));
+  SQ_CHECK(bundle_encode(h));
   cudaEventRecord(ev[4], s);
   SQ_CUDA(cudaStreamSynchronize(s));
   float f;
@@ -1076,7 +1078,17 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
 // ------------------------------------------------------------------ export / import (compatibility paths, host side)
 int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
   if (!h->d_rowptr) { set_error("export_upper: no matrix"); return 2; }
-  if (!h->wcsr) return export_upper_device(h, counts, indices, values);
+  if (!h->wcsr) {
+    const int was_bundled = h->bundle_R;
+    SQ_CHECK(bundle_decode(h));  // the exporter walks plain rows; re-ordered again afterwards
+    int rc = export_upper_device(h, counts, indices, values);
+    if (rc) return rc;
+    if (was_bundled) {
+      SQ_CHECK(bundle_encode_r(h, was_bundled));
+      SQ_CUDA(cudaStreamSynchronize(G.stream));
+    }
+    return 0;
+  }
   // opt-in window-staged layout: decoded on the host (inspection path of an experimental layout)
   const int64_t nloc = h->row1 - h->row0;
   std::vector<int64_t> rowptr(nloc + 1);
@@ -1126,7 +1138,7 @@ int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const in
   SQ_CHECK(import_upper_device(h, n, counts, indices, values));
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
-  return 0;
+  return bundle_encode(h);
 }
 
 }  // namespace sqmc

@@ -127,6 +127,8 @@ struct sqmc_b200_handle {
   int32_t *d_eBpos = nullptr;    // [n] beta-major position -> beta group
   int32_t *d_bidx = nullptr;     // [n] beta-major position -> internal row
   int32_t *d_binv = nullptr;     // [n] internal row -> beta-major position
+  // ---- row-bundle ordering (csrc/bundle.cu; active when bundle_R > 0: d_cols holds column << 3 | row-in-bundle) ----
+  int bundle_R = 0, bundle_cap = 0;
   // ---- WCSR layout (active when wcsr == true; then d_cols holds packed indices) ----
   bool wcsr = false;
   sqmc::WPart WA, WB;
@@ -181,6 +183,12 @@ int wcsr_decode_host(sqmc_b200_handle *h, std::vector<int64_t> &rowptr, std::vec
 void wcsr_free(sqmc_b200_handle *h);
 int wcsr_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 int extract_diag(sqmc_b200_handle *h, double *diag_dev, cudaStream_t s);
+// bundle.cu
+int bundle_encode(sqmc_b200_handle *h);  // plain CSR -> row bundles in place (SQMC_BUNDLE=2|4|8), no-op otherwise
+int bundle_encode_r(sqmc_b200_handle *h, int R);  // same with an explicit bundle size
+int bundle_decode(sqmc_b200_handle *h);  // exact inverse
+int bundle_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
+int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 // davidson.cu
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
              int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);

@@ -193,6 +193,7 @@ static int launch_cta_bin(sqmc_b200_handle *h, const double *x, double *y, cudaS
 int spmv_launch(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
   if (h->wcsr) return wcsr_spmv(h, x, y, s);
+  if (h->bundle_R) return bundle_spmv(h, x, y, s);
   SQ_CHECK(launch_vec_bins<0>(h, x, y, s));
   return launch_cta_bin(h, x, y, s);
 }
@@ -228,7 +229,7 @@ int spmv_gather_multiply(sqmc_b200_handle *h, double *x, double *y, cudaStream_t
   // determinants): the NCCL kernels compete for SMs/L2 with the SpMV and the row has to be visited twice.
   static int overlap = -1;
   if (overlap < 0) { const char *e = getenv("SQMC_OVERLAP"); overlap = (e && atoi(e) > 0) ? 1 : 0; }
-  if (h->wcsr || nloc == 0 || !overlap) {
+  if (h->wcsr || h->bundle_R || nloc == 0 || !overlap) {
     SQ_CHECK(allgather_rows(h, x, s));
     return spmv_launch(h, x, y, s);
   }

@@ -83,6 +83,40 @@ def c2_lowest_energy_space(chem, n_dets, target_irrep=1, time_sym=False):
     return np.ascontiguousarray(np.stack([up, z], axis=1)), np.ascontiguousarray(np.stack([dn, z], axis=1)), total
 
 
+def hci_space(H, system, n_dets, eps_schedule=(1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 5e-6, 2e-6, 1e-6, 5e-7, 2e-7, 1e-7), log=None):
+    """The determinant space of an HCI run (perform_hci, hci.f90:359-517) grown on the GPU through the library itself --
+    heat-bath selection, H build and Davidson per iteration -- with eps_var lowered along `eps_schedule` until the space
+    holds n_dets determinants (the last batch of new determinants, sorted by label, is cut to land exactly on n_dets).
+    This is the BASELINE.json configs[3] recipe ("eps_var lowered to give ~10^7 determinants").  Under torchrun every
+    rank runs the same loop (selection is replicated, build / Davidson are sharded collectives) and obtains identical lists.
+    Returns (up, dn, wts, energy); H keeps the matrix of the final space resident."""
+    from .api import dets_to_u64
+    up = dets_to_u64([system.hf_up])
+    dn = dets_to_u64([system.hf_dn])
+    wts = np.ones((1, 1))
+    min_h = np.full(1, 9e99)
+    energy = None
+    for it, eps in enumerate(eps_schedule, 1):
+        n_old = len(up)
+        nu, nd, min_h = H.get_next_det_list(up, dn, np.abs(wts[:, 0]), min_h, eps)
+        if len(nu) == 0:
+            continue
+        if n_old + len(nu) > n_dets:
+            nu, nd = nu[:n_dets - n_old], nd[:n_dets - n_old]
+        up, dn = np.concatenate([up, nu]), np.concatenate([dn, nd])
+        min_h = np.concatenate([min_h, np.full(len(nu), 9e99)])
+        nnz = H.generate_sparse_ham_upper_triangular(up, dn, ndet_old=n_old)
+        v0 = np.zeros((len(up), 1))
+        v0[:n_old, 0] = wts[:, 0]
+        d = H.davidson_sparse(n_states=1, initial_vector=v0)
+        wts, energy = d["evecs"], float(d["evals"][0])
+        if log is not None:
+            log.append({"iter": it, "eps_var": eps, "n_dets": len(up), "nnz_upper": int(nnz), "energy": energy})
+        if len(up) >= n_dets:
+            break
+    return up, dn, wts, energy
+
+
 def hubbard_momentum_sector(hub, n_dets=None, ktot=(0, 0)):
     """Determinants of one total-momentum sector of the k-space Hubbard model, ranked by
     ascending diagonal energy then label, truncated to n_dets, stored sorted by label

@@ -7,6 +7,8 @@
   c2_s1_hci.json       oracle HCI on the shipped C2 cc-pVDZ input (C2_v2z_curve/r1.24253/i_1sigma_g).
                        The reference ships no output for this input: "parity unpinned by the
                        reference", pinned by the oracle (itself pinned on the HEG log).
+  c2_hci_sched.json    oracle HCI with the benchmark's eps_var schedule (1e-3, 3e-4, 1e-4; one iteration each) on
+                       C2 r1.24253 time_sym=f: sizes, nnz, energies and a SHA-256 of the final determinant list.
   c2_small_space.npz   2000 lowest-energy A_g determinants of C2 + the oracle's upper-triangular H.
 
 Run from the repo root:  python tests/golden/make_golden.py
@@ -95,6 +97,24 @@ def c2_from_oracle():
     print("wrote c2_s1_hci.json, c2_small_space.npz", len(cnt), len(idx))
 
 
+def c2_sched_from_oracle():
+    import hashlib
+    from conftest import C2_FCIDUMP, C2_ORBSYM
+    from oracle import oracle as O
+    S = O.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM)
+    sched = [1e-3, 3e-4, 1e-4]
+    r = S.hci(sched[-1], eps_var_sched=sched, max_iters=len(sched))
+    order = np.lexsort((r["dn"][:, 0], r["up"][:, 0]))
+    dig = hashlib.sha256(np.ascontiguousarray(np.stack([r["up"][order, 0], r["dn"][order, 0]], axis=1)).tobytes()).hexdigest()
+    out = {"source": "oracle perform_hci restatement (hci.f90:359-517), one iteration per eps_var_sched entry",
+           "input": "data/C2_v2z_curve/r1.24253/FCIDUMP, time_sym=f", "eps_var_sched": sched,
+           "n_det": r["ndet"].tolist(), "nnz": r["nnz"].tolist(), "iter_energy": r["iter_energy"][:, 0].tolist(),
+           "sha256_sorted_up_dn_u64": dig}
+    json.dump(out, open(os.path.join(HERE, "c2_hci_sched.json"), "w"), indent=1)
+    print("wrote c2_hci_sched.json", out["n_det"], out["nnz"])
+
+
 if __name__ == "__main__":
     heg_from_reference_log()
     c2_from_oracle()
+    c2_sched_from_oracle()

@@ -109,3 +109,22 @@ def test_c2_hci_loop_fully_on_gpu_matches_fixture():
     assert [l[1] for l in log] == gold["nnz"]
     assert np.max(np.abs(np.array([l[2][0] for l in log]) - np.array(gold["iter_energy"])[:, 0])) < 1e-8
     assert abs(log[-1][2][0] - gold["energy"][0]) < 1e-8   # C2 cc-pVDZ HCI variational energy, eps_var = 1e-3
+
+
+def test_c2_eps_scheduled_hci_space_matches_oracle_golden():
+    """spaces.hci_space (the bench workload's recipe) stopped at eps_var = 1e-4: sizes, nnz, energies and the exact
+    determinant list (SHA-256 over the label-sorted list) equal the oracle's perform_hci run (tests/golden/c2_hci_sched.json)."""
+    import hashlib
+    import sqmc_b200 as sq
+    from sqmc_b200 import spaces
+    gold = json.load(open(os.path.join(HERE, "golden", "c2_hci_sched.json")))
+    cs = sq.ChemSystem(C2_FCIDUMP)
+    H = sq.SparseHamiltonian(cs)
+    log = []
+    up, dn, wts, e = spaces.hci_space(H, cs, 10**9, eps_schedule=gold["eps_var_sched"], log=log)
+    assert [l["n_dets"] for l in log] == gold["n_det"]
+    assert [l["nnz_upper"] for l in log] == gold["nnz"]
+    assert np.max(np.abs(np.array([l["energy"] for l in log]) - np.array(gold["iter_energy"]))) < 1e-8
+    order = np.lexsort((dn[:, 0], up[:, 0]))
+    dig = hashlib.sha256(np.ascontiguousarray(np.stack([up[order, 0], dn[order, 0]], axis=1)).tobytes()).hexdigest()
+    assert dig == gold["sha256_sorted_up_dn_u64"]
