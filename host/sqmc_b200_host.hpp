@@ -140,6 +140,8 @@ inline void davidson_sparse(model_system &S, int n, int n_states, std::vector<rk
 
 // do_walk.f90:2259-2290 with the stored matrix already scaled by -tau (semistoch.f90:657,880)
 inline void scale_values(model_system &S, rk ratio) { check(sqmc_b200_scale_values(S.h, ratio)); }
+// storage-order hint for H.v (0 = plain rows, 2/4/8 = column-merged bundles); no reference counterpart
+inline void set_row_bundle(model_system &S, int rows_per_bundle) { check(sqmc_b200_set_row_bundle(S.h, rows_per_bundle)); }
 inline void deterministic_projector_step(model_system &S, rk tau, rk e_trial, const std::vector<rk> &imp_wt, std::vector<rk> &deltaw) {
   deltaw.assign(S.n, 0.0);
   check(sqmc_b200_projector(S.h, tau, e_trial, imp_wt.data(), deltaw.data()));
