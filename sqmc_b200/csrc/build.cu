@@ -29,11 +29,34 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 
 #include "handle.h"
 
 namespace sqmc {
+
+// host wall-clock marks of one build (SQMC_BUILD_PROFILE=1 prints them): finds time spent outside kernels
+// (allocation of the ~100 GB arrays, host loops, synchronisation) that the CUDA-event phases do not see
+struct HostMarks {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  HostMarks() {
+    const char *e = getenv("SQMC_BUILD_PROFILE");
+    on = e && atoi(e) > 0;
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sqmc build] %-28s %9.1f ms  (t = %9.1f ms)\n", what, std::chrono::duration<double, std::milli>(t - last).count(),
+            std::chrono::duration<double, std::milli>(t - t0).count());
+    last = t;
+  }
+};
+
 
 // ------------------------------------------------------------------ helpers
 static const int kThreads = 256;
@@ -532,6 +555,26 @@ static int exclusive_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n,
   return 0;
 }
 
+// same scan with caller-provided temporary storage and no synchronisation (the chunk loop of the build stays asynchronous)
+static int exclusive_scan_i32_to_i64_async(const int32_t *in, int64_t *out, int64_t n, void *tmp, size_t tmp_bytes, cudaStream_t s) {
+  auto it = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>(in, cub::CastOp<int64_t>());
+  size_t tb = tmp_bytes;
+  SQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, it, out, (int)(n + 1), s));
+  g_launch_count += 2;
+  return 0;
+}
+static size_t exclusive_scan_tmp_bytes(int64_t n) {
+  size_t tb = 0;
+  auto it = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>((const int32_t *)nullptr, cub::CastOp<int64_t>());
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, it, (int64_t *)nullptr, (int)(n + 1));
+  return tb;
+}
+__global__ void add_offset_dev_kernel(int64_t *a, int64_t n, const int64_t *off) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] += *off;
+}
+__global__ void set_scalar_kernel(int64_t *dst, const int64_t *src) { *dst = *src; }
+
 // ---- helpers shared with select.cu
 // upload n 16-byte determinants (host) and split them into NW-word strings (device, caller allocates n*NW words)
 int upload_dets(int NW, int norb, const void *host16, uint64_t *out, int64_t n, cudaStream_t s) {
@@ -616,6 +659,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   const ModelTables &T = h->T;
   cudaEvent_t ev[5];
   for (auto &e : ev) cudaEventCreate(&e);
+  HostMarks HM;
   cudaEventRecord(ev[0], s);
 
   // ---- upload + split
@@ -818,6 +862,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   auto row_entry = [&](int64_t p) -> int64_t { return ts ? (int64_t)rowE_host[p] : p; };
   std::vector<TileDesc> fill_tiles;
   DevBuf<TileDesc> fill_tiles_dev;
+  HM.mark("prep (sort, groups, keys)");
   cudaEventRecord(ev[1], s);
 
   // ---- P1: candidate counts.  Under sharding every rank counts an equal slice of rows,
@@ -854,6 +899,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       SQ_CUDA(cudaStreamSynchronize(s));
     }
   }
+  HM.mark("count pass");
   DevBuf<int64_t> cand_prefix;  // n+1 exclusive prefix of candidate counts over ALL rows
   SQ_CHECK(cand_prefix.alloc(n + 1));
   SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p, cand_prefix.p, n, s));
@@ -867,6 +913,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->row1 = h->row_starts[G.rank + 1];
   const int64_t nloc = h->row1 - h->row0;
   const int64_t Tloc = hprefix[h->row1] - hprefix[h->row0];
+  HM.mark("prefix + partition");
   cudaEventRecord(ev[2], s);
 
   // ---- final arrays (capacity = candidate upper bound)
@@ -878,6 +925,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
   SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
 
+  HM.mark("alloc cols/vals/rowptr");
   // ---- chunks of rows bounded by temp candidates
   const int64_t kChunkCand = 1ll << 27;
   int64_t maxlen = 0;
@@ -888,8 +936,18 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   DevBuf<int64_t> cptr, rptr;
   int64_t r = h->row0;
   int64_t tmp_cap = 0, rows_cap = 0;
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  // the chunk loop is asynchronous: the running entry count lives on the device, the scans use one preallocated
+  // workspace, and the per-chunk timing events are read after the loop; the host prepares the next chunk's tiles meanwhile
+  DevBuf<int64_t> base_dev;
+  SQ_CHECK(base_dev.alloc(1));
+  SQ_CUDA(cudaMemsetAsync(base_dev.p, 0, sizeof(int64_t), s));
+  const size_t scan_bytes = exclusive_scan_tmp_bytes(std::max<int64_t>(nloc, 1)) + 256;
+  DevBuf<char> scan_tmp;
+  SQ_CHECK(scan_tmp.alloc((int64_t)scan_bytes));
+  // plan: chunk boundaries, the connection tiles of every chunk (uploaded once) and the temporary sizes
+  struct ChunkPlan { int64_t r, r_end, tile_off, ntiles, ml; };
+  std::vector<ChunkPlan> plan;
+  std::vector<TileDesc> all_tiles;
   while (r < h->row1) {
     int64_t r_end = r + 1;
     {  // largest r_end with prefix[r_end]-prefix[r] <= kChunkCand
@@ -898,45 +956,52 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       if (r_end <= r) r_end = r + 1;
       if (r_end > h->row1) r_end = h->row1;
     }
-    const int64_t nr = r_end - r, tc = hprefix[r_end] - hprefix[r];
-    if (tc > tmp_cap) {
-      tmp_cap = tc;
-      SQ_CHECK(cand_tmp.alloc(tmp_cap));
-      SQ_CHECK(vals_tmp.alloc(tmp_cap));
-    }
-    if (nr > rows_cap) {
-      rows_cap = nr;
-      SQ_CHECK(row_nnz.alloc(rows_cap + 1));
-      SQ_CHECK(cptr.alloc(rows_cap + 1));
-      SQ_CHECK(rptr.alloc(rows_cap + 1));
-    }
+    int64_t ml = 0;
+    for (int64_t q = r; q < r_end; q++) ml = std::max(ml, hprefix[q + 1] - hprefix[q]);
+    maxlen = std::max(maxlen, ml);
+    tmp_cap = std::max(tmp_cap, hprefix[r_end] - hprefix[r]);
+    rows_cap = std::max(rows_cap, r_end - r);
+    make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
+    plan.push_back({r, r_end, (int64_t)all_tiles.size(), (int64_t)fill_tiles.size(), ml});
+    all_tiles.insert(all_tiles.end(), fill_tiles.begin(), fill_tiles.end());
+    r = r_end;
+  }
+  if (!plan.empty()) {
+    SQ_CHECK(cand_tmp.alloc(tmp_cap));
+    SQ_CHECK(vals_tmp.alloc(tmp_cap));
+    SQ_CHECK(row_nnz.alloc(rows_cap + 1));
+    SQ_CHECK(cptr.alloc(rows_cap + 1));
+    SQ_CHECK(rptr.alloc(rows_cap + 1));
+    SQ_CHECK(fill_tiles_dev.alloc(std::max<int64_t>((int64_t)all_tiles.size(), 1)));
+    SQ_CUDA(cudaMemcpyAsync(fill_tiles_dev.p, all_tiles.data(), all_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+    SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
+  }
+  std::vector<cudaEvent_t> evs;
+  for (const ChunkPlan &cp : plan) {
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    evs.push_back(e0); evs.push_back(e1); evs.push_back(e2);
+    r = cp.r;
+    const int64_t r_end = cp.r_end, nr = r_end - r;
     cudaEventRecord(e0, s);
     // chunk-local candidate offsets
-    SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p + r, cptr.p, nr, s));
+    SQ_CHECK(exclusive_scan_i32_to_i64_async(cand_count.p + r, cptr.p, nr, scan_tmp.p, scan_bytes, s));
     // the scan above read cand_count[r+nr] as its spare slot; offsets beyond nr are unused
     {
-      make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
-      if ((int64_t)fill_tiles.size() > fill_tiles_dev.n) SQ_CHECK(fill_tiles_dev.alloc((int64_t)fill_tiles.size() * 2));
-      SQ_CUDA(cudaMemcpyAsync(fill_tiles_dev.p, fill_tiles.data(), fill_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-      const unsigned cgrid = (unsigned)std::min<int64_t>((int64_t)fill_tiles.size(), G.sm_count * 16);
+      const TileDesc *td = fill_tiles_dev.p + cp.tile_off;
+      const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cp.ntiles, G.sm_count * 16));
       if (NW == 1 && T.norb <= 32)
-        connect_tile_kernel<NW, true, true><<<cgrid, kConnTile, 0, s>>>(V, fill_tiles_dev.p, (int64_t)fill_tiles.size(), r, nullptr, cptr.p, cand_tmp.p);
+        connect_tile_kernel<NW, true, true><<<cgrid, kConnTile, 0, s>>>(V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p);
       else
-        connect_tile_kernel<NW, true, false><<<cgrid, kConnTile, 0, s>>>(V, fill_tiles_dev.p, (int64_t)fill_tiles.size(), r, nullptr, cptr.p, cand_tmp.p);
+        connect_tile_kernel<NW, true, false><<<cgrid, kConnTile, 0, s>>>(V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p);
       SQ_LAUNCH_CHECK();
     }
     sort_rows_warp_kernel<<<nblocks(nr, 8), 256, 0, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
     SQ_LAUNCH_CHECK();
-    {
-      int64_t ml = 0;
-      for (int64_t q = r; q < r_end; q++) ml = std::max(ml, hprefix[q + 1] - hprefix[q]);
-      maxlen = std::max(maxlen, ml);
-      if (ml > kWarpSortMax) {
-        int smem = (int)std::min<int64_t>(ml, kBlockSortMax) * 4;
-        SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
-        sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
-        SQ_LAUNCH_CHECK();
-      }
+    if (cp.ml > kWarpSortMax) {
+      int smem = (int)std::min<int64_t>(cp.ml, kBlockSortMax) * 4;
+      sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
+      SQ_LAUNCH_CHECK();
     }
     cudaEventRecord(e1, s);
     SQ_CUDA(cudaMemsetAsync(row_nnz.p, 0, (nr + 1) * sizeof(int32_t), s));
@@ -944,25 +1009,27 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     eval_kernel<NW><<<nblocks(nr * 32), 256, c2bytes, s>>>(T, h->d_up, h->d_dn, h->d_perm, r, r_end, cptr.p, cand_count.p + r,
                                                            cand_tmp.p, vals_tmp.p, row_nnz.p);
     SQ_LAUNCH_CHECK();
-    SQ_CHECK(exclusive_scan_i32_to_i64(row_nnz.p, rptr.p, nr, s));
-    add_offset_kernel<<<nblocks(nr + 1), kThreads, 0, s>>>(rptr.p, nr + 1, base_nnz);
+    SQ_CHECK(exclusive_scan_i32_to_i64_async(row_nnz.p, rptr.p, nr, scan_tmp.p, scan_bytes, s));
+    add_offset_dev_kernel<<<nblocks(nr + 1), kThreads, 0, s>>>(rptr.p, nr + 1, base_dev.p);
     SQ_LAUNCH_CHECK();
     compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaMemcpyAsync(h->d_rowptr + (r - h->row0), rptr.p, (nr + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    int64_t last = 0;
-    SQ_CUDA(cudaMemcpyAsync(&last, rptr.p + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    set_scalar_kernel<<<1, 1, 0, s>>>(base_dev.p, rptr.p + nr);
+    SQ_LAUNCH_CHECK();
     cudaEventRecord(e2, s);
-    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  SQ_CUDA(cudaMemcpyAsync(&base_nnz, base_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  for (size_t q = 0; q + 2 < evs.size(); q += 3) {
     float f1 = 0, f2 = 0;
-    cudaEventElapsedTime(&f1, e0, e1);
-    cudaEventElapsedTime(&f2, e1, e2);
+    cudaEventElapsedTime(&f1, evs[q], evs[q + 1]);
+    cudaEventElapsedTime(&f2, evs[q + 1], evs[q + 2]);
     ms_fill += f1;
     ms_eval += f2;
-    base_nnz = last;
-    r = r_end;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  for (cudaEvent_t e : evs) cudaEventDestroy(e);
+  HM.mark("fill/sort/eval/compact chunks");
   if (nloc == 0) SQ_CUDA(cudaMemsetAsync(h->d_rowptr, 0, sizeof(int64_t), s));
   h->nnz_local = base_nnz;
   cudaEventRecord(ev[3], s);
@@ -1007,6 +1074,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       cudaGetLastError();
     }
   }
+  HM.mark("nnz reduce + shrink");
   if (!ts) {
     h->nA = nA;
     h->nB = nB;
@@ -1019,10 +1087,13 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     invert_perm_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_bidx, h->d_binv, n);
     SQ_LAUNCH_CHECK();
   }
+  HM.mark("keep group structure");
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
+  HM.mark("work vectors + bins");
   SQ_CHECK(wcsr_convert(h));
   SQ_CHECK(bundle_encode(h));
+  HM.mark("bundle encode");
   cudaEventRecord(ev[4], s);
   SQ_CUDA(cudaStreamSynchronize(s));
   float f;
@@ -1044,7 +1115,11 @@ int build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *det
   if (n >= (1ll << 31) - 2) { set_error("build_h: n=%lld exceeds 32-bit row indices", (long long)n); return 2; }
   if (ndet_old < 0 || ndet_old > n) { set_error("build_h: ndet_old out of range"); return 2; }
   // incremental semantics: the result equals a from-scratch build, so rebuild.
-  free_matrix(h);
+  {
+    HostMarks FM;
+    free_matrix(h);
+    FM.mark("free previous matrix");
+  }
   return h->NW == 1 ? build_impl<1>(h, n, dets_up, dets_dn) : build_impl<2>(h, n, dets_up, dets_dn);
 }
 
