@@ -174,6 +174,10 @@ int sqmc_b200_free(sqmc_b200_handle *h) {
   if (!h) return 0;
   free_matrix(h);
   if (h->d_orbsym) cudaFree(h->d_orbsym);
+  for (int k = 0; k < 2; k++) {
+    if (h->d_hb_val[k]) cudaFree(h->d_hb_val[k]);
+    if (h->d_hb_rs[k]) cudaFree(h->d_hb_rs[k]);
+  }
   if (h->d_integrals) cudaFree(h->d_integrals);
   if (h->d_combine_2) cudaFree(h->d_combine_2);
   if (h->d_kvec) cudaFree(h->d_kvec);

@@ -145,6 +145,11 @@ struct sqmc_b200_handle {
   // ---- heat-bath selection (select.cu) ----
   int32_t *d_orbsym = nullptr;        // [norb] orbital irreps (chem), set by sqmc_b200_system_orbital_symmetries
   std::vector<uint64_t> sel_new_up, sel_new_dn;  // result of the last hci_select (host, 16 B per det)
+  // heat-bath tables of the chem double excitations (norb <= 64): per hole pair (p,q) -- row p*norb+q -- the particle
+  // pairs (r,s) packed r | s<<8, sorted by decreasing |H|; [0] same spin (p<q, r<s), [1] opposite spin (p,r up; q,s dn)
+  double *d_hb_val[2] = {nullptr, nullptr};
+  uint16_t *d_hb_rs[2] = {nullptr, nullptr};
+  int hb_norb = 0;
   double build_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [5] candidates (local) [6] alpha groups [7] beta groups
 };
 

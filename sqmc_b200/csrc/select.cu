@@ -13,11 +13,17 @@
 // determinant (one warp per determinant) and evaluates the same element arithmetic (elements.cuh, no FMA).
 // Time-reversal symmetry: new_up == new_dn dropped for z<0, the time-reversed partner of det i dropped, results
 // mapped to the representative up <= dn (:6949-6952,6966-6971,7110-7132).
+// Chem doubles (norb <= 64) use heat-bath tables like the reference's dtm_hb (chemistry.f90:872-994): |H| of a double
+// excitation depends on the four orbitals only, so per hole pair the particle pairs are stored sorted by decreasing |H|
+// (built on the device with the same chem_double arithmetic on two-electron determinants -> bit-identical magnitudes);
+// a determinant then visits only the table range eps' < |H| <= min_H_already_done of each of its hole pairs instead of
+// all ~10^4 double excitations.  Singles, HEG and norb > 64 enumerate and evaluate every excitation.
 // The generated determinants are sorted by label, made unique, and those already in the list removed: what
 // remains is exactly the tail the reference appends to its list (hci.f90:945-991).
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "handle.h"
 
@@ -33,7 +39,83 @@ struct SelCtx {
   const double *coeffs, *min_H;
   double eps_var;
   int64_t n;
+  const double *hb_val[2];   // heat-bath tables (null: enumerate all doubles)
+  const uint16_t *hb_rs[2];
 };
+
+// ---- heat-bath tables
+struct RowOffset {
+  int n2;
+  __host__ __device__ __forceinline__ int operator()(const int &row) const { return row * n2; }
+};
+__global__ void hb_fill_kernel(ModelTables T, int os, double *val, uint16_t *rs) {
+  extern __shared__ int32_t c2s[];
+  const int norb = T.norb, n1 = norb + 1;
+  for (int k = threadIdx.x; k < n1 * n1; k += blockDim.x) c2s[k] = T.combine_2[k];
+  __syncthreads();
+  const int64_t n2 = (int64_t)norb * norb, tot = n2 * n2;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= tot) return;
+  const int row = (int)(t / n2), col = (int)(t % n2);
+  const int p = row / norb, q = row % norb, r = col / norb, s = col % norb;
+  double v = 0.0;
+  ChemCtx C{T.integrals, c2s, n1, T.enuc, T.sqrt2, T.sqrt2inv, T.z};
+  Bits<1> iu = b_zero<1>(), id = b_zero<1>(), ju = b_zero<1>(), jd = b_zero<1>();
+  if (!os) {
+    if (p < q && r < s && r != p && r != q && s != p && s != q) {
+      b_set(iu, p); b_set(iu, q); b_set(ju, r); b_set(ju, s);
+      v = fabs(chem_double(C, iu, id, ju, jd));
+    }
+  } else {
+    if (r != p && s != q) {
+      b_set(iu, p); b_set(id, q); b_set(ju, r); b_set(jd, s);
+      v = fabs(chem_double(C, iu, id, ju, jd));
+    }
+  }
+  val[t] = v;
+  rs[t] = (uint16_t)(r | (s << 8));
+}
+static int hb_build(sqmc_b200_handle *h) {
+  const ModelTables &T = h->T;
+  if (h->hb_norb == T.norb && h->d_hb_val[0]) return 0;
+  cudaStream_t s = G.stream;
+  const int norb = T.norb;
+  const int64_t n2 = (int64_t)norb * norb, tot = n2 * n2;
+  const int c2bytes = (norb + 1) * (norb + 1) * 4;
+  DevBuf<double> kin;
+  DevBuf<uint16_t> vin;
+  SQ_CHECK(kin.alloc(tot));
+  SQ_CHECK(vin.alloc(tot));
+  cub::CountingInputIterator<int> cnt0(0), cnt1(1);
+  cub::TransformInputIterator<int, RowOffset, cub::CountingInputIterator<int>> beg(cnt0, RowOffset{(int)n2}), end(cnt1, RowOffset{(int)n2});
+  for (int os = 0; os < 2; os++) {
+    if (h->d_hb_val[os]) { cudaFree(h->d_hb_val[os]); h->d_hb_val[os] = nullptr; }
+    if (h->d_hb_rs[os]) { cudaFree(h->d_hb_rs[os]); h->d_hb_rs[os] = nullptr; }
+    SQ_CUDA(cudaMalloc(&h->d_hb_val[os], tot * sizeof(double)));
+    SQ_CUDA(cudaMalloc(&h->d_hb_rs[os], tot * sizeof(uint16_t)));
+    hb_fill_kernel<<<(unsigned)div_up(tot, 256), 256, c2bytes, s>>>(T, os, kin.p, vin.p);
+    SQ_LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, tb, kin.p, h->d_hb_val[os], vin.p, h->d_hb_rs[os], (int)tot, (int)n2, beg, end, 0, 64, s);
+    DevBuf<char> tmp;
+    SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+    SQ_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp.p, tb, kin.p, h->d_hb_val[os], vin.p, h->d_hb_rs[os], (int)tot, (int)n2, beg, end, 0, 64, s));
+    g_launch_count += 1;
+    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  h->hb_norb = norb;
+  return 0;
+}
+// number of leading entries of a row (sorted by decreasing value) that are > x
+__device__ __forceinline__ int hb_count_gt(const double *row, int n, double x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (row[mid] > x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
 
 __device__ __forceinline__ int nth_set(const uint8_t *list, int k) { return list[k]; }
 
@@ -117,8 +199,64 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
         }
       }
     }
+    const bool use_hb = (T.model == MODEL_CHEM) && S.hb_val[0] != nullptr;
+    if (use_hb) {
+      // ---- doubles from the heat-bath tables: one lane per hole pair finds its table range, then the warp walks it
+      const int nss_u = nu_ * (nu_ - 1) / 2, nss_d = nd_ * (nd_ - 1) / 2, nos = nu_ * nd_;
+      const int npairs = nss_u + nss_d + nos;
+      const int n2 = norb * norb;
+      for (int pb0 = 0; pb0 < npairs; pb0 += 32) {
+        int kind = 0, p = 0, q = 0, lo = 0, hi = 0;  // kind 0: up-up, 1: dn-dn, 2: up-dn
+        const int pi = pb0 + lane;
+        if (pi < npairs) {
+          int t = pi;
+          if (t < nss_u + nss_d) {
+            kind = t < nss_u ? 0 : 1;
+            if (kind == 1) t -= nss_u;
+            const uint8_t *occ = kind == 0 ? occ_u : occ_d;
+            const int no = kind == 0 ? nu_ : nd_;
+            int a = 0;
+            while (t >= no - 1 - a) { t -= no - 1 - a; a++; }
+            p = occ[a]; q = occ[a + 1 + t];
+          } else {
+            kind = 2;
+            t -= nss_u + nss_d;
+            p = occ_u[t / nd_]; q = occ_d[t % nd_];
+          }
+          const double *row = S.hb_val[kind == 2] + (int64_t)(p * norb + q) * n2;
+          lo = hb_count_gt(row, n2, minH);  // |H| > min_H_already_done: handled in an earlier iteration
+          hi = hb_count_gt(row, n2, eps);   // |H| > eps'
+        }
+        const int npb = min(32, npairs - pb0);
+        for (int j = 0; j < npb; j++) {
+          const int kj = __shfl_sync(full, kind, j), pj = __shfl_sync(full, p, j), qj = __shfl_sync(full, q, j);
+          const int loj = __shfl_sync(full, lo, j), hij = __shfl_sync(full, hi, j);
+          const uint16_t *rsrow = S.hb_rs[kj == 2] + (int64_t)(pj * norb + qj) * n2;
+          for (int f0 = loj; f0 < hij; f0 += 32) {
+            const int f = f0 + lane;
+            bool keep = false;
+            Bits<NW> nu = u, nd = d;
+            if (f < hij) {
+              const int rs = rsrow[f], r = rs & 255, sx = rs >> 8;
+              if (kj == 0) {
+                keep = !b_test(u, r) && !b_test(u, sx);
+                b_clear(nu, pj); b_clear(nu, qj); b_set(nu, r); b_set(nu, sx);
+              } else if (kj == 1) {
+                keep = !b_test(d, r) && !b_test(d, sx);
+                b_clear(nd, pj); b_clear(nd, qj); b_set(nd, r); b_set(nd, sx);
+              } else {
+                keep = !b_test(u, r) && !b_test(d, sx);
+                b_clear(nu, pj); b_set(nu, r); b_clear(nd, qj); b_set(nd, sx);
+              }
+              if (keep && ts_excluded(nu, nd)) keep = false;
+            }
+            emit(keep, nu, nd);
+          }
+        }
+      }
+    }
     // ---- same-spin doubles
-    for (int spin = 0; spin < 2; spin++) {
+    for (int spin = 0; spin < 2 && !use_hb; spin++) {
       const uint8_t *occ = spin == 0 ? occ_u : occ_d, *vir = spin == 0 ? vir_u : vir_d;
       const int no = spin == 0 ? nu_ : nd_, nv = spin == 0 ? nvu : nvd;
       const int npo = no * (no - 1) / 2, npv = nv * (nv - 1) / 2;
@@ -149,7 +287,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
       }
     }
     // ---- opposite-spin doubles
-    {
+    if (!use_hb) {
       const int tu = nu_ * nvu, td = nd_ * nvd;
       const int64_t tot = (int64_t)tu * td;
       for (int64_t b0 = 0; b0 < tot; b0 += 32) {
@@ -266,7 +404,12 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
     SQ_CHECK(gather_strings(NW, up.p, idx.p, sup.p, n, s));
     SQ_CHECK(gather_strings(NW, dn.p, idx.p, sdn.p, n, s));
   }
-  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_var, n};
+  static int want_hb = -1;
+  if (want_hb < 0) { const char *e = getenv("SQMC_SELECT_TABLES"); want_hb = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool use_hb = want_hb && T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
+  if (use_hb) SQ_CHECK(hb_build(h));
+  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_var, n,
+               {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
   const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
   // count pass over all determinants
   DevBuf<int32_t> counts;
