@@ -115,6 +115,24 @@ class SparseHamiltonian:
         check(self._L.sqmc_b200_import_upper(self._h, len(cnt), _p(cnt), _p(idx), _p(val)))
         self.n = len(cnt)
 
+    def dump_dtm_projector(self, path, dets_up, dets_dn, dtm_energy=0.0, tau=None, n_core_orb=0):
+        """Write the resident matrix as the reference's deterministic-projector text file (do_walk.f90:964-1013).
+        The file holds H itself; pass tau when the handle currently stores -tau*H (after scale_values(-tau))."""
+        from . import formats
+        cnt, idx, val = self.export_upper()
+        if tau is not None:
+            val = -val / tau          # do_walk.f90:1007
+        formats.write_dtm_projector(path, dets_up, dets_dn, cnt, idx, val, dtm_energy=dtm_energy, n_core_orb=n_core_orb)
+
+    def load_dtm_projector(self, path, tau, nup, ndn, n_core_orb=0):
+        """Read a deterministic-projector file and keep -tau*H resident (do_walk.f90:883-945: the values are multiplied
+        by -tau right after the read).  -> (imp_up, imp_dn) of the file."""
+        from . import formats
+        d = formats.read_dtm_projector(path, nup, ndn, n_core_orb=n_core_orb)
+        self.import_upper(d["counts"], d["indices"], d["values"])
+        self.scale_values(-tau)
+        return d["up"], d["dn"]
+
     def nnz(self):
         n, u, f = C.c_int64(), C.c_int64(), C.c_int64()
         check(self._L.sqmc_b200_nnz(self._h, C.byref(n), C.byref(u), C.byref(f)))
