@@ -621,7 +621,7 @@ void free_matrix(sqmc_b200_handle *h) {
     p = nullptr;
   };
   F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
-  F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_split_lo); F(h->d_split_hi);
+  F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_x2); F(h->d_y2); F(h->d_split_lo); F(h->d_split_hi);
   F(h->d_gA_off); F(h->d_eA); F(h->d_gB_off); F(h->d_eBpos); F(h->d_bidx); F(h->d_binv);
   wcsr_free(h);
   h->bundle_R = 0;

@@ -258,6 +258,84 @@ __global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__
   if (lane < R && r0 + lane < nloc) y[r0 + lane] = mine;
 }
 
+// two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x2 / y2 hold the two vectors
+// interleaved (x2[2*col + k]), so one 16-byte gather serves both and the matrix is streamed once:
+// algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)
+__device__ __forceinline__ double2 bld_x2(const double *p, const BPolicies &P) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(P.x));
+  return r;
+}
+template <int R, int U>
+__global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
+                                                                const double *__restrict__ vals, const double *__restrict__ x2, double *__restrict__ y2) {
+  const BPolicies P;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nb) return;
+  const int64_t r0 = b * R;
+  const int64_t e = rowptr[min(r0 + R, nloc)];
+  int64_t kb = rowptr[r0];
+  double acc0[R], acc1[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) { acc0[r] = 0.0; acc1[r] = 0.0; }
+  int32_t c[U];
+  double v[U];
+  bool have = kb + 32 * U <= e;
+  if (have) {
+#pragma unroll
+    for (int u = 0; u < U; u++) c[u] = bld_col(cols + kb + lane + 32 * u, P);
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = bld_val(vals + kb + lane + 32 * u, P);
+  }
+  while (have) {
+    double2 xx[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) xx[u] = bld_x2(x2 + 2 * (int64_t)(c[u] >> kBShift), P);
+    const int64_t kn = kb + 32 * U;
+    const bool hn = kn + 32 * U <= e;
+    int32_t cn[U];
+    double vn[U];
+    if (hn) {
+#pragma unroll
+      for (int u = 0; u < U; u++) cn[u] = bld_col(cols + kn + lane + 32 * u, P);
+#pragma unroll
+      for (int u = 0; u < U; u++) vn[u] = bld_val(vals + kn + lane + 32 * u, P);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      badd<R>(acc0, c[u], v[u] * xx[u].x);
+      badd<R>(acc1, c[u], v[u] * xx[u].y);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) { c[u] = cn[u]; v[u] = vn[u]; }
+    kb = kn;
+    have = hn;
+  }
+  for (int64_t k = kb + lane; k < e; k += 32) {
+    const int32_t cc = bld_col(cols + k, P);
+    const double vv = bld_val(vals + k, P);
+    const double2 xv = bld_x2(x2 + 2 * (int64_t)(cc >> kBShift), P);
+    badd<R>(acc0, cc, vv * xv.x);
+    badd<R>(acc1, cc, vv * xv.y);
+  }
+  double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    double a0 = acc0[r], a1 = acc1[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == r) { m0 = a0; m1 = a1; }
+  }
+  if (lane < R && r0 + lane < nloc) {
+    y2[2 * (r0 + lane)] = m0;
+    y2[2 * (r0 + lane) + 1] = m1;
+  }
+}
+
 // ------------------------------------------------------------------ host side
 // default: bundles of 4 rows (measured best on B200, profiles/r01_bundle_experiment.txt); SQMC_BUNDLE=0|2|4|8 overrides
 static int bundle_want() {
@@ -367,6 +445,27 @@ int bundle_spmv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s)
     if (R == 2) SQ_BL(spmv_bundle_kernel<2>); else if (R == 4) SQ_BL(spmv_bundle_kernel<4>); else SQ_BL(spmv_bundle_kernel<8>);
   }
 #undef SQ_BL
+  SQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// y2 = H x2 for two interleaved vectors; only on bundled matrices (the caller falls back to two H.v otherwise)
+int bundle_spmm2(sqmc_b200_handle *h, const double *x2, double *y2, cudaStream_t s) {
+  const int64_t nloc = h->row1 - h->row0;
+  const int R = h->bundle_R;
+  if (!R) { set_error("bundle_spmm2: matrix is not in row-bundle order"); return 2; }
+  const int64_t nb = div_up(nloc, (int64_t)R);
+  if (nb == 0) return 0;
+  const unsigned grid = (unsigned)div_up(nb * 32, (int64_t)256);
+  const char *ue = getenv("SQMC_SPMM_PIPE");
+  const int U = ue ? atoi(ue) : 4;  // measured at 10^7 dets: 25.7 ms per pair with 4 blocks in flight, 29.8 ms with 2
+#define SQ_BM(KERN) KERN<<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x2, y2)
+  if (U == 4) {
+    if (R == 2) SQ_BM((spmm2_bundle_pipe_kernel<2, 4>)); else if (R == 4) SQ_BM((spmm2_bundle_pipe_kernel<4, 4>)); else SQ_BM((spmm2_bundle_pipe_kernel<8, 2>));
+  } else {
+    if (R == 2) SQ_BM((spmm2_bundle_pipe_kernel<2, 2>)); else if (R == 4) SQ_BM((spmm2_bundle_pipe_kernel<4, 2>)); else SQ_BM((spmm2_bundle_pipe_kernel<8, 2>));
+  }
+#undef SQ_BM
   SQ_LAUNCH_CHECK();
   return 0;
 }

@@ -164,10 +164,11 @@ struct Dav {
   cudaStream_t s;
   int64_t n, nloc, ld;
   double *V = nullptr, *HV = nullptr, *W = nullptr, *HW = nullptr, *diag = nullptr, *partial = nullptr, *scal = nullptr, *coef = nullptr;
+  double *resid = nullptr;  // n_states residual norms kept on the device until their Krylov columns are fetched
   double *h_scal = nullptr;  // pinned
   int nmv = 0;
   ~Dav() {
-    for (double *p : {V, HV, W, HW, diag, partial, scal, coef})
+    for (double *p : {V, HV, W, HW, diag, partial, scal, coef, resid})
       if (p) cudaFree(p);
     if (h_scal) cudaFreeHost(h_scal);
   }
@@ -213,6 +214,16 @@ struct Dav {
     nmv++;
     return 0;
   }
+  // the same for a list of basis columns: pairs share one pass over the matrix (two-vector kernel, csrc/bundle.cu)
+  int apply_h_block(const std::vector<int> &cols_) {
+    size_t k = 0;
+    for (; k + 1 < cols_.size(); k += 2) {
+      SQ_CHECK(spmv_pair(h, V + (int64_t)cols_[k] * ld, V + (int64_t)cols_[k + 1] * ld, HV + (int64_t)cols_[k] * ld, HV + (int64_t)cols_[k + 1] * ld, s));
+      nmv += 2;
+    }
+    if (k < cols_.size()) SQ_CHECK(apply_h(V + (int64_t)cols_[k] * ld, HV + (int64_t)cols_[k] * ld));
+    return 0;
+  }
 };
 
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
@@ -247,6 +258,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   SQ_CUDA(cudaMalloc(&D.partial, (size_t)kDotBlocks * (m + 2) * sizeof(double)));
   SQ_CUDA(cudaMalloc(&D.scal, (size_t)(m + 8) * sizeof(double)));
   SQ_CUDA(cudaMalloc(&D.coef, (size_t)m * n_states * sizeof(double)));
+  SQ_CUDA(cudaMalloc(&D.resid, (size_t)n_states * sizeof(double)));
   SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(m + 8) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * m * sizeof(double), s));
   auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
@@ -298,7 +310,11 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     return 0;
   }
   SQ_CHECK(extract_diag(h, D.diag, s));
-  for (int i = 0; i < n_states; i++) SQ_CHECK(D.apply_h(Vc(i), HVc(i)));
+  {
+    std::vector<int> first(n_states);
+    for (int i = 0; i < n_states; i++) first[i] = i;
+    SQ_CHECK(D.apply_h_block(first));
+  }
   for (int j = 0; j < n_states; j++) {
     SQ_CHECK(D.dots(D.V, n_states, HVc(j), D.scal));
     SQ_CHECK(D.fetch(D.scal, n_states, col.data()));
@@ -311,6 +327,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
 
   const int64_t niter = std::min<int64_t>(n, (int64_t)n_states * iterations);
   bool converged = false;
+  std::vector<int> pending;  // basis columns of the current block whose H.v is still to be applied
   for (int64_t it = n_states + 1; it <= niter * 10; it++) {
     const int it_circ = (int)((it - 1) % niter) + 1;
     if (it > niter && it_circ == 1) {  // restart with the current Ritz vectors (:2144-2163)
@@ -331,7 +348,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
       resid_precond_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.HW + (int64_t)i * ld, D.W + (int64_t)i * ld, D.diag, lowest[i], Vc(c), nloc);
       SQ_LAUNCH_CHECK();
     }
-    double *d_resid = D.scal + m + 1;  // kept until the end of the iteration
+    double *d_resid = D.resid + i;  // kept on the device until this column's Krylov entries are fetched
     SQ_CHECK(D.dots(Vc(c), 1, Vc(c), d_resid));
     for (int k = 0; k < c; k++) {  // modified Gram-Schmidt (:2176-2179)
       SQ_CHECK(D.dots(Vc(c), 1, Vc(k), D.scal + m + 2));
@@ -340,19 +357,28 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
     SQ_CHECK(D.dots(Vc(c), 1, Vc(c), D.scal + m + 2));
     SQ_CHECK(D.normalize(Vc(c), D.scal + m + 2));
     PT.stop(1);  // residual + Gram-Schmidt
+    // The new vector of state i+1 does not depend on H times the vector of state i (only on the Ritz pairs of the last
+    // subspace diagonalisation and on the basis itself), so the H.v of one block of n_states vectors are applied
+    // together -- identical arithmetic per vector, one pass over the matrix per pair of vectors.
+    pending.push_back(c);
+    if (i != n_states - 1 && it_circ != niter) continue;
     PT.start();
-    SQ_CHECK(D.apply_h(Vc(c), HVc(c)));
+    SQ_CHECK(D.apply_h_block(pending));
     PT.stop(2);  // H.v
     PT.start();
-    SQ_CHECK(D.dots(D.V, c + 1, HVc(c), D.scal));  // Krylov column (:2194-2197)
-    SQ_CUDA(cudaMemcpyAsync(D.scal + c + 1, d_resid, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SQ_CHECK(D.fetch(D.scal, c + 2, col.data()));
-    for (int k = 0; k <= c; k++) { HK(k, c) = col[k]; HK(c, k) = col[k]; }
-    residual_norm[i] = col[c + 1];
+    for (int cc : pending) {
+      const int ii = cc % n_states;
+      SQ_CHECK(D.dots(D.V, cc + 1, HVc(cc), D.scal));  // Krylov column (:2194-2197)
+      SQ_CUDA(cudaMemcpyAsync(D.scal + cc + 1, D.resid + ii, sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(D.fetch(D.scal, cc + 2, col.data()));
+      for (int k = 0; k <= cc; k++) { HK(k, cc) = col[k]; HK(cc, k) = col[k]; }
+      residual_norm[ii] = col[cc + 1];
+      double rs = 0;
+      for (int q = 0; q < n_states; q++) rs += residual_norm[q];
+      if (rs < 1.e-12) converged = true;
+    }
+    pending.clear();
     PT.stop(3);  // Krylov column
-    double rs = 0;
-    for (int q = 0; q < n_states; q++) rs += residual_norm[q];
-    if (rs < 1.e-12) converged = true;
 
     if (it_circ % n_states == 0) {
       const int dim = it_circ;

@@ -142,6 +142,8 @@ struct sqmc_b200_handle {
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
   double *d_tmp = nullptr; // n (caller order staging)
+  double *d_x2 = nullptr;  // 2n: two vectors interleaved (global length), allocated on first use by the two-vector H.v
+  double *d_y2 = nullptr;  // 2*local rows
   // ---- heat-bath selection (select.cu) ----
   int32_t *d_orbsym = nullptr;        // [norb] orbital irreps (chem), set by sqmc_b200_system_orbital_symmetries
   std::vector<uint64_t> sel_new_up, sel_new_dn;  // result of the last hci_select (host, 16 B per det)
@@ -175,6 +177,9 @@ int permute_scatter(const double *src, const int32_t *idx, double *dst, int64_t 
 int scale_array(double *a, int64_t n, double r, cudaStream_t s);
 int projector_epilogue(double *deltaw, const double *w, double c, int64_t n, cudaStream_t s);  // deltaw += c*w
 int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-place allgather of row blocks
+int allgather_rows_k(sqmc_b200_handle *h, double *x_full, int k, cudaStream_t s);  // same for k interleaved vectors
+// HVa = H Va, HVb = H Vb (local blocks) with ONE pass over the matrix when it is in row-bundle order
+int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *HVa, double *HVb, cudaStream_t s);
 // all-gather x (own block valid on entry) and multiply; under nranks>1 the all-gather runs on the comm stream while the
 // local-column part of every row is multiplied, the remote-column part follows
 int spmv_gather_multiply(sqmc_b200_handle *h, double *x_full, double *y_dev, cudaStream_t s);
@@ -193,6 +198,7 @@ int bundle_encode(sqmc_b200_handle *h);  // plain CSR -> row bundles in place (S
 int bundle_encode_r(sqmc_b200_handle *h, int R);  // same with an explicit bundle size
 int bundle_decode(sqmc_b200_handle *h);  // exact inverse
 int bundle_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
+int bundle_spmm2(sqmc_b200_handle *h, const double *x2_dev, double *y2_dev, cudaStream_t s);  // two interleaved vectors
 int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 // davidson.cu
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,

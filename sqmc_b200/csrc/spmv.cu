@@ -309,4 +309,51 @@ int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s) {
   return 0;
 }
 
+int allgather_rows_k(sqmc_b200_handle *h, double *x_full, int k, cudaStream_t s) {
+  if (G.nranks == 1) return 0;
+  ncclGroupStart();
+  for (int r = 0; r < G.nranks; r++) {
+    int64_t c = (h->row_starts[r + 1] - h->row_starts[r]) * k;
+    if (c == 0) continue;
+    ncclBroadcast(x_full + h->row_starts[r] * k, x_full + h->row_starts[r] * k, c, ncclDouble, r, G.comm, s);
+  }
+  ncclResult_t r = ncclGroupEnd();
+  if (r != ncclSuccess) { set_error("allgather_rows_k: NCCL error %s", ncclGetErrorString(r)); return 3; }
+  return 0;
+}
+
+__global__ void interleave2_kernel(const double *a, const double *b, double *out2, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { out2[2 * i] = a[i]; out2[2 * i + 1] = b[i]; }
+}
+__global__ void deinterleave2_kernel(const double *in2, double *a, double *b, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = in2[2 * i]; b[i] = in2[2 * i + 1]; }
+}
+
+int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *HVa, double *HVb, cudaStream_t s) {
+  const int64_t nloc = h->row1 - h->row0;
+  if (!h->bundle_R) {  // plain rows / WCSR: two single-vector products
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Va, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CHECK(spmv_gather_multiply(h, h->d_x, HVa, s));
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Vb, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return spmv_gather_multiply(h, h->d_x, HVb, s);
+  }
+  if (!h->d_x2) {
+    SQ_CUDA(cudaMalloc(&h->d_x2, std::max<int64_t>(h->n, 1) * 2 * sizeof(double)));
+    SQ_CUDA(cudaMalloc(&h->d_y2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
+  }
+  if (nloc > 0) {
+    interleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(Va, Vb, h->d_x2 + 2 * h->row0, nloc);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CHECK(allgather_rows_k(h, h->d_x2, 2, s));
+  SQ_CHECK(bundle_spmm2(h, h->d_x2, h->d_y2, s));
+  if (nloc > 0) {
+    deinterleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(h->d_y2, HVa, HVb, nloc);
+    SQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace sqmc
