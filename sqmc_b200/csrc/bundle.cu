@@ -35,7 +35,8 @@ __global__ void bundle_len_kernel(const int64_t *rowptr, int64_t nloc, int R, in
 
 // ------------------------------------------------------------------ encode: plain rows -> (column,row)-ordered bundle
 template <int R>
-__global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, int32_t *cols, double *vals, int cap) {
+__global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, int32_t *cols, double *vals, int cap,
+                                                            int len_lo, bool take_longer) {
   extern __shared__ __align__(8) unsigned char bsm[];
   double *sv = reinterpret_cast<double *>(bsm);
   int32_t *sc = reinterpret_cast<int32_t *>(sv + cap);
@@ -45,6 +46,9 @@ __global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__res
     __syncthreads();
     const int64_t base = rp[0];
     const int L = (int)min(rp[R] - base, (int64_t)0x7fffffff);
+    // this launch handles bundles with len_lo < length <= cap (and the longer, tag-only ones when take_longer):
+    // short bundles run with a small shared-memory footprint, i.e. several CTAs per SM
+    if (rp[R] - base <= len_lo || (rp[R] - base > cap && !take_longer)) { __syncthreads(); continue; }
     int off[R + 1];
 #pragma unroll
     for (int r = 0; r <= R; r++) off[r] = (int)(rp[r] - base);
@@ -359,10 +363,18 @@ static int bundle_pipe() {  // read per launch (a getenv is ~100 ns) so that scr
 template <int R>
 static int encode_t(sqmc_b200_handle *h, int cap, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0, nb = div_up(nloc, (int64_t)R);
+  SQ_CUDA(cudaFuncSetAttribute(bundle_encode_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 12));
+  // two passes: bundles up to kSmall entries with 4 CTAs per SM, the rest with the full staging capacity
+  const int kSmall = 4096;
+  int lo = 0;
+  if (cap > kSmall) {
+    bundle_encode_kernel<R><<<(unsigned)std::min<int64_t>(nb, (int64_t)G.sm_count * 4), 512, kSmall * 12, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, kSmall, 0, false);
+    SQ_LAUNCH_CHECK();
+    lo = kSmall;
+  }
   const int smem = cap * 12;
-  SQ_CUDA(cudaFuncSetAttribute(bundle_encode_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int per_sm = std::max(1, std::min(4, (220 * 1024) / std::max(smem, 1)));
-  bundle_encode_kernel<R><<<(unsigned)std::min<int64_t>(nb, (int64_t)G.sm_count * per_sm), 512, smem, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, cap);
+  bundle_encode_kernel<R><<<(unsigned)std::min<int64_t>(nb, (int64_t)G.sm_count * per_sm), 512, smem, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, cap, lo, true);
   SQ_LAUNCH_CHECK();
   return 0;
 }
