@@ -24,8 +24,18 @@ def main():
     ap.add_argument("--target", type=int, default=10_000_000)
     ap.add_argument("--iters-per-eps", type=int, default=1)
     args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:   # torchrun: selection, build and Davidson are all sharded over the ranks
+        import torch
+        import torch.distributed as dist
+        from sqmc_b200 import _lib
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        obj = [_lib.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        _lib.init(device=local, rank=rank, nranks=world, unique_id=obj[0])
     cs = sq.ChemSystem(os.path.join(ROOT, "data", "C2_v2z_curve", "r" + args.r, "FCIDUMP"), time_sym=args.time_sym, z=1)
-    H = sq.SparseHamiltonian(cs)
+    H = sq.SparseHamiltonian(cs, device=local)
     up = sq.dets_to_u64([cs.hf_up])
     dn = sq.dets_to_u64([cs.hf_dn])
     wts = np.ones((1, 1))
@@ -56,9 +66,10 @@ def main():
             d = H.davidson_sparse(n_states=1, initial_vector=v0)
             t_dav = time.perf_counter() - t0
             wts = d["evecs"]
-            print(json.dumps({"iter": it, "eps_var": eps, "n_dets": n, "n_new": int(len(nu)), "nnz_upper": int(nnz), "energy": float(d["evals"][0]),
-                              "n_matvec": d["n_matvec"], "select_s": t_sel, "build_s": t_build, "davidson_s": t_dav,
-                              "elapsed_s": time.perf_counter() - t_start}), flush=True)
+            if rank == 0:
+              print(json.dumps({"n_gpus": world, "iter": it, "eps_var": eps, "n_dets": n, "n_new": int(len(nu)), "nnz_upper": int(nnz), "energy": float(d["evals"][0]),
+                                "n_matvec": d["n_matvec"], "select_s": t_sel, "build_s": t_build, "davidson_s": t_dav,
+                                "elapsed_s": time.perf_counter() - t_start}), flush=True)
             if n >= args.target:
                 return
 

@@ -32,6 +32,51 @@ static int require_init() {
 
 using namespace sqmc;
 
+namespace sqmc {
+static const uint64_t kPoolKeepBytes = 16ull << 30;  // cached by the device memory pool between calls
+static bool g_use_pool = true;
+int devbuf_alloc(void **p, size_t bytes) {
+  cudaError_t e = g_use_pool ? cudaMallocAsync(p, bytes, G.stream) : cudaMalloc(p, bytes);
+  if (e != cudaSuccess && g_use_pool) {  // pool exhausted next to a large matrix: give the cache back and retry
+    cudaGetLastError();
+    cudaStreamSynchronize(G.stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMallocAsync(p, bytes, G.stream);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("device allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return 1;
+  }
+  return 0;
+}
+void devbuf_free(void *p) {
+  if (!p) return;
+  if (g_use_pool && G.stream) cudaFreeAsync(p, G.stream);
+  else cudaFree(p);
+}
+// cudaMalloc for the long-lived large arrays: when it fails, the temporaries cached by the pool are released first
+int big_malloc(void **p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamSynchronize(G.stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+    *p = nullptr;
+    return 1;
+  }
+  return 0;
+}
+}  // namespace sqmc
+
 extern "C" {
 
 const char *sqmc_b200_last_error(void) { return g_last_error.c_str(); }
@@ -70,6 +115,18 @@ int sqmc_b200_init(int device, int rank, int nranks, const void *id128) {
   SQ_CUDA(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
   SQ_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
   SQ_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
+  {
+    const char *pe = getenv("SQMC_POOL");
+    sqmc::g_use_pool = !(pe && atoi(pe) == 0);
+    cudaMemPool_t pool;
+    if (sqmc::g_use_pool && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = sqmc::kPoolKeepBytes;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      sqmc::g_use_pool = false;
+      cudaGetLastError();
+    }
+  }
   if (G.nranks > 1) {
     if (!id128) { set_error("sqmc_b200_init: nranks>1 needs an ncclUniqueId"); return 1; }
     ncclUniqueId id;

@@ -37,25 +37,6 @@
 
 namespace sqmc {
 
-// host wall-clock marks of one build (SQMC_BUILD_PROFILE=1 prints them): finds time spent outside kernels
-// (allocation of the ~100 GB arrays, host loops, synchronisation) that the CUDA-event phases do not see
-struct HostMarks {
-  bool on;
-  std::chrono::steady_clock::time_point t0, last;
-  HostMarks() {
-    const char *e = getenv("SQMC_BUILD_PROFILE");
-    on = e && atoi(e) > 0;
-    t0 = last = std::chrono::steady_clock::now();
-  }
-  void mark(const char *what) {
-    if (!on) return;
-    cudaDeviceSynchronize();
-    auto t = std::chrono::steady_clock::now();
-    fprintf(stderr, "[sqmc build] %-28s %9.1f ms  (t = %9.1f ms)\n", what, std::chrono::duration<double, std::milli>(t - last).count(),
-            std::chrono::duration<double, std::milli>(t - t0).count());
-    last = t;
-  }
-};
 
 
 // ------------------------------------------------------------------ helpers
@@ -919,8 +900,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   // ---- final arrays (capacity = candidate upper bound)
   h->capacity = std::max<int64_t>(Tloc, 1);
   // + kSlack entries: the WCSR kernel's masked 128-bit loads may touch up to 2 steps past the last entry
-  SQ_CUDA(cudaMalloc(&h->d_cols, (h->capacity + kSlack) * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_vals, (h->capacity + kSlack) * sizeof(double)));
+  SQ_CHECK(big_malloc((void **)&h->d_cols, (h->capacity + kSlack) * sizeof(int32_t)));
+  SQ_CHECK(big_malloc((void **)&h->d_vals, (h->capacity + kSlack) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(h->d_cols + h->capacity, 0, kSlack * sizeof(int32_t), s));
   SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
   SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));

@@ -169,7 +169,7 @@ struct Dav {
   int nmv = 0;
   ~Dav() {
     for (double *p : {V, HV, W, HW, diag, partial, scal, coef, resid})
-      if (p) cudaFree(p);
+      if (p) devbuf_free(p);  // stream-ordered, back into the pool cache: the next HCI iteration reuses it
     if (h_scal) cudaFreeHost(h_scal);
   }
   unsigned blocks(int64_t cnt) const { return (unsigned)std::max<int64_t>(1, div_up(cnt, 256)); }
@@ -250,15 +250,15 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   cudaStream_t s = D.s;
   int iterations = (int)std::min<int64_t>(n, max_vec);
   const int m = n_states * iterations;
-  SQ_CUDA(cudaMalloc(&D.V, (size_t)ld * m * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.HV, (size_t)ld * m * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.W, (size_t)ld * n_states * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.HW, (size_t)ld * n_states * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.diag, (size_t)ld * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.partial, (size_t)kDotBlocks * (m + 2) * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.scal, (size_t)(m + 8) * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.coef, (size_t)m * n_states * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&D.resid, (size_t)n_states * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.V, (size_t)ld * m * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.HV, (size_t)ld * m * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.W, (size_t)ld * n_states * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.HW, (size_t)ld * n_states * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.diag, (size_t)ld * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.partial, (size_t)kDotBlocks * (m + 2) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(m + 8) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)m * n_states * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.resid, (size_t)n_states * sizeof(double)));
   SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(m + 8) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * m * sizeof(double), s));
   auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };

@@ -3,6 +3,9 @@
 #pragma once
 #include <nccl.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -21,7 +24,13 @@ struct Global {
 };
 extern Global G;
 
-// RAII device buffer
+// RAII device buffer for temporaries.  Stream-ordered allocation from the device's default memory pool on the library
+// stream (the pool keeps up to kPoolKeepBytes cached, sqmc_b200_init): the selection / build / conversion paths allocate
+// and free dozens of temporaries per call and cudaMalloc / cudaFree cost milliseconds each next to a ~100 GB matrix.
+// SQMC_POOL=0 falls back to cudaMalloc / cudaFree.
+int devbuf_alloc(void **p, size_t bytes);
+void devbuf_free(void *p);
+int big_malloc(void **p, size_t bytes);  // cudaMalloc that first releases the pool's cache when memory is short
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -30,16 +39,14 @@ struct DevBuf {
     release();
     n = count;
     if (count <= 0) return 0;
-    cudaError_t e = cudaMalloc(&p, (size_t)count * sizeof(T));
-    if (e != cudaSuccess) {
-      set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * sizeof(T)), cudaGetErrorString(e));
+    if (devbuf_alloc((void **)&p, (size_t)count * sizeof(T))) {
       p = nullptr;
       return 1;
     }
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) devbuf_free(p);
     p = nullptr;
     n = 0;
   }
@@ -50,6 +57,27 @@ struct DevBuf {
     return q;
   }
   ~DevBuf() { release(); }
+};
+
+// host wall-clock marks of one build (SQMC_BUILD_PROFILE=1 prints them): finds time spent outside kernels
+// (allocation of the ~100 GB arrays, host loops, synchronisation) that the CUDA-event phases do not see
+struct HostMarks {
+  bool on;
+  const char *tag;
+  std::chrono::steady_clock::time_point t0, last;
+  explicit HostMarks(const char *env = "SQMC_BUILD_PROFILE", const char *tag_ = "build") : tag(tag_) {
+    const char *e = getenv(env);
+    on = e && atoi(e) > 0;
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sqmc %s] %-28s %9.1f ms  (t = %9.1f ms)\n", tag, what, std::chrono::duration<double, std::milli>(t - last).count(),
+            std::chrono::duration<double, std::milli>(t - t0).count());
+    last = t;
+  }
 };
 
 // number of degree bins for the SpMV (sub-warp vector sizes 2,4,8,16,32 + CTA-per-row)

@@ -312,6 +312,11 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
   if (!FILL && lane == 0) counts[i - i_begin] = cnt;
 }
 
+__global__ void stride_index_kernel(int32_t *idx, int64_t m, int first, int stride) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < m) idx[k] = (int32_t)(first + k * stride);
+}
+
 template <int NW>
 __global__ void uniq_flag_kernel(const uint64_t *a, const uint64_t *b, int32_t *flag, int64_t m) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -384,6 +389,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
                        int64_t *n_new_out) {
   cudaStream_t s = G.stream;
   const ModelTables &T = h->T;
+  HostMarks HM("SQMC_SELECT_PROFILE", "select");
   DevBuf<uint64_t> up, dn, sup, sdn;
   DevBuf<double> dc, dm;
   SQ_CHECK(up.alloc(n * NW));
@@ -404,33 +410,64 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
     SQ_CHECK(gather_strings(NW, up.p, idx.p, sup.p, n, s));
     SQ_CHECK(gather_strings(NW, dn.p, idx.p, sdn.p, n, s));
   }
+  HM.mark("upload + sorted copy of the list");
   static int want_hb = -1;
   if (want_hb < 0) { const char *e = getenv("SQMC_SELECT_TABLES"); want_hb = (e && atoi(e) == 0) ? 0 : 1; }
   const bool use_hb = want_hb && T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
   if (use_hb) SQ_CHECK(hb_build(h));
-  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_var, n,
+  // nranks > 1: the determinants are dealt round-robin to the ranks (the early, large-coefficient determinants of an HCI
+  // list generate most of the connections, so contiguous slices would be unbalanced); every rank expands its share,
+  // removes duplicates and members of the list locally, and the survivors are all-gathered and merged below
+  int64_t nd = n;
+  const uint64_t *eu = up.p, *ed = dn.p;
+  const double *ec = dc.p, *em = dm.p;
+  DevBuf<uint64_t> lu, ld_;
+  DevBuf<double> lc, lm;
+  if (G.nranks > 1) {
+    nd = n > G.rank ? (n - G.rank + G.nranks - 1) / G.nranks : 0;
+    DevBuf<int32_t> sidx;
+    SQ_CHECK(sidx.alloc(std::max<int64_t>(nd, 1)));
+    SQ_CHECK(lu.alloc(std::max<int64_t>(nd, 1) * NW));
+    SQ_CHECK(ld_.alloc(std::max<int64_t>(nd, 1) * NW));
+    SQ_CHECK(lc.alloc(std::max<int64_t>(nd, 1)));
+    SQ_CHECK(lm.alloc(std::max<int64_t>(nd, 1)));
+    if (nd > 0) {
+      stride_index_kernel<<<(unsigned)div_up(nd, 256), 256, 0, s>>>(sidx.p, nd, G.rank, G.nranks);
+      SQ_LAUNCH_CHECK();
+      SQ_CHECK(gather_strings(NW, up.p, sidx.p, lu.p, nd, s));
+      SQ_CHECK(gather_strings(NW, dn.p, sidx.p, ld_.p, nd, s));
+      SQ_CHECK(permute_gather(dc.p, sidx.p, lc.p, nd, s));
+      SQ_CHECK(permute_gather(dm.p, sidx.p, lm.p, nd, s));
+      SQ_CUDA(cudaStreamSynchronize(s));
+    }
+    eu = lu.p; ed = ld_.p; ec = lc.p; em = lm.p;
+  }
+  SelCtx<NW> S{T, h->d_orbsym, eu, ed, ec, em, eps_var, nd,
                {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
   const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
   // count pass over all determinants
   DevBuf<int32_t> counts;
-  SQ_CHECK(counts.alloc(n + 1));
-  SQ_CUDA(cudaMemsetAsync(counts.p, 0, (n + 1) * sizeof(int32_t), s));
-  select_kernel<NW, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr);
-  SQ_LAUNCH_CHECK();
-  std::vector<int32_t> hc(n + 1);
-  SQ_CUDA(cudaMemcpyAsync(hc.data(), counts.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  SQ_CHECK(counts.alloc(nd + 1));
+  SQ_CUDA(cudaMemsetAsync(counts.p, 0, (nd + 1) * sizeof(int32_t), s));
+  if (nd > 0) {
+    select_kernel<NW, false><<<(unsigned)div_up(nd * 32, 128), 128, c2bytes, s>>>(S, 0, nd, counts.p, nullptr, nullptr, nullptr);
+    SQ_LAUNCH_CHECK();
+  }
+  std::vector<int32_t> hc(nd + 1);
+  SQ_CUDA(cudaMemcpyAsync(hc.data(), counts.p, (nd + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   SQ_CUDA(cudaStreamSynchronize(s));
-  std::vector<int64_t> prefix(n + 1, 0);
-  for (int64_t i = 0; i < n; i++) prefix[i + 1] = prefix[i] + hc[i];
+  std::vector<int64_t> prefix(nd + 1, 0);
+  for (int64_t i = 0; i < nd; i++) prefix[i + 1] = prefix[i] + hc[i];
+  HM.mark("count pass + prefix");
   // chunks of determinants bounded by generated candidates; per chunk: fill, sort, unique, drop members of the list
   const int64_t kChunk = 1ll << 27;
   DevBuf<uint64_t> acc_a, acc_b;  // unique new determinants found so far (unsorted union of the chunk results)
   int64_t acc_n = 0;
   int64_t i0 = 0;
-  while (i0 < n) {
+  while (i0 < nd) {
     int64_t i1 = std::upper_bound(prefix.begin() + i0 + 1, prefix.end(), prefix[i0] + kChunk) - prefix.begin() - 1;
     if (i1 <= i0) i1 = i0 + 1;
-    if (i1 > n) i1 = n;
+    if (i1 > nd) i1 = nd;
     const int64_t m = prefix[i1] - prefix[i0];
     if (m >= (1ll << 31)) { set_error("hci_select: one determinant generates too many connections"); return 2; }
     DevBuf<uint64_t> ca, cb, ra, rb;
@@ -463,10 +500,51 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
     }
     i0 = i1;
   }
+  HM.mark("fill + sort/unique chunks");
   // final sort + unique across chunks (members of the list are already gone)
   DevBuf<uint64_t> fa, fb;
   int64_t nf = 0;
   SQ_CHECK(sort_unique_new<NW>(T.norb, acc_a, acc_b, acc_n, nullptr, nullptr, 0, fa, fb, nf, s));
+  if (G.nranks > 1) {  // merge the rank-local results: sizes, padded all-gather, sort + unique once more
+    DevBuf<int64_t> cnt_dev;
+    SQ_CHECK(cnt_dev.alloc(G.nranks));
+    SQ_CUDA(cudaMemcpyAsync(cnt_dev.p + G.rank, &nf, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ncclResult_t rc = ncclAllGather(cnt_dev.p + G.rank, cnt_dev.p, 1, ncclInt64, G.comm, s);
+    if (rc != ncclSuccess) { set_error("hci_select: ncclAllGather(sizes) failed: %s", ncclGetErrorString(rc)); return 3; }
+    std::vector<int64_t> cnts(G.nranks);
+    SQ_CUDA(cudaMemcpyAsync(cnts.data(), cnt_dev.p, G.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    int64_t mx = 0, tot = 0;
+    for (int64_t c : cnts) { mx = std::max(mx, c); tot += c; }
+    DevBuf<uint64_t> ga, gb, ca, cb, ma, mb;
+    int64_t nm = 0;
+    if (mx > 0) {
+      SQ_CHECK(ga.alloc(mx * NW * G.nranks));
+      SQ_CHECK(gb.alloc(mx * NW * G.nranks));
+      if (nf > 0) {
+        SQ_CUDA(cudaMemcpyAsync(ga.p + (int64_t)G.rank * mx * NW, fa.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(gb.p + (int64_t)G.rank * mx * NW, fb.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+      }
+      rc = ncclAllGather(ga.p + (int64_t)G.rank * mx * NW, ga.p, mx * NW, ncclUint64, G.comm, s);
+      if (rc == ncclSuccess) rc = ncclAllGather(gb.p + (int64_t)G.rank * mx * NW, gb.p, mx * NW, ncclUint64, G.comm, s);
+      if (rc != ncclSuccess) { set_error("hci_select: ncclAllGather(dets) failed: %s", ncclGetErrorString(rc)); return 3; }
+      SQ_CHECK(ca.alloc(std::max<int64_t>(tot, 1) * NW));
+      SQ_CHECK(cb.alloc(std::max<int64_t>(tot, 1) * NW));
+      int64_t off = 0;
+      for (int r = 0; r < G.nranks; r++) {
+        if (cnts[r] == 0) continue;
+        SQ_CUDA(cudaMemcpyAsync(ca.p + off * NW, ga.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(cb.p + off * NW, gb.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+        off += cnts[r];
+      }
+      SQ_CUDA(cudaStreamSynchronize(s));
+      SQ_CHECK(sort_unique_new<NW>(T.norb, ca, cb, tot, nullptr, nullptr, 0, ma, mb, nm, s));
+    }
+    fa.release(); fb.release();
+    fa.p = ma.take(); fb.p = mb.take();
+    nf = nm;
+  }
+  HM.mark("final merge");
   h->sel_new_up.assign((size_t)nf * 2, 0);
   h->sel_new_dn.assign((size_t)nf * 2, 0);
   if (nf > 0) {
@@ -481,6 +559,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   }
   // min_H_already_done of the current dets (hci.f90:1015); new dets start at 9e99 on the caller's side (:1016)
   for (int64_t i = 0; i < n; i++) min_H[i] = std::min(min_H[i], eps_var / fabs(coeffs[i]) - 1.e-14);
+  HM.mark("download + min_H");
   *n_new_out = nf;
   return 0;
 }
