@@ -12,7 +12,7 @@ module sqmc_b200_iface
   implicit none
   private
   public :: b200_init, b200_system_chem, b200_system_heg, b200_system_hubbardk, b200_build_h, &
-            b200_export_upper, b200_matvec, b200_projector, b200_scale_values, b200_davidson, b200_free, b200_check
+            b200_export_upper, b200_matvec, b200_projector, b200_scale_values, b200_davidson, b200_lanczos, b200_free, b200_check
   public :: sqmc_b200_get_unique_id
 
   interface
@@ -93,6 +93,14 @@ module sqmc_b200_iface
       real(c_double) :: evecs(*), evals(*)
       real(c_double), value :: tol
       integer(c_int) :: n_matvec, n_ritz
+    end function
+    integer(c_int) function sqmc_b200_lanczos(h, v0, evec, eig3, tol, max_iter, n_iter, ritz_log, ritz_cap, n_ritz) bind(C, name="sqmc_b200_lanczos")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: h, v0, ritz_log          ! v0 / ritz_log may be c_null_ptr
+      real(c_double) :: evec(*), eig3(3)
+      real(c_double), value :: tol
+      integer(c_int), value :: max_iter, ritz_cap
+      integer(c_int) :: n_iter, n_ritz
     end function
   end interface
 
@@ -201,6 +209,24 @@ contains
     if (present(initial_vector)) v0 = c_loc(initial_vector)
     call b200_check(sqmc_b200_davidson(h, int(n_states, c_int), v0, final_vector, lowest_eigenvalues, 1.e-10_c_double, &
                     50_c_int, nmv, c_null_ptr, 0_c_int, nlog))
+  end subroutine
+
+  ! matrix_lanczos_sparse(n,lowest_eigenvector,lowest_eigenvalue,...,highest_eigenvalue,second_lowest_eigenvalue,initial_vector)
+  ! (more_tools.f90:1742) on the handle's resident matrix
+  subroutine b200_lanczos(h, lowest_eigenvector, lowest_eigenvalue, highest_eigenvalue, second_lowest_eigenvalue, initial_vector)
+    type(c_ptr), intent(in) :: h
+    real(c_double), intent(out) :: lowest_eigenvector(:), lowest_eigenvalue
+    real(c_double), intent(out), optional :: highest_eigenvalue, second_lowest_eigenvalue
+    real(c_double), intent(in), optional, target :: initial_vector(:)
+    real(c_double) :: eig3(3)
+    integer(c_int) :: nit, nlog
+    type(c_ptr) :: v0
+    v0 = c_null_ptr
+    if (present(initial_vector)) v0 = c_loc(initial_vector)
+    call b200_check(sqmc_b200_lanczos(h, v0, lowest_eigenvector, eig3, 1.e-10_c_double, 50_c_int, nit, c_null_ptr, 0_c_int, nlog))
+    lowest_eigenvalue = eig3(1)
+    if (present(highest_eigenvalue)) highest_eigenvalue = eig3(2)
+    if (present(second_lowest_eigenvalue)) second_lowest_eigenvalue = eig3(3)
   end subroutine
 
   subroutine b200_free(h)

@@ -140,6 +140,21 @@ inline void davidson_sparse(model_system &S, int n, int n_states, std::vector<rk
 
 // do_walk.f90:2259-2290 with the stored matrix already scaled by -tau (semistoch.f90:657,880)
 inline void scale_values(model_system &S, rk ratio) { check(sqmc_b200_scale_values(S.h, ratio)); }
+// matrix_lanczos_sparse(n, lowest_eigenvector, lowest_eigenvalue, matrix_indices, nelem_nonzero, matrix_values,
+//                       highest_eigenvalue, second_lowest_eigenvalue, initial_vector)   (more_tools.f90:1742)
+// the matrix arguments are the handle's resident matrix; optional outputs / input as pointers (null = absent)
+inline void matrix_lanczos_sparse(model_system &S, std::vector<rk> &lowest_eigenvector, rk &lowest_eigenvalue, rk *highest_eigenvalue = nullptr,
+                                  rk *second_lowest_eigenvalue = nullptr, const std::vector<rk> *initial_vector = nullptr) {
+  int64_t n = 0, nu = 0, nf = 0;
+  check(sqmc_b200_nnz(S.h, &n, &nu, &nf));
+  lowest_eigenvector.assign((size_t)n, 0.0);
+  rk eig3[3] = {0, 0, 0};
+  int nit = 0, nlog = 0;
+  check(sqmc_b200_lanczos(S.h, initial_vector ? initial_vector->data() : nullptr, lowest_eigenvector.data(), eig3, 1.0e-10, 50, &nit, nullptr, 0, &nlog));
+  lowest_eigenvalue = eig3[0];
+  if (highest_eigenvalue) *highest_eigenvalue = eig3[1];
+  if (second_lowest_eigenvalue) *second_lowest_eigenvalue = eig3[2];
+}
 // storage-order hint for H.v (0 = plain rows, 2/4/8 = column-merged bundles); no reference counterpart
 inline void set_row_bundle(model_system &S, int rows_per_bundle) { check(sqmc_b200_set_row_bundle(S.h, rows_per_bundle)); }
 inline void deterministic_projector_step(model_system &S, rk tau, rk e_trial, const std::vector<rk> &imp_wt, std::vector<rk> &deltaw) {

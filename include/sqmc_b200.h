@@ -139,6 +139,16 @@ int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle);
 int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
 
+/* ---- Lanczos -------------------------------------------------------------------
+ * Replaces matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver of the
+ * k-space Hubbard path: <= min(n, max_iter = 50) vectors, full Gram-Schmidt pass per
+ * step, stop when |dE| < tol (1e-10, :73,1847).  v0: n-vector or NULL (unit vector on
+ * the first row, :1788-1790).  evec: n.  eig3: lowest, highest and second-lowest
+ * eigenvalue of the tridiagonal matrix (the optional outputs of the reference).
+ * ritz_log (may be NULL): the values printed as "Iteration, Eigenvalue=" (:1852). */
+int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter,
+                      int *n_iter_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+
 /* ---- device-resident entry points (used by bench.py for the HBM-resident leg)
  * x_dev/y_dev are device pointers in the library's INTERNAL row order (length n for x,
  * n_local_rows for y).  Under nranks>1 only this rank's row block of x_dev needs to be valid on

@@ -57,6 +57,8 @@ def lib():
         L.orc_matvec_upper.argtypes = [i64, vp, vp, vp, vp, vp]
         L.orc_matvec_upper_mt.argtypes = [i64, vp, vp, vp, vp, vp, i32]
         L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        L.orc_lanczos.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_lanczos.restype = i32
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
         L.orc_select.restype = i64
         L.orc_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, i64, vp, vp]
@@ -265,6 +267,23 @@ def davidson(counts, idx, val, n_states=1, v0=None):
         v0p = _p(v0)
     nl = lib().orc_davidson(n, n_states, _p(idx), _p(counts), _p(val), v0p, _p(evecs), _p(evals), _p(ritz), len(ritz), C.addressof(nmv))
     return dict(evals=evals, evecs=evecs.reshape(n_states, n).T, ritz=ritz[:min(nl, len(ritz))].reshape(-1, n_states), n_matvec=nmv.value)
+
+
+def lanczos(counts, idx, val, v0=None):
+    """matrix_lanczos_sparse (more_tools.f90:1742-1883) -> dict(lowest, highest, second_lowest, evec, ritz (per step), n_iter)"""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(counts)
+    evec = np.zeros(n)
+    out3 = np.zeros(4)
+    ritz = np.zeros(64)
+    v0p = None
+    if v0 is not None:
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        v0p = _p(v0)
+    nit = lib().orc_lanczos(n, _p(idx), _p(counts), _p(val), v0p, _p(evec), _p(out3), _p(ritz), len(ritz))
+    return dict(lowest=out3[0], highest=out3[1], second_lowest=out3[2], evec=evec, n_iter=nit, ritz=ritz[:min(int(out3[3]), 64)].copy())
 
 
 def projector_step(counts, idx, minus_tau_H, tau, e_trial, w):

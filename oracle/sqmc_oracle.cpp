@@ -1374,6 +1374,85 @@ int orc_davidson(long long n, int n_states, const i8b *indices, const i8b *count
   for (int i = 0; i < m; i++) ritz[i] = log[i];
   return (int)log.size();
 }
+// matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver of the k-space Hubbard path: <= min(n,50) Lanczos
+// vectors, one Gram-Schmidt pass against all previous vectors per step (:1820-1826), the tridiagonal matrix diagonalised
+// every step (dsyev there, Jacobi here), stop when |E - E_prev| < 1e-10 (:1847) or the new vector vanishes (:1816).
+// out3 = {lowest, highest, second lowest, number of logged values}; ritz receives the values printed as
+// "Iteration, Eigenvalue=" (the converging step is not printed, :1847-1853); returns the step count.
+int orc_lanczos(long long n, const i8b *indices, const i8b *counts, const double *values, const double *v0, double *evec, double *out3,
+                double *ritz, int ritz_cap) {
+  const double epsilon = 1.e-10;  // more_tools.f90:73
+  if (n <= 1) {                   // :1874-1876
+    out3[0] = out3[1] = out3[2] = values[0];
+    out3[3] = 0;
+    evec[0] = v0 ? v0[0] / std::sqrt(v0[0] * v0[0]) : 1.0;  // lowest_eigenvector = v(:,1)
+    return 0;
+  }
+  const int iterations = (int)std::min<long long>(n, 50);
+  std::vector<std::vector<double>> v(iterations + 1, std::vector<double>(n, 0.0));
+  std::vector<double> w(n, 0.0), alphas(iterations + 1, 0.0), betas(iterations + 2, 0.0);
+  auto dot = [&](const std::vector<double> &a, const std::vector<double> &b) {
+    double t = 0.0;
+    for (long long i = 0; i < n; i++) t += a[i] * b[i];
+    return t;
+  };
+  if (v0) {
+    double t = 0.0;
+    for (long long i = 0; i < n; i++) t += v0[i] * v0[i];
+    const double norm = 1.0 / std::sqrt(t);
+    for (long long i = 0; i < n; i++) v[0][i] = norm * v0[i];
+  } else {
+    v[0][0] = 1.0;
+  }
+  bool converged = false;
+  double lowest = 0, highest = 0, second = 0, prev = 0;
+  std::vector<double> evals, evecs;
+  int it = 1, nlog = 0;
+  for (; it <= iterations; it++) {
+    matvec_upper(n, indices, counts, values, v[it - 1].data(), w.data());
+    if (it > 1)
+      for (long long i = 0; i < n; i++) w[i] = w[i] - betas[it - 1] * v[it - 2][i];
+    alphas[it - 1] = dot(w, v[it - 1]);
+    for (long long i = 0; i < n; i++) w[i] = w[i] - alphas[it - 1] * v[it - 1][i];
+    double norm = dot(w, w);
+    if (norm < 1.e-12) converged = true;
+    betas[it] = std::sqrt(norm);
+    const double norm_inv = 1.0 / betas[it];
+    for (long long i = 0; i < n; i++) v[it][i] = w[i] * norm_inv;
+    w = v[it];
+    for (int k = 0; k < it; k++) {  // reorthogonalisation: coefficients from v(:,it+1), subtracted from w
+      const double c = dot(v[it], v[k]);
+      for (long long i = 0; i < n; i++) w[i] = w[i] - c * v[k][i];
+    }
+    v[it] = w;
+    norm = dot(v[it], v[it]);
+    const double ninv = 1.0 / std::sqrt(norm);
+    for (long long i = 0; i < n; i++) v[it][i] = v[it][i] * ninv;
+    std::vector<double> tri((size_t)it * it, 0.0);
+    for (int k = 0; k < it; k++) {
+      tri[(size_t)k * it + k] = alphas[k];
+      if (k < it - 1) { tri[(size_t)(k + 1) * it + k] = betas[k + 1]; tri[(size_t)k * it + k + 1] = betas[k + 1]; }
+    }
+    jacobi_eigh(it, tri, evals, evecs);
+    lowest = evals[0];
+    highest = evals[it - 1];
+    if (it > 1) second = evals[1];
+    if (it > 1 && std::fabs(lowest - prev) < epsilon) { converged = true; break; }
+    prev = lowest;
+    if (nlog < ritz_cap) ritz[nlog] = lowest;
+    nlog++;
+    if (converged) break;
+  }
+  it = std::min(it, iterations);
+  for (long long i = 0; i < n; i++) {  // v(:,1) = matmul(v(:,1:it), tridiag(1:it,1))
+    double t = 0.0;
+    for (int k = 0; k < it; k++) t += v[k][i] * evecs[k];
+    evec[i] = t;
+  }
+  out3[0] = lowest; out3[1] = highest; out3[2] = second; out3[3] = (double)nlog;
+  return it;
+}
+
 // projector step of do_walk.f90:2255-2325 on the deterministic space:
 // deltaw = (-tau H) w  (stored matrix already scaled by -tau, semistoch.f90:657,880)
 // deltaw += e_trial*tau*w ; w += deltaw

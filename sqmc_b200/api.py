@@ -223,3 +223,21 @@ class SparseHamiltonian:
         k = min(nlog.value, cap)
         return dict(evals=evals, evecs=np.ascontiguousarray(evecs), ritz=ritz[:k * n_states].reshape(k, n_states),
                     n_matvec=nmv.value)
+
+    def matrix_lanczos_sparse(self, initial_vector=None, tol=1.0e-10, max_iter=50):
+        """matrix_lanczos_sparse (more_tools.f90:1742-1883) on the resident matrix ->
+        dict(lowest_eigenvalue, highest_eigenvalue, second_lowest_eigenvalue, lowest_eigenvector, ritz, n_iter)."""
+        n = self.n
+        evec = np.zeros(n)
+        eig3 = np.zeros(3)
+        ritz = np.zeros(max_iter + 2)
+        nit, nlog = C.c_int(), C.c_int()
+        v0p = None
+        if initial_vector is not None:
+            v0 = np.ascontiguousarray(initial_vector, dtype=np.float64).reshape(-1)
+            if len(v0) != n:
+                raise ValueError("initial_vector must have n entries")
+            v0p = _p(v0)
+        check(self._L.sqmc_b200_lanczos(self._h, v0p, _p(evec), _p(eig3), float(tol), int(max_iter), C.byref(nit), _p(ritz), len(ritz), C.byref(nlog)))
+        return dict(lowest_eigenvalue=eig3[0], highest_eigenvalue=eig3[1], second_lowest_eigenvalue=eig3[2], lowest_eigenvector=evec,
+                    ritz=ritz[:nlog.value].copy(), n_iter=nit.value)

@@ -354,6 +354,14 @@ int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio) {
   return 0;
 }
 
+int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out,
+                      double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("lanczos: null handle"); return 2; }
+  if (max_iter < 1) { set_error("lanczos: max_iter must be positive"); return 2; }
+  return lanczos(h, v0, evec, eig3, tol, max_iter, n_iter_out, ritz_log, ritz_log_cap, n_ritz_logged);
+}
+
 int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle) {
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("set_row_bundle: no matrix on this handle"); return 2; }

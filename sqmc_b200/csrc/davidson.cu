@@ -424,4 +424,129 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   return 0;
 }
 
+// y += c * x with a host scalar
+__global__ void axpy_host_kernel(double *y, const double *x, double c, int64_t n) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j < n) y[j] = y[j] + c * x[j];
+}
+__global__ void scale_copy_kernel(double *dst, const double *src, double c, int64_t n) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j < n) dst[j] = src[j] * c;
+}
+
+// ------------------------------------------------------------------ Lanczos
+// Statement-by-statement device version of matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver the k-space
+// Hubbard path uses: <= min(n, max_iter = 50) vectors, w = H v - beta v_prev - alpha v, one Gram-Schmidt pass of the new
+// vector against all previous ones (coefficients taken from v_{it+1}, :1820-1826), the tridiagonal matrix diagonalised on
+// the host every step (cyclic Jacobi for dsyev), stop at |E - E_prev| < tol (1e-10, :1847) or when the new vector
+// vanishes (:1816).  eig3 = {lowest, highest, second lowest}; ritz_log receives the "Iteration, Eigenvalue=" values.
+int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out, double *ritz_log,
+            int ritz_log_cap, int *n_ritz_logged) {
+  if (!h->d_rowptr) { set_error("lanczos: no matrix on this handle"); return 2; }
+  const int64_t n = h->n;
+  if (n_ritz_logged) *n_ritz_logged = 0;
+  if (n_iter_out) *n_iter_out = 0;
+  if (n == 1) {  // :1874-1876
+    double d = 0;
+    SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
+    eig3[0] = eig3[1] = eig3[2] = d;
+    evec[0] = 1.0;
+    return 0;
+  }
+  Dav D;
+  D.h = h;
+  D.s = G.stream;
+  D.n = n;
+  D.nloc = h->row1 - h->row0;
+  D.ld = std::max<int64_t>(D.nloc, 1);
+  const int64_t nloc = D.nloc, ld = D.ld;
+  cudaStream_t s = D.s;
+  const int iterations = (int)std::min<int64_t>(n, max_iter);
+  SQ_CHECK(devbuf_alloc((void **)&D.V, (size_t)ld * (iterations + 1) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.W, (size_t)ld * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.partial, (size_t)kDotBlocks * (iterations + 2) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * (iterations + 1) * sizeof(double), s));
+  auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
+  double *w = D.W;
+  // initial vector: normalised input, or the unit vector on the first CALLER row (:1785-1791)
+  {
+    std::vector<double> e;
+    const double *src = v0;
+    if (!v0) { e.assign(n, 0.0); e[0] = 1.0; src = e.data(); }
+    SQ_CUDA(cudaMemcpyAsync(h->d_tmp, src, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    SQ_CHECK(permute_gather(h->d_tmp, h->d_perm, h->d_x, n, s));
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(Vc(0), h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    if (v0) {
+      SQ_CHECK(D.dots(Vc(0), 1, Vc(0), D.scal));
+      SQ_CHECK(D.normalize(Vc(0), D.scal));
+    }
+  }
+  std::vector<double> alphas(iterations + 1, 0.0), betas(iterations + 2, 0.0), evals, evecs;
+  double lowest = 0, highest = 0, second = 0, prev = 0, sc[2];
+  bool converged = false;
+  int it = 1, nlogged = 0;
+  for (; it <= iterations; it++) {
+    SQ_CHECK(D.apply_h(Vc(it - 1), w));
+    if (it > 1 && nloc > 0) {
+      axpy_host_kernel<<<D.blocks(nloc), 256, 0, s>>>(w, Vc(it - 2), -betas[it - 1], nloc);
+      SQ_LAUNCH_CHECK();
+    }
+    SQ_CHECK(D.dots(w, 1, Vc(it - 1), D.scal));
+    SQ_CHECK(D.fetch(D.scal, 1, sc));
+    alphas[it - 1] = sc[0];
+    if (nloc > 0) {
+      axpy_host_kernel<<<D.blocks(nloc), 256, 0, s>>>(w, Vc(it - 1), -alphas[it - 1], nloc);
+      SQ_LAUNCH_CHECK();
+    }
+    SQ_CHECK(D.dots(w, 1, w, D.scal));
+    SQ_CHECK(D.fetch(D.scal, 1, sc));
+    if (sc[0] < 1.e-12) converged = true;
+    betas[it] = sqrt(sc[0]);
+    if (nloc > 0) {
+      scale_copy_kernel<<<D.blocks(nloc), 256, 0, s>>>(Vc(it), w, 1.0 / betas[it], nloc);
+      SQ_LAUNCH_CHECK();
+      SQ_CUDA(cudaMemcpyAsync(w, Vc(it), nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    SQ_CHECK(D.dots(D.V, it, Vc(it), D.coef));  // all coefficients v_{it+1}.v_i at once, as the reference computes them
+    for (int k = 0; k < it; k++) SQ_CHECK(D.axpy_neg(w, Vc(k), D.coef + k));
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(Vc(it), w, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CHECK(D.dots(Vc(it), 1, Vc(it), D.scal));
+    SQ_CHECK(D.normalize(Vc(it), D.scal));
+    std::vector<double> tri((size_t)it * it, 0.0);
+    for (int k = 0; k < it; k++) {
+      tri[(size_t)k * it + k] = alphas[k];
+      if (k < it - 1) { tri[(size_t)(k + 1) * it + k] = betas[k + 1]; tri[(size_t)k * it + k + 1] = betas[k + 1]; }
+    }
+    jacobi_eigh(it, tri, evals, evecs);
+    lowest = evals[0];
+    highest = evals[it - 1];
+    if (it > 1) second = evals[1];
+    if (it > 1 && fabs(lowest - prev) < tol) { converged = true; break; }
+    prev = lowest;
+    if (ritz_log && nlogged < ritz_log_cap) ritz_log[nlogged] = lowest;
+    nlogged++;
+    if (converged) break;
+  }
+  it = std::min(it, iterations);
+  // lowest eigenvector = V(:,1:it) * tridiagonal eigenvector 1 (:1868), published in caller order on every rank
+  SQ_CUDA(cudaMemcpyAsync(D.coef, evecs.data(), it * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (nloc > 0) {
+    combine_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.V, ld, it, D.coef, 1, w, nloc);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, w, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  SQ_CHECK(allgather_rows(h, h->d_x, s));
+  SQ_CHECK(permute_scatter(h->d_x, h->d_perm, h->d_tmp, n, s));
+  SQ_CUDA(cudaMemcpyAsync(evec, h->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  eig3[0] = lowest; eig3[1] = highest; eig3[2] = second;
+  if (n_iter_out) *n_iter_out = it;
+  if (n_ritz_logged) *n_ritz_logged = std::min(nlogged, ritz_log_cap);
+  return 0;
+}
+
 }  // namespace sqmc

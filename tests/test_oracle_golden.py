@@ -83,3 +83,20 @@ def test_davidson_two_states_against_dense(oracle):
     w = np.linalg.eigvalsh(oracle.upper_to_scipy(cnt, idx, val).toarray())
     d = oracle.davidson(cnt, idx, val, n_states=2)
     assert np.max(np.abs(d["evals"] - w[:2])) < 1e-9
+
+
+def test_lanczos_against_dense(oracle, heg_space):
+    """matrix_lanczos_sparse restatement (more_tools.f90:1742-1883): lowest eigenpair against numpy on the 277-det matrix,
+    whose Davidson energy the reference log pins (o_det_ref:270)."""
+    s, r = heg_space
+    up, dn = r["up"][:277], r["dn"][:277]
+    cnt, idx, val = s.build_upper(up, dn)
+    A = oracle.upper_to_scipy(cnt, idx, val).toarray()
+    w, v = np.linalg.eigh(A)
+    L = oracle.lanczos(cnt, idx, val)
+    assert abs(L["lowest"] - w[0]) < 1e-9 and abs(L["lowest"] - 58.2825967049) < 5e-9
+    assert L["n_iter"] == len(L["ritz"]) + 1                      # the converging step is not printed (:1847-1853)
+    assert abs(abs(np.dot(L["evec"], v[:, 0])) - 1) < 1e-6
+    x = np.sin(np.arange(277.0)) + 2.0
+    L2 = oracle.lanczos(cnt, idx, val, v0=x)
+    assert abs(L2["lowest"] - w[0]) < 1e-9 and L2["highest"] <= w[-1] + 1e-9 and L2["second_lowest"] >= w[1] - 1e-9
