@@ -100,3 +100,26 @@ def test_two_state_davidson_uses_the_pair_kernel(oracle, c2_space_ts):
         for q in range(2):
             a, b = got[4]["evecs"][:, q], got[R]["evecs"][:, q]
             assert min(np.max(np.abs(a - b)), np.max(np.abs(a + b))) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 33])
+def test_tiny_spaces_in_every_layout(oracle, heg_space, n):
+    """fewer rows than a bundle, ragged last bundle, single-determinant space: build, H.v, row access, Davidson, Lanczos"""
+    import sqmc_b200 as sq
+    s, r = heg_space
+    up, dn = r["up"][:n], r["dn"][:n]
+    cnt, idx, val = s.build_upper(up, dn)
+    H = sq.SparseHamiltonian(sq.HegSystem(3, 0.5, 14, 7, 1.49))
+    assert H.generate_sparse_ham_upper_triangular(up, dn) == len(idx)
+    x = np.linspace(-1.0, 1.0, n) + 0.25
+    yref = oracle.matvec_upper(cnt, idx, val, x)
+    ref = oracle.davidson(cnt, idx, val, n_states=1)
+    for R in (4, 8, 2, 0):
+        H.set_row_bundle(R)
+        assert np.max(np.abs(H.matvec(x) - yref)) <= 1e-12 * max(np.max(np.abs(yref)), 1e-300)
+        e = H.export_upper()
+        assert np.array_equal(e[0], cnt) and np.array_equal(e[1], idx) and np.array_equal(e[2], val)
+        c, v = H.get_row(n)
+        assert c[-1] == n and v[-1] == val[-1]        # full row, ascending columns: its last entry is the diagonal of row n
+        assert abs(H.davidson_sparse(n_states=1)["evals"][0] - ref["evals"][0]) < 1e-8
+        assert abs(H.matrix_lanczos_sparse()["lowest_eigenvalue"] - oracle.lanczos(cnt, idx, val)["lowest"]) < 1e-8
