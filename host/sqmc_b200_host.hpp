@@ -155,6 +155,12 @@ inline void matrix_lanczos_sparse(model_system &S, std::vector<rk> &lowest_eigen
   if (highest_eigenvalue) *highest_eigenvalue = eig3[1];
   if (second_lowest_eigenvalue) *second_lowest_eigenvalue = eig3[2];
 }
+// second_order_pt(ndets, dets_up, dets_dn, wts, diag_elems, var_energy, eps_pt, delta_e_2pt, ndets_connected)   (hci.f90:1100)
+// diag_elems is not needed (H_aa is evaluated on the device); determinants as 16-byte integers like the reference's integer(ik)
+inline void second_order_pt(model_system &S, int64_t ndets, const void *dets_up, const void *dets_dn, const std::vector<rk> &wts, rk var_energy,
+                            rk eps_pt, rk &delta_e_2pt, int64_t &ndets_connected) {
+  check(sqmc_b200_pt2(S.h, ndets, dets_up, dets_dn, wts.data(), var_energy, eps_pt, &delta_e_2pt, &ndets_connected));
+}
 // storage-order hint for H.v (0 = plain rows, 2/4/8 = column-merged bundles); no reference counterpart
 inline void set_row_bundle(model_system &S, int rows_per_bundle) { check(sqmc_b200_set_row_bundle(S.h, rows_per_bundle)); }
 inline void deterministic_projector_step(model_system &S, rk tau, rk e_trial, const std::vector<rk> &imp_wt, std::vector<rk> &deltaw) {

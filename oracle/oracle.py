@@ -59,6 +59,8 @@ def lib():
         L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
         L.orc_lanczos.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_lanczos.restype = i32
+        L.orc_pt2.argtypes = [vp, i64, vp, vp, vp, C.c_double, C.c_double, vp]
+        L.orc_pt2.restype = C.c_double
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
         L.orc_select.restype = i64
         L.orc_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, i64, vp, vp]
@@ -203,6 +205,15 @@ class System:
         nn = lib().orc_select(self.h, len(up), _p(up), _p(dn), _p(c), _p(mh), float(eps_var), cap, _p(nu), _p(nd))
         assert nn <= cap
         return nu[:nn].copy(), nd[:nn].copy(), mh
+
+    def pt2(self, up, dn, wts, var_energy, eps_pt):
+        """deterministic second-order PT (second_order_pt, hci.f90:1100-1182) -> (delta_E, ndets_connected)"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        w = np.ascontiguousarray(wts, dtype=np.float64).reshape(-1)
+        nconn = C.c_longlong()
+        de = lib().orc_pt2(self.h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), C.addressof(nconn))
+        return de, nconn.value
 
     def hci(self, eps_var, eps_var_sched=(), n_states=1, max_iters=50, max_dets=0):
         sched = np.zeros(30)

@@ -1477,6 +1477,52 @@ long long orc_select(void *h, long long n, const det_t *up, const det_t *dn, con
   for (long long i = 0; i < nn && i < cap; i++) { new_up[i] = nu[n + i]; new_dn[i] = nd[n + i]; }
   return nn;
 }
+// Deterministic second-order Epstein-Nesbet correction with the HCI screened sum: second_order_pt (hci.f90:1100-1182) over
+// find_doubly_excited(..., eps_var_pt = eps_pt, e_mix_num) (semistoch.f90:1579-2231):
+//   every variational determinant i with c_i != 0 contributes H_ai * c_i to each of its important connections a
+//   (|H_ai| above eps_pt/|c_i| by the selection rules; the determinant itself comes first with element 0, heg.f90:2525-2529);
+//   contributions to the same determinant are summed after a sort by label (merge_original_with_spawned3);
+//   delta_E = sum over a NOT in the variational space of (sum_i H_ai c_i)^2 / (E_var - H_aa)   (hci.f90:1160-1170).
+// Returns delta_E; *n_connected = number of distinct determinants generated (variational ones included), the
+// "ndets_connected" the reference prints.  Chemistry: plain determinants only (time_sym = f).
+double orc_pt2(void *h, long long n, const det_t *up, const det_t *dn, const double *wts, double var_energy, double eps_pt, long long *n_connected) {
+  System &S = *(System *)h;
+  if (S.model == 0) chem_max_double(S); else if (S.model == 1) heg_max_double(S);
+  std::vector<det_t> cu, cd, tu, td;
+  std::vector<double> num;
+  for (long long i = 0; i < n; i++) {
+    if (wts[i] == 0.0) continue;                       // semistoch.f90:1762
+    tu.clear(); td.clear();
+    const double eps = eps_pt / std::fabs(wts[i]);
+    if (S.model == 0) important_connected_chem(S, up[i], dn[i], eps, 9.e99, tu, td);
+    else important_connected_heg(S, up[i], dn[i], eps, tu, td);
+    for (size_t k = 0; k < tu.size(); k++) {
+      double me = 0.0;                                  // first entry = the determinant itself, element set to 0
+      if (k > 0) me = hamiltonian(S, up[i], dn[i], tu[k], td[k]);
+      cu.push_back(tu[k]); cd.push_back(td[k]); num.push_back(me * wts[i]);
+    }
+  }
+  std::vector<size_t> ord(cu.size());
+  for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
+  std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cu[a] < cu[b] || (cu[a] == cu[b] && cd[a] < cd[b]); });
+  std::vector<size_t> vord(n);
+  for (long long i = 0; i < n; i++) vord[i] = i;
+  std::sort(vord.begin(), vord.end(), [&](size_t a, size_t b) { return up[a] < up[b] || (up[a] == up[b] && dn[a] < dn[b]); });
+  double delta = 0.0;
+  long long distinct = 0;
+  size_t k = 0, o = 0;
+  while (k < ord.size()) {
+    const det_t au = cu[ord[k]], ad = cd[ord[k]];
+    double sum = 0.0;
+    while (k < ord.size() && cu[ord[k]] == au && cd[ord[k]] == ad) { sum += num[ord[k]]; k++; }
+    distinct++;
+    while (o < vord.size() && (up[vord[o]] < au || (up[vord[o]] == au && dn[vord[o]] < ad))) o++;
+    const bool in_var = o < vord.size() && up[vord[o]] == au && dn[vord[o]] == ad;
+    if (!in_var) delta += sum * sum / (var_energy - hamiltonian(S, au, ad, au, ad));
+  }
+  if (n_connected) *n_connected = distinct;
+  return delta;
+}
 int orc_hci(void *h, const double *eps_var_sched30, int n_states, int max_iters, int max_dets) {
   return perform_hci(*(System *)h, eps_var_sched30, n_states, max_iters, max_dets);
 }

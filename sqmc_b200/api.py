@@ -241,3 +241,14 @@ class SparseHamiltonian:
         check(self._L.sqmc_b200_lanczos(self._h, v0p, _p(evec), _p(eig3), float(tol), int(max_iter), C.byref(nit), _p(ritz), len(ritz), C.byref(nlog)))
         return dict(lowest_eigenvalue=eig3[0], highest_eigenvalue=eig3[1], second_lowest_eigenvalue=eig3[2], lowest_eigenvector=evec,
                     ritz=ritz[:nlog.value].copy(), n_iter=nit.value)
+
+    def second_order_pt(self, dets_up, dets_dn, wts, var_energy, eps_pt):
+        """Deterministic second-order PT with the HCI screened sum (second_order_pt, hci.f90:1100-1182) -> (delta_e_2pt, ndets_connected)."""
+        up = np.ascontiguousarray(dets_up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dets_dn, dtype=np.uint64).reshape(-1, 2)
+        w = np.ascontiguousarray(wts, dtype=np.float64).reshape(-1)
+        if len(dn) != len(up) or len(w) != len(up):
+            raise ValueError("second_order_pt: dets_up, dets_dn and wts must have the same length")
+        de, nc = C.c_double(), C.c_int64()
+        check(self._L.sqmc_b200_pt2(self._h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), C.byref(de), C.byref(nc)))
+        return de.value, nc.value

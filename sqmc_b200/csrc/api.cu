@@ -354,6 +354,13 @@ int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio) {
   return 0;
 }
 
+int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+                  double *delta_e, int64_t *n_connected) {
+  SQ_CHECK(require_init());
+  if (!h || !delta_e || !n_connected) { set_error("pt2: null argument"); return 2; }
+  return pt2(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_e, n_connected);
+}
+
 int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out,
                       double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());

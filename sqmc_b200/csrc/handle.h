@@ -197,6 +197,8 @@ int gather_strings(int NW, const uint64_t *src, const int32_t *idx, uint64_t *ou
 // select.cu
 int hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,
                int64_t *n_new_out);
+int pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+        double *delta_out, int64_t *nconn_out);
 // spmv.cu
 int spmv_setup_bins(sqmc_b200_handle *h);
 int spmv_launch(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);

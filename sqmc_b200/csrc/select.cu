@@ -119,10 +119,11 @@ __device__ __forceinline__ int hb_count_gt(const double *row, int n, double x) {
 
 __device__ __forceinline__ int nth_set(const uint8_t *list, int k) { return list[k]; }
 
-// one warp per determinant; FILL=false counts, FILL=true writes (up,dn) of the selected determinants at out_ptr[i]
-template <int NW, bool FILL>
+// one warp per determinant; FILL=false counts, FILL=true writes (up,dn) of the selected determinants at out_ptr[i];
+// VALS additionally writes H(selected, i) * c_i, the numerator contributions of the second-order correction (pt2 below)
+template <int NW, bool FILL, bool VALS>
 __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_begin, int64_t i_end, int32_t *counts, const int64_t *out_ptr,
-                                                     uint64_t *out_up, uint64_t *out_dn) {
+                                                     uint64_t *out_up, uint64_t *out_dn, double *out_val) {
   __shared__ uint8_t s_occ[4][2][kSelMaxOrb], s_virt[4][2][kSelMaxOrb];
   extern __shared__ int32_t c2s[];
   const ModelTables &T = S.T;
@@ -138,22 +139,23 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
   if (i >= i_end) return;
   const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
   const Bits<NW> u = b_load<NW>(S.up, i), d = b_load<NW>(S.dn, i);
-  const double c = fabs(S.coeffs[i]), minH = S.min_H[i];
+  const double cs = S.coeffs[i], c = fabs(cs), minH = S.min_H[i];
   const int norb = T.norb;
   const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
   int64_t base = FILL ? out_ptr[i - i_begin] : 0;
   int cnt = 0;
-  auto emit = [&](bool keep, Bits<NW> nu, Bits<NW> nd) {
+  auto emit = [&](bool keep, Bits<NW> nu, Bits<NW> nd, double val) {
     if (keep && ts && b_lt(nd, nu)) { Bits<NW> t = nu; nu = nd; nd = t; }  // representative up <= dn
     unsigned m = __ballot_sync(full, keep);
     if (FILL && keep) {
       int64_t q = base + cnt + __popc(m & lt);
       b_store<NW>(out_up, q, nu);
       b_store<NW>(out_dn, q, nd);
+      if (VALS) out_val[q] = val;
     }
     cnt += __popc(m);
   };
-  emit(lane == 0, u, d);  // the determinant itself comes first (chemistry.f90:6893-6895)
+  emit(lane == 0, u, d, 0.0);  // the determinant itself comes first (chemistry.f90:6893-6895), with element 0 (heg.f90:2525-2529)
   const bool expand = c * minH > S.eps_var;  // semistoch.f90:1825
   if (expand) {  // warp-uniform
     const double eps = S.eps_var / c;
@@ -184,18 +186,20 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
         for (int b0 = 0; b0 < tot; b0 += 32) {
           const int f = b0 + lane;
           bool keep = false;
+          double val = 0.0;
           Bits<NW> nu = u, nd = d;
           if (f < tot) {
             const int p = occ[f / nv], r = vir[f % nv];
             if (S.orbsym[p] == S.orbsym[r]) {
               if (spin == 0) { b_clear(nu, p); b_set(nu, r); } else { b_clear(nd, p); b_set(nd, r); }
               if (!ts_excluded(nu, nd)) {
-                const double me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 1));
+                val = chem_hamiltonian_level(C, u, d, nu, nd, 1);
+                const double me = fabs(val);
                 keep = !(me < eps) && !(me > minH);
               }
             }
           }
-          emit(keep, nu, nd);
+          emit(keep, nu, nd, val * cs);
         }
       }
     }
@@ -250,7 +254,9 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
               }
               if (keep && ts_excluded(nu, nd)) keep = false;
             }
-            emit(keep, nu, nd);
+            double val = 0.0;
+            if (VALS && keep) val = chem_double(C, u, d, nu, nd) * cs;  // the table holds |H|; the sign needs the determinant
+            emit(keep, nu, nd, val);
           }
         }
       }
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
       for (int b0 = 0; b0 < tot; b0 += 32) {
         const int f = b0 + lane;
         bool keep = false;
+        double val = 0.0;
         Bits<NW> nu = u, nd = d;
         if (f < tot) {
           int po = f / npv, pv = f % npv;
@@ -277,13 +284,13 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
           Bits<NW> &tgt = spin == 0 ? nu : nd;
           b_clear(tgt, occ[a]); b_clear(tgt, occ[bq]); b_set(tgt, vir[r]); b_set(tgt, vir[sq]);
           if (!ts_excluded(nu, nd)) {
-            double me;
-            if (T.model == MODEL_CHEM) me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 2));
-            else me = fabs(heg_hamiltonian(Hg, u, d, nu, nd));
+            if (T.model == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
+            else val = heg_hamiltonian(Hg, u, d, nu, nd);
+            const double me = fabs(val);
             keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
           }
         }
-        emit(keep, nu, nd);
+        emit(keep, nu, nd, val * cs);
       }
     }
     // ---- opposite-spin doubles
@@ -293,19 +300,20 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
       for (int64_t b0 = 0; b0 < tot; b0 += 32) {
         const int64_t f = b0 + lane;
         bool keep = false;
+        double val = 0.0;
         Bits<NW> nu = u, nd = d;
         if (f < tot) {
           const int fu = (int)(f / td), fd = (int)(f % td);
           b_clear(nu, occ_u[fu / nvu]); b_set(nu, vir_u[fu % nvu]);
           b_clear(nd, occ_d[fd / nvd]); b_set(nd, vir_d[fd % nvd]);
           if (!ts_excluded(nu, nd)) {
-            double me;
-            if (T.model == MODEL_CHEM) me = fabs(chem_hamiltonian_level(C, u, d, nu, nd, 2));
-            else me = fabs(heg_hamiltonian(Hg, u, d, nu, nd));
+            if (T.model == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
+            else val = heg_hamiltonian(Hg, u, d, nu, nd);
+            const double me = fabs(val);
             keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
           }
         }
-        emit(keep, nu, nd);
+        emit(keep, nu, nd, val * cs);
       }
     }
   }
@@ -450,7 +458,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   SQ_CHECK(counts.alloc(nd + 1));
   SQ_CUDA(cudaMemsetAsync(counts.p, 0, (nd + 1) * sizeof(int32_t), s));
   if (nd > 0) {
-    select_kernel<NW, false><<<(unsigned)div_up(nd * 32, 128), 128, c2bytes, s>>>(S, 0, nd, counts.p, nullptr, nullptr, nullptr);
+    select_kernel<NW, false, false><<<(unsigned)div_up(nd * 32, 128), 128, c2bytes, s>>>(S, 0, nd, counts.p, nullptr, nullptr, nullptr, nullptr);
     SQ_LAUNCH_CHECK();
   }
   std::vector<int32_t> hc(nd + 1);
@@ -478,7 +486,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
     std::vector<int64_t> hp(prefix.begin() + i0, prefix.begin() + i1 + 1);
     for (auto &v : hp) v -= prefix[i0];
     SQ_CUDA(cudaMemcpyAsync(optr.p, hp.data(), hp.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    select_kernel<NW, true><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p);
+    select_kernel<NW, true, false><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, nullptr);
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaStreamSynchronize(s));
     int64_t mu = 0;
@@ -562,6 +570,212 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   HM.mark("download + min_H");
   *n_new_out = nf;
   return 0;
+}
+
+// ------------------------------------------------------------------ deterministic second-order correction
+// second_order_pt (hci.f90:1100-1182) over find_doubly_excited(..., eps_var_pt = eps_pt, e_mix_num) (semistoch.f90:1579-2231):
+// every variational determinant i contributes H_ai c_i to each important connection a (the same screened enumeration as the
+// selection, without the min_H_already_done bound); contributions are summed per determinant after a sort by label;
+// delta_E = sum over a outside the variational space of (sum_i H_ai c_i)^2 / (E_var - H_aa).  n_connected = number of
+// distinct determinants generated (variational ones included), the "ndets_connected" of the reference's log.
+__global__ void fill_double_kernel(double *a, int64_t n, double v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
+template <int NW>
+__global__ void pt_term_kernel(ModelTables T, const uint64_t *a, const uint64_t *b, const double *num, const int32_t *external, double e_var,
+                               double *term, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  double r = 0.0;
+  if (external[t]) {
+    const Bits<NW> u = b_load<NW>(a, t), d = b_load<NW>(b, t);
+    const double haa = model_hamiltonian<NW>(T, T.combine_2, u, d, u, d);
+    r = num[t] * num[t] / (e_var - haa);
+  }
+  term[t] = r;
+}
+// sort (a,b,v) by label and sum the values of equal determinants -> (ra, rb, rv), mout distinct determinants
+template <int NW>
+static int reduce_by_det(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, DevBuf<double> &v, int64_t m, DevBuf<uint64_t> &ra, DevBuf<uint64_t> &rb,
+                         DevBuf<double> &rv, int64_t &mout, cudaStream_t s) {
+  mout = 0;
+  if (m == 0) return 0;
+  DevBuf<int32_t> idx, flag, sel, num;
+  DevBuf<uint64_t> sa, sb;
+  DevBuf<double> sv;
+  SQ_CHECK(idx.alloc(m));
+  SQ_CHECK(sort_pairs_index(NW, norb, a.p, b.p, idx.p, m, s));
+  SQ_CHECK(sa.alloc(m * NW));
+  SQ_CHECK(sb.alloc(m * NW));
+  SQ_CHECK(sv.alloc(m));
+  SQ_CHECK(gather_strings(NW, a.p, idx.p, sa.p, m, s));
+  SQ_CHECK(gather_strings(NW, b.p, idx.p, sb.p, m, s));
+  SQ_CHECK(permute_gather(v.p, idx.p, sv.p, m, s));
+  SQ_CHECK(flag.alloc(m));
+  uniq_flag_kernel<NW><<<(unsigned)div_up(m, 256), 256, 0, s>>>(sa.p, sb.p, flag.p, m);
+  SQ_LAUNCH_CHECK();
+  SQ_CHECK(sel.alloc(m + 1));
+  SQ_CHECK(num.alloc(1));
+  cub::CountingInputIterator<int32_t> it(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, it, flag.p, sel.p, num.p, (int)m, s);
+  DevBuf<char> tmp;
+  SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+  SQ_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, it, flag.p, sel.p, num.p, (int)m, s));
+  g_launch_count += 2;
+  int32_t k = 0;
+  SQ_CUDA(cudaMemcpyAsync(&k, num.p, 4, cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  mout = k;
+  set_i32_kernel<<<1, 1, 0, s>>>(sel.p + mout, (int32_t)m);  // closing offset of the last segment
+  SQ_LAUNCH_CHECK();
+  SQ_CHECK(rv.alloc(mout));
+  size_t tb2 = 0;
+  cub::DeviceSegmentedReduce::Sum(nullptr, tb2, sv.p, rv.p, (int)mout, sel.p, sel.p + 1, s);
+  DevBuf<char> tmp2;
+  SQ_CHECK(tmp2.alloc((int64_t)tb2 + 16));
+  SQ_CUDA(cub::DeviceSegmentedReduce::Sum(tmp2.p, tb2, sv.p, rv.p, (int)mout, sel.p, sel.p + 1, s));
+  g_launch_count += 1;
+  SQ_CHECK(ra.alloc(mout * NW));
+  SQ_CHECK(rb.alloc(mout * NW));
+  SQ_CHECK(gather_strings(NW, sa.p, sel.p, ra.p, mout, s));
+  SQ_CHECK(gather_strings(NW, sb.p, sel.p, rb.p, mout, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <int NW>
+static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+                    double *delta_out, int64_t *nconn_out) {
+  cudaStream_t s = G.stream;
+  const ModelTables &T = h->T;
+  DevBuf<uint64_t> up, dn, sup, sdn;
+  DevBuf<double> dc, dm;
+  SQ_CHECK(up.alloc(n * NW));
+  SQ_CHECK(dn.alloc(n * NW));
+  SQ_CHECK(upload_dets(NW, T.norb, dets_up, up.p, n, s));
+  SQ_CHECK(upload_dets(NW, T.norb, dets_dn, dn.p, n, s));
+  SQ_CHECK(dc.alloc(n));
+  SQ_CHECK(dm.alloc(n));
+  SQ_CUDA(cudaMemcpyAsync(dc.p, wts, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  fill_double_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(dm.p, n, 9.e99);  // no upper bound on |H| in the PT sum
+  SQ_LAUNCH_CHECK();
+  {
+    DevBuf<int32_t> idx;
+    SQ_CHECK(idx.alloc(n));
+    SQ_CHECK(sort_pairs_index(NW, T.norb, up.p, dn.p, idx.p, n, s));
+    SQ_CHECK(sup.alloc(n * NW));
+    SQ_CHECK(sdn.alloc(n * NW));
+    SQ_CHECK(gather_strings(NW, up.p, idx.p, sup.p, n, s));
+    SQ_CHECK(gather_strings(NW, dn.p, idx.p, sdn.p, n, s));
+  }
+  const bool use_hb = T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
+  if (use_hb) SQ_CHECK(hb_build(h));
+  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_pt, n,
+               {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
+  const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
+  DevBuf<int32_t> counts;
+  SQ_CHECK(counts.alloc(n + 1));
+  SQ_CUDA(cudaMemsetAsync(counts.p, 0, (n + 1) * sizeof(int32_t), s));
+  select_kernel<NW, false, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr, nullptr);
+  SQ_LAUNCH_CHECK();
+  std::vector<int32_t> hc(n + 1);
+  SQ_CUDA(cudaMemcpyAsync(hc.data(), counts.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  std::vector<int64_t> prefix(n + 1, 0);
+  for (int64_t i = 0; i < n; i++) prefix[i + 1] = prefix[i] + hc[i];
+  // chunks of determinants bounded by generated connections; per chunk: fill, sort, sum per determinant; the partial sums
+  // of all chunks are concatenated and reduced once more at the end
+  const int64_t kChunk = 1ll << 27;
+  DevBuf<uint64_t> acc_a, acc_b;
+  DevBuf<double> acc_v;
+  int64_t acc_n = 0;
+  int64_t i0 = 0;
+  while (i0 < n) {
+    int64_t i1 = std::upper_bound(prefix.begin() + i0 + 1, prefix.end(), prefix[i0] + kChunk) - prefix.begin() - 1;
+    if (i1 <= i0) i1 = i0 + 1;
+    if (i1 > n) i1 = n;
+    const int64_t m = prefix[i1] - prefix[i0];
+    if (m >= (1ll << 31)) { set_error("pt2: one determinant generates too many connections"); return 2; }
+    DevBuf<uint64_t> ca, cb, ra, rb;
+    DevBuf<double> cv, rv;
+    DevBuf<int64_t> optr;
+    SQ_CHECK(ca.alloc(std::max<int64_t>(m, 1) * NW));
+    SQ_CHECK(cb.alloc(std::max<int64_t>(m, 1) * NW));
+    SQ_CHECK(cv.alloc(std::max<int64_t>(m, 1)));
+    SQ_CHECK(optr.alloc(i1 - i0 + 1));
+    std::vector<int64_t> hp(prefix.begin() + i0, prefix.begin() + i1 + 1);
+    for (auto &x : hp) x -= prefix[i0];
+    SQ_CUDA(cudaMemcpyAsync(optr.p, hp.data(), hp.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    select_kernel<NW, true, true><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, cv.p);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaStreamSynchronize(s));
+    int64_t mu = 0;
+    SQ_CHECK(reduce_by_det<NW>(T.norb, ca, cb, cv, m, ra, rb, rv, mu, s));
+    if (mu > 0) {
+      DevBuf<uint64_t> na, nb;
+      DevBuf<double> nv;
+      SQ_CHECK(na.alloc((acc_n + mu) * NW));
+      SQ_CHECK(nb.alloc((acc_n + mu) * NW));
+      SQ_CHECK(nv.alloc(acc_n + mu));
+      if (acc_n) {
+        SQ_CUDA(cudaMemcpyAsync(na.p, acc_a.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(nb.p, acc_b.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(nv.p, acc_v.p, acc_n * 8, cudaMemcpyDeviceToDevice, s));
+      }
+      SQ_CUDA(cudaMemcpyAsync(na.p + acc_n * NW, ra.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaMemcpyAsync(nb.p + acc_n * NW, rb.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaMemcpyAsync(nv.p + acc_n, rv.p, mu * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaStreamSynchronize(s));
+      acc_a.release(); acc_b.release(); acc_v.release();
+      acc_a.p = na.take(); acc_b.p = nb.take(); acc_v.p = nv.take();
+      acc_n += mu;
+    }
+    i0 = i1;
+  }
+  DevBuf<uint64_t> fa, fb;
+  DevBuf<double> fv;
+  int64_t nf = 0;
+  SQ_CHECK(reduce_by_det<NW>(T.norb, acc_a, acc_b, acc_v, acc_n, fa, fb, fv, nf, s));
+  double delta = 0.0;
+  if (nf > 0) {
+    DevBuf<int32_t> ext;
+    DevBuf<double> term, total;
+    SQ_CHECK(ext.alloc(nf));
+    SQ_CHECK(term.alloc(nf));
+    SQ_CHECK(total.alloc(1));
+    const unsigned g = (unsigned)div_up(nf, 256);
+    uniq_flag_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, ext.p, nf);   // all ones: the list is already unique
+    SQ_LAUNCH_CHECK();
+    not_in_list_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, sup.p, sdn.p, n, ext.p, nf);  // 0 for variational determinants
+    SQ_LAUNCH_CHECK();
+    pt_term_kernel<NW><<<g, 256, 0, s>>>(T, fa.p, fb.p, fv.p, ext.p, var_energy, term.p, nf);
+    SQ_LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceReduce::Sum(nullptr, tb, term.p, total.p, (int)nf, s);
+    DevBuf<char> tmp;
+    SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+    SQ_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, term.p, total.p, (int)nf, s));
+    g_launch_count += 1;
+    SQ_CUDA(cudaMemcpyAsync(&delta, total.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  *delta_out = delta;
+  *nconn_out = nf;
+  return 0;
+}
+
+int pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+        double *delta_out, int64_t *nconn_out) {
+  if (n <= 0) { set_error("pt2: n must be positive"); return 2; }
+  if (h->T.model == MODEL_HUBBARDK) { set_error("pt2: only chem and heg"); return 2; }
+  if (h->T.model == MODEL_CHEM && h->T.time_sym) { set_error("pt2: time-reversal symmetrised determinants are not supported (time_sym = f only)"); return 2; }
+  if (h->T.model == MODEL_CHEM && !h->d_orbsym) { set_error("pt2: call sqmc_b200_system_orbital_symmetries first"); return 2; }
+  if (!(eps_pt > 0.0)) { set_error("pt2: eps_pt must be > 0 (the screened sum, hci.f90:1143)"); return 2; }
+  return h->NW == 1 ? pt2_impl<1>(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_out, nconn_out)
+                    : pt2_impl<2>(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_out, nconn_out);
 }
 
 int hci_select(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,

@@ -61,6 +61,13 @@ def heg_from_reference_log():
         m = re.search(r"davidson_sparse: n, iter, Lowest eigenvalue =\s*(\d+)\s+(\d+)\s+(\S+)", ln)
         if m:
             out["davidson_final"].append({"n": int(m.group(1)), "iter": int(m.group(2)), "energy": float(m.group(3))})
+    for i, ln in enumerate(lines):
+        m = re.search(r"PT_correction, eps_pt, ndets_connected for fully deterministic run=\s*(\S+)\s+(\S+)\s+(\d+)", ln)
+        if m:
+            out["pt"] = {"pt_correction": float(m.group(1)), "eps_pt": float(m.group(2)), "ndets_connected": int(m.group(3)), "line": i + 1}
+        m = re.search(r"ndets, ndets_connected\(total\), Variational, PT, Total Energies=\s*(\d+)\s+(\d+)\s+(\S+)\s+(\S+)\s+(\S+)", ln)
+        if m:
+            out["pt"].update({"ndets": int(m.group(1)), "variational_energy": float(m.group(3)), "total_energy": float(m.group(5)), "total_line": i + 1})
     coefs = []
     for i, ln in enumerate(lines):
         if ln.startswith("Final variational wavefunctions"):

@@ -100,3 +100,16 @@ def test_lanczos_against_dense(oracle, heg_space):
     x = np.sin(np.arange(277.0)) + 2.0
     L2 = oracle.lanczos(cnt, idx, val, v0=x)
     assert abs(L2["lowest"] - w[0]) < 1e-9 and L2["highest"] <= w[-1] + 1e-9 and L2["second_lowest"] >= w[1] - 1e-9
+
+
+def test_heg_pt_reproduces_reference_log(oracle):
+    """second_order_pt restatement against the reference's own log (o_det_ref:431,437): eps_pt = 2e-7 on the final
+    9475-determinant wavefunction -> 501881 connected determinants, PT correction -0.000939196, total 58.275966889."""
+    gold = json.load(open(os.path.join(HERE, "golden", "heg_o_det_ref.json")))["pt"]
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    r = S.hci(1e-3, n_states=1)
+    assert len(r["up"]) == gold["ndets"]
+    de, nconn = S.pt2(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], gold["eps_pt"])
+    assert nconn == gold["ndets_connected"]
+    assert abs(de - gold["pt_correction"]) < 5e-10                  # printed with 9 decimals
+    assert abs(r["energy"][0] + de - gold["total_energy"]) < 1e-9
