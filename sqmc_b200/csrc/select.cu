@@ -673,14 +673,41 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   }
   const bool use_hb = T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
   if (use_hb) SQ_CHECK(hb_build(h));
+  // nranks > 1: determinants dealt round-robin to the ranks (as in the selection); the per-rank partial sums are merged below
+  const int64_t n_all = n;
+  DevBuf<uint64_t> lu, ld_;
+  DevBuf<double> lc, lm;
+  if (G.nranks > 1) {
+    const int64_t nd = n > G.rank ? (n - G.rank + G.nranks - 1) / G.nranks : 0;
+    DevBuf<int32_t> sidx;
+    SQ_CHECK(sidx.alloc(std::max<int64_t>(nd, 1)));
+    SQ_CHECK(lu.alloc(std::max<int64_t>(nd, 1) * NW));
+    SQ_CHECK(ld_.alloc(std::max<int64_t>(nd, 1) * NW));
+    SQ_CHECK(lc.alloc(std::max<int64_t>(nd, 1)));
+    SQ_CHECK(lm.alloc(std::max<int64_t>(nd, 1)));
+    if (nd > 0) {
+      stride_index_kernel<<<(unsigned)div_up(nd, 256), 256, 0, s>>>(sidx.p, nd, G.rank, G.nranks);
+      SQ_LAUNCH_CHECK();
+      SQ_CHECK(gather_strings(NW, up.p, sidx.p, lu.p, nd, s));
+      SQ_CHECK(gather_strings(NW, dn.p, sidx.p, ld_.p, nd, s));
+      SQ_CHECK(permute_gather(dc.p, sidx.p, lc.p, nd, s));
+      SQ_CHECK(permute_gather(dm.p, sidx.p, lm.p, nd, s));
+      SQ_CUDA(cudaStreamSynchronize(s));
+    }
+    up.release(); dn.release(); dc.release(); dm.release();
+    up.p = lu.take(); dn.p = ld_.take(); dc.p = lc.take(); dm.p = lm.take();
+    n = nd;
+  }
   SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_pt, n,
                {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
   const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
   DevBuf<int32_t> counts;
   SQ_CHECK(counts.alloc(n + 1));
   SQ_CUDA(cudaMemsetAsync(counts.p, 0, (n + 1) * sizeof(int32_t), s));
-  select_kernel<NW, false, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr, nullptr);
-  SQ_LAUNCH_CHECK();
+  if (n > 0) {
+    select_kernel<NW, false, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr, nullptr);
+    SQ_LAUNCH_CHECK();
+  }
   std::vector<int32_t> hc(n + 1);
   SQ_CUDA(cudaMemcpyAsync(hc.data(), counts.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   SQ_CUDA(cudaStreamSynchronize(s));
@@ -739,6 +766,51 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   DevBuf<double> fv;
   int64_t nf = 0;
   SQ_CHECK(reduce_by_det<NW>(T.norb, acc_a, acc_b, acc_v, acc_n, fa, fb, fv, nf, s));
+  if (G.nranks > 1) {  // sizes, padded all-gather of (determinant, partial sum), one more reduction: identical on every rank
+    DevBuf<int64_t> cnt_dev;
+    SQ_CHECK(cnt_dev.alloc(G.nranks));
+    SQ_CUDA(cudaMemcpyAsync(cnt_dev.p + G.rank, &nf, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ncclResult_t rc = ncclAllGather(cnt_dev.p + G.rank, cnt_dev.p, 1, ncclInt64, G.comm, s);
+    if (rc != ncclSuccess) { set_error("pt2: ncclAllGather(sizes) failed: %s", ncclGetErrorString(rc)); return 3; }
+    std::vector<int64_t> cnts(G.nranks);
+    SQ_CUDA(cudaMemcpyAsync(cnts.data(), cnt_dev.p, G.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    int64_t mx = 0, tot = 0;
+    for (int64_t c : cnts) { mx = std::max(mx, c); tot += c; }
+    DevBuf<uint64_t> ga, gb, ca, cb, ma, mb;
+    DevBuf<double> gv, cv, mv;
+    int64_t nm = 0;
+    if (mx > 0) {
+      SQ_CHECK(ga.alloc(mx * NW * G.nranks));
+      SQ_CHECK(gb.alloc(mx * NW * G.nranks));
+      SQ_CHECK(gv.alloc(mx * G.nranks));
+      if (nf > 0) {
+        SQ_CUDA(cudaMemcpyAsync(ga.p + (int64_t)G.rank * mx * NW, fa.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(gb.p + (int64_t)G.rank * mx * NW, fb.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(gv.p + (int64_t)G.rank * mx, fv.p, nf * 8, cudaMemcpyDeviceToDevice, s));
+      }
+      rc = ncclAllGather(ga.p + (int64_t)G.rank * mx * NW, ga.p, mx * NW, ncclUint64, G.comm, s);
+      if (rc == ncclSuccess) rc = ncclAllGather(gb.p + (int64_t)G.rank * mx * NW, gb.p, mx * NW, ncclUint64, G.comm, s);
+      if (rc == ncclSuccess) rc = ncclAllGather(gv.p + (int64_t)G.rank * mx, gv.p, mx, ncclDouble, G.comm, s);
+      if (rc != ncclSuccess) { set_error("pt2: ncclAllGather failed: %s", ncclGetErrorString(rc)); return 3; }
+      SQ_CHECK(ca.alloc(std::max<int64_t>(tot, 1) * NW));
+      SQ_CHECK(cb.alloc(std::max<int64_t>(tot, 1) * NW));
+      SQ_CHECK(cv.alloc(std::max<int64_t>(tot, 1)));
+      int64_t off = 0;
+      for (int r = 0; r < G.nranks; r++) {
+        if (cnts[r] == 0) continue;
+        SQ_CUDA(cudaMemcpyAsync(ca.p + off * NW, ga.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(cb.p + off * NW, gb.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemcpyAsync(cv.p + off, gv.p + (int64_t)r * mx, cnts[r] * 8, cudaMemcpyDeviceToDevice, s));
+        off += cnts[r];
+      }
+      SQ_CUDA(cudaStreamSynchronize(s));
+      SQ_CHECK(reduce_by_det<NW>(T.norb, ca, cb, cv, tot, ma, mb, mv, nm, s));
+    }
+    fa.release(); fb.release(); fv.release();
+    fa.p = ma.take(); fb.p = mb.take(); fv.p = mv.take();
+    nf = nm;
+  }
   double delta = 0.0;
   if (nf > 0) {
     DevBuf<int32_t> ext;
@@ -749,7 +821,7 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
     const unsigned g = (unsigned)div_up(nf, 256);
     uniq_flag_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, ext.p, nf);   // all ones: the list is already unique
     SQ_LAUNCH_CHECK();
-    not_in_list_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, sup.p, sdn.p, n, ext.p, nf);  // 0 for variational determinants
+    not_in_list_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, sup.p, sdn.p, n_all, ext.p, nf);  // 0 for variational determinants
     SQ_LAUNCH_CHECK();
     pt_term_kernel<NW><<<g, 256, 0, s>>>(T, fa.p, fb.p, fv.p, ext.p, var_energy, term.p, nf);
     SQ_LAUNCH_CHECK();

@@ -88,6 +88,15 @@ def main():
         if rank == 0:
             print("multi-gpu parity ok: world=%d time_sym=%s n=%d nnz=%d E=%.10f" % (world, time_sym, n, nnz, got["evals"][0]))
         H.close()
+    # deterministic second-order PT, determinants dealt round-robin to the ranks: the reference's golden HEG numbers
+    Sh = O.System.heg(3, 0.5, 14, 7, 1.49)
+    rh = Sh.hci(1e-3, n_states=1)
+    Hh = sq.SparseHamiltonian(sq.HegSystem(3, 0.5, 14, 7, 1.49), device=local)
+    de, nconn = Hh.second_order_pt(rh["up"], rh["dn"], rh["wts"][:, 0], rh["energy"][0], 2e-7)
+    assert nconn == 501881 and abs(de - (-0.000939196)) < 5e-10, (nconn, de)     # src/e2e_tests/heg/o_det_ref:431
+    if rank == 0:
+        print("multi-gpu PT ok: world=%d ndets_connected=%d delta_e=%.9f" % (world, nconn, de))
+    Hh.close()
     dist.barrier()
     dist.destroy_process_group()
 
