@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "handle.h"
+#include "stream_loads.cuh"
 
 namespace sqmc {
 
@@ -128,29 +129,6 @@ __global__ void __launch_bounds__(256) bundle_decode_kernel(const int64_t *__res
 }
 
 // ------------------------------------------------------------------ H.v on bundles: one warp per bundle, R sums per lane
-struct BPolicies {
-  uint64_t stream, x;
-  __device__ __forceinline__ BPolicies() {
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(x));
-  }
-};
-__device__ __forceinline__ int32_t bld_col(const int32_t *p, const BPolicies &P) {
-  int32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(P.stream));
-  return r;
-}
-__device__ __forceinline__ double bld_val(const double *p, const BPolicies &P) {
-  double r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(P.stream));
-  return r;
-}
-__device__ __forceinline__ double bld_x(const double *p, const BPolicies &P) {
-  double r;
-  asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(P.x));
-  return r;
-}
-
 // branch-free on purpose: written as `if (f == r) acc[r] += p` the compiler emits a jump table and the warp diverges
 template <int R, int Q>
 __device__ __forceinline__ void badd_one(double (&acc)[R], int f, double p) {
@@ -167,7 +145,7 @@ __device__ __forceinline__ void badd(double (&acc)[R], int32_t word, double p) {
 template <int R>
 __global__ void __launch_bounds__(256) spmv_bundle_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
                                                           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
-  const BPolicies P;
+  const Policies P;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= nb) return;
@@ -178,17 +156,17 @@ __global__ void __launch_bounds__(256) spmv_bundle_kernel(const int64_t *__restr
 #pragma unroll
   for (int r = 0; r < R; r++) acc[r] = 0.0;
   for (; k + 96 < e; k += 128) {
-    const int32_t c0 = bld_col(cols + k, P), c1 = bld_col(cols + k + 32, P), c2 = bld_col(cols + k + 64, P), c3 = bld_col(cols + k + 96, P);
-    const double v0 = bld_val(vals + k, P), v1 = bld_val(vals + k + 32, P), v2 = bld_val(vals + k + 64, P), v3 = bld_val(vals + k + 96, P);
-    const double x0 = bld_x(x + (c0 >> kBShift), P), x1 = bld_x(x + (c1 >> kBShift), P), x2 = bld_x(x + (c2 >> kBShift), P), x3 = bld_x(x + (c3 >> kBShift), P);
+    const int32_t c0 = ld_col(cols + k, P), c1 = ld_col(cols + k + 32, P), c2 = ld_col(cols + k + 64, P), c3 = ld_col(cols + k + 96, P);
+    const double v0 = ld_val(vals + k, P), v1 = ld_val(vals + k + 32, P), v2 = ld_val(vals + k + 64, P), v3 = ld_val(vals + k + 96, P);
+    const double x0 = ld_x(x + (c0 >> kBShift), P), x1 = ld_x(x + (c1 >> kBShift), P), x2 = ld_x(x + (c2 >> kBShift), P), x3 = ld_x(x + (c3 >> kBShift), P);
     badd<R>(acc, c0, v0 * x0);
     badd<R>(acc, c1, v1 * x1);
     badd<R>(acc, c2, v2 * x2);
     badd<R>(acc, c3, v3 * x3);
   }
   for (; k < e; k += 32) {
-    const int32_t c = bld_col(cols + k, P);
-    badd<R>(acc, c, bld_val(vals + k, P) * bld_x(x + (c >> kBShift), P));
+    const int32_t c = ld_col(cols + k, P);
+    badd<R>(acc, c, ld_val(vals + k, P) * ld_x(x + (c >> kBShift), P));
   }
   double mine = 0.0;
 #pragma unroll
@@ -207,7 +185,7 @@ __global__ void __launch_bounds__(256) spmv_bundle_kernel(const int64_t *__restr
 template <int R, int U>
 __global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
                                                                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
-  const BPolicies P;
+  const Policies P;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= nb) return;
@@ -222,23 +200,23 @@ __global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__
   bool have = kb + 32 * U <= e;
   if (have) {
 #pragma unroll
-    for (int u = 0; u < U; u++) c[u] = bld_col(cols + kb + lane + 32 * u, P);
+    for (int u = 0; u < U; u++) c[u] = ld_col(cols + kb + lane + 32 * u, P);
 #pragma unroll
-    for (int u = 0; u < U; u++) v[u] = bld_val(vals + kb + lane + 32 * u, P);
+    for (int u = 0; u < U; u++) v[u] = ld_val(vals + kb + lane + 32 * u, P);
   }
   while (have) {
     double xx[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) xx[u] = bld_x(x + (c[u] >> kBShift), P);
+    for (int u = 0; u < U; u++) xx[u] = ld_x(x + (c[u] >> kBShift), P);
     const int64_t kn = kb + 32 * U;
     const bool hn = kn + 32 * U <= e;
     int32_t cn[U];
     double vn[U];
     if (hn) {
 #pragma unroll
-      for (int u = 0; u < U; u++) cn[u] = bld_col(cols + kn + lane + 32 * u, P);
+      for (int u = 0; u < U; u++) cn[u] = ld_col(cols + kn + lane + 32 * u, P);
 #pragma unroll
-      for (int u = 0; u < U; u++) vn[u] = bld_val(vals + kn + lane + 32 * u, P);
+      for (int u = 0; u < U; u++) vn[u] = ld_val(vals + kn + lane + 32 * u, P);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) badd<R>(acc, c[u], v[u] * xx[u]);
@@ -248,8 +226,8 @@ __global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__
     have = hn;
   }
   for (int64_t k = kb + lane; k < e; k += 32) {
-    const int32_t cc = bld_col(cols + k, P);
-    badd<R>(acc, cc, bld_val(vals + k, P) * bld_x(x + (cc >> kBShift), P));
+    const int32_t cc = ld_col(cols + k, P);
+    badd<R>(acc, cc, ld_val(vals + k, P) * ld_x(x + (cc >> kBShift), P));
   }
   double mine = 0.0;
 #pragma unroll
@@ -265,7 +243,7 @@ __global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__
 // two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x2 / y2 hold the two vectors
 // interleaved (x2[2*col + k]), so one 16-byte gather serves both and the matrix is streamed once:
 // algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)
-__device__ __forceinline__ double2 bld_x2(const double *p, const BPolicies &P) {
+__device__ __forceinline__ double2 bld_x2(const double *p, const Policies &P) {
   double2 r;
   asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(P.x));
   return r;
@@ -273,7 +251,7 @@ __device__ __forceinline__ double2 bld_x2(const double *p, const BPolicies &P) {
 template <int R, int U>
 __global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
                                                                 const double *__restrict__ vals, const double *__restrict__ x2, double *__restrict__ y2) {
-  const BPolicies P;
+  const Policies P;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= nb) return;
@@ -288,9 +266,9 @@ __global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *_
   bool have = kb + 32 * U <= e;
   if (have) {
 #pragma unroll
-    for (int u = 0; u < U; u++) c[u] = bld_col(cols + kb + lane + 32 * u, P);
+    for (int u = 0; u < U; u++) c[u] = ld_col(cols + kb + lane + 32 * u, P);
 #pragma unroll
-    for (int u = 0; u < U; u++) v[u] = bld_val(vals + kb + lane + 32 * u, P);
+    for (int u = 0; u < U; u++) v[u] = ld_val(vals + kb + lane + 32 * u, P);
   }
   while (have) {
     double2 xx[U];
@@ -302,9 +280,9 @@ __global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *_
     double vn[U];
     if (hn) {
 #pragma unroll
-      for (int u = 0; u < U; u++) cn[u] = bld_col(cols + kn + lane + 32 * u, P);
+      for (int u = 0; u < U; u++) cn[u] = ld_col(cols + kn + lane + 32 * u, P);
 #pragma unroll
-      for (int u = 0; u < U; u++) vn[u] = bld_val(vals + kn + lane + 32 * u, P);
+      for (int u = 0; u < U; u++) vn[u] = ld_val(vals + kn + lane + 32 * u, P);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -317,8 +295,8 @@ __global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *_
     have = hn;
   }
   for (int64_t k = kb + lane; k < e; k += 32) {
-    const int32_t cc = bld_col(cols + k, P);
-    const double vv = bld_val(vals + k, P);
+    const int32_t cc = ld_col(cols + k, P);
+    const double vv = ld_val(vals + k, P);
     const double2 xv = bld_x2(x2 + 2 * (int64_t)(cc >> kBShift), P);
     badd<R>(acc0, cc, vv * xv.x);
     badd<R>(acc1, cc, vv * xv.y);

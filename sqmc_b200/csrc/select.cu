@@ -392,6 +392,84 @@ static int sort_unique_new(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, i
   return 0;
 }
 
+// nranks > 1: deal the determinants round-robin to the ranks (the early, large-coefficient determinants of an HCI list
+// generate most of the connections, so contiguous slices would be unbalanced).  Replaces (up, dn, c, m) by this rank's
+// share and returns its size.
+template <int NW>
+static int shard_round_robin(DevBuf<uint64_t> &up, DevBuf<uint64_t> &dn, DevBuf<double> &c, DevBuf<double> &m, int64_t n, int64_t &n_local,
+                             cudaStream_t s) {
+  n_local = n;
+  if (G.nranks == 1) return 0;
+  const int64_t nd = n > G.rank ? (n - G.rank + G.nranks - 1) / G.nranks : 0;
+  DevBuf<int32_t> sidx;
+  DevBuf<uint64_t> lu, ld_;
+  DevBuf<double> lc, lm;
+  SQ_CHECK(sidx.alloc(std::max<int64_t>(nd, 1)));
+  SQ_CHECK(lu.alloc(std::max<int64_t>(nd, 1) * NW));
+  SQ_CHECK(ld_.alloc(std::max<int64_t>(nd, 1) * NW));
+  SQ_CHECK(lc.alloc(std::max<int64_t>(nd, 1)));
+  SQ_CHECK(lm.alloc(std::max<int64_t>(nd, 1)));
+  if (nd > 0) {
+    stride_index_kernel<<<(unsigned)div_up(nd, 256), 256, 0, s>>>(sidx.p, nd, G.rank, G.nranks);
+    SQ_LAUNCH_CHECK();
+    SQ_CHECK(gather_strings(NW, up.p, sidx.p, lu.p, nd, s));
+    SQ_CHECK(gather_strings(NW, dn.p, sidx.p, ld_.p, nd, s));
+    SQ_CHECK(permute_gather(c.p, sidx.p, lc.p, nd, s));
+    SQ_CHECK(permute_gather(m.p, sidx.p, lm.p, nd, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  up.release(); dn.release(); c.release(); m.release();
+  up.p = lu.take(); dn.p = ld_.take(); c.p = lc.take(); m.p = lm.take();
+  n_local = nd;
+  return 0;
+}
+
+// nranks > 1: concatenate the rank-local lists (a, b[, v]) of nf entries on every rank (sizes all-gathered, payload padded to the
+// largest list for a plain ncclAllGather).  v may be null.  Returns the concatenation in (ca, cb, cv) with tot entries.
+template <int NW>
+static int allgather_lists(const uint64_t *a, const uint64_t *b, const double *v, int64_t nf, DevBuf<uint64_t> &ca, DevBuf<uint64_t> &cb,
+                           DevBuf<double> &cv, int64_t &tot, cudaStream_t s) {
+  DevBuf<int64_t> cnt_dev;
+  SQ_CHECK(cnt_dev.alloc(G.nranks));
+  SQ_CUDA(cudaMemcpyAsync(cnt_dev.p + G.rank, &nf, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  ncclResult_t rc = ncclAllGather(cnt_dev.p + G.rank, cnt_dev.p, 1, ncclInt64, G.comm, s);
+  if (rc != ncclSuccess) { set_error("ncclAllGather(list sizes) failed: %s", ncclGetErrorString(rc)); return 3; }
+  std::vector<int64_t> cnts(G.nranks);
+  SQ_CUDA(cudaMemcpyAsync(cnts.data(), cnt_dev.p, G.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  int64_t mx = 0;
+  tot = 0;
+  for (int64_t c : cnts) { mx = std::max(mx, c); tot += c; }
+  if (mx == 0) return 0;
+  DevBuf<uint64_t> ga, gb;
+  DevBuf<double> gv;
+  SQ_CHECK(ga.alloc(mx * NW * G.nranks));
+  SQ_CHECK(gb.alloc(mx * NW * G.nranks));
+  if (v) SQ_CHECK(gv.alloc(mx * G.nranks));
+  if (nf > 0) {
+    SQ_CUDA(cudaMemcpyAsync(ga.p + (int64_t)G.rank * mx * NW, a, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaMemcpyAsync(gb.p + (int64_t)G.rank * mx * NW, b, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
+    if (v) SQ_CUDA(cudaMemcpyAsync(gv.p + (int64_t)G.rank * mx, v, nf * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  rc = ncclAllGather(ga.p + (int64_t)G.rank * mx * NW, ga.p, mx * NW, ncclUint64, G.comm, s);
+  if (rc == ncclSuccess) rc = ncclAllGather(gb.p + (int64_t)G.rank * mx * NW, gb.p, mx * NW, ncclUint64, G.comm, s);
+  if (rc == ncclSuccess && v) rc = ncclAllGather(gv.p + (int64_t)G.rank * mx, gv.p, mx, ncclDouble, G.comm, s);
+  if (rc != ncclSuccess) { set_error("ncclAllGather(lists) failed: %s", ncclGetErrorString(rc)); return 3; }
+  SQ_CHECK(ca.alloc(std::max<int64_t>(tot, 1) * NW));
+  SQ_CHECK(cb.alloc(std::max<int64_t>(tot, 1) * NW));
+  if (v) SQ_CHECK(cv.alloc(std::max<int64_t>(tot, 1)));
+  int64_t off = 0;
+  for (int r = 0; r < G.nranks; r++) {
+    if (cnts[r] == 0) continue;
+    SQ_CUDA(cudaMemcpyAsync(ca.p + off * NW, ga.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaMemcpyAsync(cb.p + off * NW, gb.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
+    if (v) SQ_CUDA(cudaMemcpyAsync(cv.p + off, gv.p + (int64_t)r * mx, cnts[r] * 8, cudaMemcpyDeviceToDevice, s));
+    off += cnts[r];
+  }
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 template <int NW>
 static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *coeffs, double *min_H, double eps_var,
                        int64_t *n_new_out) {
@@ -423,34 +501,9 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   if (want_hb < 0) { const char *e = getenv("SQMC_SELECT_TABLES"); want_hb = (e && atoi(e) == 0) ? 0 : 1; }
   const bool use_hb = want_hb && T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
   if (use_hb) SQ_CHECK(hb_build(h));
-  // nranks > 1: the determinants are dealt round-robin to the ranks (the early, large-coefficient determinants of an HCI
-  // list generate most of the connections, so contiguous slices would be unbalanced); every rank expands its share,
-  // removes duplicates and members of the list locally, and the survivors are all-gathered and merged below
-  int64_t nd = n;
-  const uint64_t *eu = up.p, *ed = dn.p;
-  const double *ec = dc.p, *em = dm.p;
-  DevBuf<uint64_t> lu, ld_;
-  DevBuf<double> lc, lm;
-  if (G.nranks > 1) {
-    nd = n > G.rank ? (n - G.rank + G.nranks - 1) / G.nranks : 0;
-    DevBuf<int32_t> sidx;
-    SQ_CHECK(sidx.alloc(std::max<int64_t>(nd, 1)));
-    SQ_CHECK(lu.alloc(std::max<int64_t>(nd, 1) * NW));
-    SQ_CHECK(ld_.alloc(std::max<int64_t>(nd, 1) * NW));
-    SQ_CHECK(lc.alloc(std::max<int64_t>(nd, 1)));
-    SQ_CHECK(lm.alloc(std::max<int64_t>(nd, 1)));
-    if (nd > 0) {
-      stride_index_kernel<<<(unsigned)div_up(nd, 256), 256, 0, s>>>(sidx.p, nd, G.rank, G.nranks);
-      SQ_LAUNCH_CHECK();
-      SQ_CHECK(gather_strings(NW, up.p, sidx.p, lu.p, nd, s));
-      SQ_CHECK(gather_strings(NW, dn.p, sidx.p, ld_.p, nd, s));
-      SQ_CHECK(permute_gather(dc.p, sidx.p, lc.p, nd, s));
-      SQ_CHECK(permute_gather(dm.p, sidx.p, lm.p, nd, s));
-      SQ_CUDA(cudaStreamSynchronize(s));
-    }
-    eu = lu.p; ed = ld_.p; ec = lc.p; em = lm.p;
-  }
-  SelCtx<NW> S{T, h->d_orbsym, eu, ed, ec, em, eps_var, nd,
+  int64_t nd = n;  // determinants this rank expands (all of them on one rank)
+  SQ_CHECK(shard_round_robin<NW>(up, dn, dc, dm, n, nd, s));
+  SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_var, nd,
                {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
   const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
   // count pass over all determinants
@@ -513,41 +566,12 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   DevBuf<uint64_t> fa, fb;
   int64_t nf = 0;
   SQ_CHECK(sort_unique_new<NW>(T.norb, acc_a, acc_b, acc_n, nullptr, nullptr, 0, fa, fb, nf, s));
-  if (G.nranks > 1) {  // merge the rank-local results: sizes, padded all-gather, sort + unique once more
-    DevBuf<int64_t> cnt_dev;
-    SQ_CHECK(cnt_dev.alloc(G.nranks));
-    SQ_CUDA(cudaMemcpyAsync(cnt_dev.p + G.rank, &nf, sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    ncclResult_t rc = ncclAllGather(cnt_dev.p + G.rank, cnt_dev.p, 1, ncclInt64, G.comm, s);
-    if (rc != ncclSuccess) { set_error("hci_select: ncclAllGather(sizes) failed: %s", ncclGetErrorString(rc)); return 3; }
-    std::vector<int64_t> cnts(G.nranks);
-    SQ_CUDA(cudaMemcpyAsync(cnts.data(), cnt_dev.p, G.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    SQ_CUDA(cudaStreamSynchronize(s));
-    int64_t mx = 0, tot = 0;
-    for (int64_t c : cnts) { mx = std::max(mx, c); tot += c; }
-    DevBuf<uint64_t> ga, gb, ca, cb, ma, mb;
-    int64_t nm = 0;
-    if (mx > 0) {
-      SQ_CHECK(ga.alloc(mx * NW * G.nranks));
-      SQ_CHECK(gb.alloc(mx * NW * G.nranks));
-      if (nf > 0) {
-        SQ_CUDA(cudaMemcpyAsync(ga.p + (int64_t)G.rank * mx * NW, fa.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(gb.p + (int64_t)G.rank * mx * NW, fb.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
-      }
-      rc = ncclAllGather(ga.p + (int64_t)G.rank * mx * NW, ga.p, mx * NW, ncclUint64, G.comm, s);
-      if (rc == ncclSuccess) rc = ncclAllGather(gb.p + (int64_t)G.rank * mx * NW, gb.p, mx * NW, ncclUint64, G.comm, s);
-      if (rc != ncclSuccess) { set_error("hci_select: ncclAllGather(dets) failed: %s", ncclGetErrorString(rc)); return 3; }
-      SQ_CHECK(ca.alloc(std::max<int64_t>(tot, 1) * NW));
-      SQ_CHECK(cb.alloc(std::max<int64_t>(tot, 1) * NW));
-      int64_t off = 0;
-      for (int r = 0; r < G.nranks; r++) {
-        if (cnts[r] == 0) continue;
-        SQ_CUDA(cudaMemcpyAsync(ca.p + off * NW, ga.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(cb.p + off * NW, gb.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
-        off += cnts[r];
-      }
-      SQ_CUDA(cudaStreamSynchronize(s));
-      SQ_CHECK(sort_unique_new<NW>(T.norb, ca, cb, tot, nullptr, nullptr, 0, ma, mb, nm, s));
-    }
+  if (G.nranks > 1) {  // merge the rank-local results: all-gather, sort + unique once more (identical on every rank)
+    DevBuf<uint64_t> ca, cb, ma, mb;
+    DevBuf<double> none;
+    int64_t tot = 0, nm = 0;
+    SQ_CHECK(allgather_lists<NW>(fa.p, fb.p, nullptr, nf, ca, cb, none, tot, s));
+    if (tot > 0) SQ_CHECK(sort_unique_new<NW>(T.norb, ca, cb, tot, nullptr, nullptr, 0, ma, mb, nm, s));
     fa.release(); fb.release();
     fa.p = ma.take(); fb.p = mb.take();
     nf = nm;
@@ -673,31 +697,8 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   }
   const bool use_hb = T.model == MODEL_CHEM && NW == 1 && T.norb <= 64;
   if (use_hb) SQ_CHECK(hb_build(h));
-  // nranks > 1: determinants dealt round-robin to the ranks (as in the selection); the per-rank partial sums are merged below
   const int64_t n_all = n;
-  DevBuf<uint64_t> lu, ld_;
-  DevBuf<double> lc, lm;
-  if (G.nranks > 1) {
-    const int64_t nd = n > G.rank ? (n - G.rank + G.nranks - 1) / G.nranks : 0;
-    DevBuf<int32_t> sidx;
-    SQ_CHECK(sidx.alloc(std::max<int64_t>(nd, 1)));
-    SQ_CHECK(lu.alloc(std::max<int64_t>(nd, 1) * NW));
-    SQ_CHECK(ld_.alloc(std::max<int64_t>(nd, 1) * NW));
-    SQ_CHECK(lc.alloc(std::max<int64_t>(nd, 1)));
-    SQ_CHECK(lm.alloc(std::max<int64_t>(nd, 1)));
-    if (nd > 0) {
-      stride_index_kernel<<<(unsigned)div_up(nd, 256), 256, 0, s>>>(sidx.p, nd, G.rank, G.nranks);
-      SQ_LAUNCH_CHECK();
-      SQ_CHECK(gather_strings(NW, up.p, sidx.p, lu.p, nd, s));
-      SQ_CHECK(gather_strings(NW, dn.p, sidx.p, ld_.p, nd, s));
-      SQ_CHECK(permute_gather(dc.p, sidx.p, lc.p, nd, s));
-      SQ_CHECK(permute_gather(dm.p, sidx.p, lm.p, nd, s));
-      SQ_CUDA(cudaStreamSynchronize(s));
-    }
-    up.release(); dn.release(); dc.release(); dm.release();
-    up.p = lu.take(); dn.p = ld_.take(); dc.p = lc.take(); dm.p = lm.take();
-    n = nd;
-  }
+  SQ_CHECK(shard_round_robin<NW>(up, dn, dc, dm, n_all, n, s));  // n = this rank's share; partial sums are merged below
   SelCtx<NW> S{T, h->d_orbsym, up.p, dn.p, dc.p, dm.p, eps_pt, n,
                {use_hb ? h->d_hb_val[0] : nullptr, use_hb ? h->d_hb_val[1] : nullptr}, {use_hb ? h->d_hb_rs[0] : nullptr, use_hb ? h->d_hb_rs[1] : nullptr}};
   const int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
@@ -766,47 +767,12 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   DevBuf<double> fv;
   int64_t nf = 0;
   SQ_CHECK(reduce_by_det<NW>(T.norb, acc_a, acc_b, acc_v, acc_n, fa, fb, fv, nf, s));
-  if (G.nranks > 1) {  // sizes, padded all-gather of (determinant, partial sum), one more reduction: identical on every rank
-    DevBuf<int64_t> cnt_dev;
-    SQ_CHECK(cnt_dev.alloc(G.nranks));
-    SQ_CUDA(cudaMemcpyAsync(cnt_dev.p + G.rank, &nf, sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    ncclResult_t rc = ncclAllGather(cnt_dev.p + G.rank, cnt_dev.p, 1, ncclInt64, G.comm, s);
-    if (rc != ncclSuccess) { set_error("pt2: ncclAllGather(sizes) failed: %s", ncclGetErrorString(rc)); return 3; }
-    std::vector<int64_t> cnts(G.nranks);
-    SQ_CUDA(cudaMemcpyAsync(cnts.data(), cnt_dev.p, G.nranks * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    SQ_CUDA(cudaStreamSynchronize(s));
-    int64_t mx = 0, tot = 0;
-    for (int64_t c : cnts) { mx = std::max(mx, c); tot += c; }
-    DevBuf<uint64_t> ga, gb, ca, cb, ma, mb;
-    DevBuf<double> gv, cv, mv;
-    int64_t nm = 0;
-    if (mx > 0) {
-      SQ_CHECK(ga.alloc(mx * NW * G.nranks));
-      SQ_CHECK(gb.alloc(mx * NW * G.nranks));
-      SQ_CHECK(gv.alloc(mx * G.nranks));
-      if (nf > 0) {
-        SQ_CUDA(cudaMemcpyAsync(ga.p + (int64_t)G.rank * mx * NW, fa.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(gb.p + (int64_t)G.rank * mx * NW, fb.p, nf * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(gv.p + (int64_t)G.rank * mx, fv.p, nf * 8, cudaMemcpyDeviceToDevice, s));
-      }
-      rc = ncclAllGather(ga.p + (int64_t)G.rank * mx * NW, ga.p, mx * NW, ncclUint64, G.comm, s);
-      if (rc == ncclSuccess) rc = ncclAllGather(gb.p + (int64_t)G.rank * mx * NW, gb.p, mx * NW, ncclUint64, G.comm, s);
-      if (rc == ncclSuccess) rc = ncclAllGather(gv.p + (int64_t)G.rank * mx, gv.p, mx, ncclDouble, G.comm, s);
-      if (rc != ncclSuccess) { set_error("pt2: ncclAllGather failed: %s", ncclGetErrorString(rc)); return 3; }
-      SQ_CHECK(ca.alloc(std::max<int64_t>(tot, 1) * NW));
-      SQ_CHECK(cb.alloc(std::max<int64_t>(tot, 1) * NW));
-      SQ_CHECK(cv.alloc(std::max<int64_t>(tot, 1)));
-      int64_t off = 0;
-      for (int r = 0; r < G.nranks; r++) {
-        if (cnts[r] == 0) continue;
-        SQ_CUDA(cudaMemcpyAsync(ca.p + off * NW, ga.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(cb.p + off * NW, gb.p + (int64_t)r * mx * NW, cnts[r] * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(cv.p + off, gv.p + (int64_t)r * mx, cnts[r] * 8, cudaMemcpyDeviceToDevice, s));
-        off += cnts[r];
-      }
-      SQ_CUDA(cudaStreamSynchronize(s));
-      SQ_CHECK(reduce_by_det<NW>(T.norb, ca, cb, cv, tot, ma, mb, mv, nm, s));
-    }
+  if (G.nranks > 1) {  // all-gather of (determinant, partial sum), one more reduction: identical on every rank
+    DevBuf<uint64_t> ca, cb, ma, mb;
+    DevBuf<double> cv, mv;
+    int64_t tot = 0, nm = 0;
+    SQ_CHECK(allgather_lists<NW>(fa.p, fb.p, fv.p, nf, ca, cb, cv, tot, s));
+    if (tot > 0) SQ_CHECK(reduce_by_det<NW>(T.norb, ca, cb, cv, tot, ma, mb, mv, nm, s));
     fa.release(); fb.release(); fv.release();
     fa.p = ma.take(); fb.p = mb.take(); fv.p = mv.take();
     nf = nm;
