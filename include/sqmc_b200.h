@@ -81,7 +81,8 @@ int sqmc_b200_hci_new_dets(sqmc_b200_handle *h, void *new_up /* n_new x 16 B */,
  * (semistoch.f90:1579-2231) + the sum over the determinants outside the variational space (:1160-1170):
  *   delta_e = sum_a (sum_i H_ai c_i)^2 / (var_energy - H_aa),  |H_ai c_i| above eps_pt by the selection rules.
  * wts: the n variational coefficients of the state; n_connected: distinct determinants generated, variational ones
- * included (the "ndets_connected" the reference prints, e2e_tests/heg/o_det_ref:431).  chem (time_sym = f) and heg. */
+ * included (the "ndets_connected" the reference prints, e2e_tests/heg/o_det_ref:431).  chem (plain and time-reversal
+ * symmetrised determinants) and heg. */
 int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy,
                   double eps_pt, double *delta_e, int64_t *n_connected);
 

@@ -977,16 +977,22 @@ static void chem_max_double(System &S) {
   S.max_double = mx;
 }
 static void important_connected_chem(System &S, det_t det_up, det_t det_dn, double eps, double min_H_done,
-                                     std::vector<det_t> &out_up, std::vector<det_t> &out_dn) {
+                                     std::vector<det_t> &out_up, std::vector<det_t> &out_dn, std::vector<double> *elems = nullptr) {
   int norb = S.norb;
   out_up.push_back(det_up); out_dn.push_back(det_dn);  // :6893-6895
-  auto emit = [&](det_t nu, det_t nd) {
+  if (elems) elems->push_back(0.0);                     // matrix_elements(1) = 0 (:6892)
+  // me = determinant-level element; with time_sym only "this contribution to the off-diagonal matrix element" is kept:
+  // norm factors :6961-6964 / :7121-7124, then z when the result is mapped to its representative :6966-6971 / :7127-7134
+  auto emit = [&](det_t nu, det_t nd, double me) {
     if (S.time_sym) {
       if (nu == nd && S.z < 0) return;
       if (det_up == nd && det_dn == nu) return;
+      if (det_up == det_dn && nu != nd) me = S.sqrt2inv * me;
+      if (nu == nd && det_up != det_dn) me = S.sqrt2 * me;
     }
-    if (S.time_sym && nu > nd) std::swap(nu, nd);
+    if (S.time_sym && nu > nd) { std::swap(nu, nd); me = S.z * me; }
     out_up.push_back(nu); out_dn.push_back(nd);
+    if (elems) elems->push_back(me);
   };
   // singles :6906-6985
   for (int spin = 0; spin < 2; spin++) {
@@ -1004,16 +1010,17 @@ static void important_connected_chem(System &S, det_t det_up, det_t det_dn, doub
         double me = hamiltonian_chem(S, det_up, det_dn, nu_, nd_, 1);
         if (std::fabs(me) < eps) continue;
         if (std::fabs(me) > min_H_done) continue;
-        emit(nu_, nd_);
+        emit(nu_, nd_, me);
       }
   }
   if (eps > S.max_double) return;  // :6995
   // doubles :7023-7157
   auto try_double = [&](det_t nu, det_t nd) {
-    double absH = std::fabs(hamiltonian_chem(S, det_up, det_dn, nu, nd, 2));
+    const double me = hamiltonian_chem(S, det_up, det_dn, nu, nd, 2);
+    double absH = std::fabs(me);
     if (absH <= eps) return;
     if (absH > min_H_done) return;
-    emit(nu, nd);
+    emit(nu, nd, me);
   };
   for (int spin = 0; spin < 2; spin++) {
     det_t d = spin == 0 ? det_up : det_dn;
@@ -1484,7 +1491,8 @@ long long orc_select(void *h, long long n, const det_t *up, const det_t *dn, con
 //   contributions to the same determinant are summed after a sort by label (merge_original_with_spawned3);
 //   delta_E = sum over a NOT in the variational space of (sum_i H_ai c_i)^2 / (E_var - H_aa)   (hci.f90:1160-1170).
 // Returns delta_E; *n_connected = number of distinct determinants generated (variational ones included), the
-// "ndets_connected" the reference prints.  Chemistry: plain determinants only (time_sym = f).
+// "ndets_connected" the reference prints.  Chemistry elements follow find_important_connected_dets_chem (incl. the
+// time-reversal factors); H_aa is the symmetrised diagonal element when time_sym (hci.f90:1164-1166).
 double orc_pt2(void *h, long long n, const det_t *up, const det_t *dn, const double *wts, double var_energy, double eps_pt, long long *n_connected) {
   System &S = *(System *)h;
   if (S.model == 0) chem_max_double(S); else if (S.model == 1) heg_max_double(S);
@@ -1493,12 +1501,13 @@ double orc_pt2(void *h, long long n, const det_t *up, const det_t *dn, const dou
   for (long long i = 0; i < n; i++) {
     if (wts[i] == 0.0) continue;                       // semistoch.f90:1762
     tu.clear(); td.clear();
+    std::vector<double> el;
     const double eps = eps_pt / std::fabs(wts[i]);
-    if (S.model == 0) important_connected_chem(S, up[i], dn[i], eps, 9.e99, tu, td);
+    if (S.model == 0) important_connected_chem(S, up[i], dn[i], eps, 9.e99, tu, td, &el);
     else important_connected_heg(S, up[i], dn[i], eps, tu, td);
     for (size_t k = 0; k < tu.size(); k++) {
       double me = 0.0;                                  // first entry = the determinant itself, element set to 0
-      if (k > 0) me = hamiltonian(S, up[i], dn[i], tu[k], td[k]);
+      if (k > 0) me = S.model == 0 ? el[k] : hamiltonian(S, up[i], dn[i], tu[k], td[k]);
       cu.push_back(tu[k]); cd.push_back(td[k]); num.push_back(me * wts[i]);
     }
   }

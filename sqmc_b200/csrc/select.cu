@@ -144,8 +144,19 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
   const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
   int64_t base = FILL ? out_ptr[i - i_begin] : 0;
   int cnt = 0;
+  // val = determinant-level element (VALS only): under time-reversal symmetry only this contribution to the symmetrised
+  // element is kept -- norm factors (chemistry.f90:6961-6964, 7121-7124), z when mapped to the representative
+  // (:6966-6971, 7127-7134) -- and the coefficient of the generating determinant is multiplied in last (semistoch.f90:2048)
   auto emit = [&](bool keep, Bits<NW> nu, Bits<NW> nd, double val) {
-    if (keep && ts && b_lt(nd, nu)) { Bits<NW> t = nu; nu = nd; nd = t; }  // representative up <= dn
+    if (VALS && keep && ts) {
+      if (b_eq(u, d) && !b_eq(nu, nd)) val = T.sqrt2inv * val;
+      if (b_eq(nu, nd) && !b_eq(u, d)) val = T.sqrt2 * val;
+    }
+    if (keep && ts && b_lt(nd, nu)) {  // representative up <= dn
+      Bits<NW> t = nu; nu = nd; nd = t;
+      if (VALS) val = T.z * val;
+    }
+    if (VALS) val = val * cs;
     unsigned m = __ballot_sync(full, keep);
     if (FILL && keep) {
       int64_t q = base + cnt + __popc(m & lt);
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
               }
             }
           }
-          emit(keep, nu, nd, val * cs);
+          emit(keep, nu, nd, val);
         }
       }
     }
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
               if (keep && ts_excluded(nu, nd)) keep = false;
             }
             double val = 0.0;
-            if (VALS && keep) val = chem_double(C, u, d, nu, nd) * cs;  // the table holds |H|; the sign needs the determinant
+            if (VALS && keep) val = chem_double(C, u, d, nu, nd);  // the table holds |H|; the sign needs the determinant
             emit(keep, nu, nd, val);
           }
         }
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
             keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
           }
         }
-        emit(keep, nu, nd, val * cs);
+        emit(keep, nu, nd, val);
       }
     }
     // ---- opposite-spin doubles
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
             keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
           }
         }
-        emit(keep, nu, nd, val * cs);
+        emit(keep, nu, nd, val);
       }
     }
   }
@@ -809,7 +820,6 @@ int pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn
         double *delta_out, int64_t *nconn_out) {
   if (n <= 0) { set_error("pt2: n must be positive"); return 2; }
   if (h->T.model == MODEL_HUBBARDK) { set_error("pt2: only chem and heg"); return 2; }
-  if (h->T.model == MODEL_CHEM && h->T.time_sym) { set_error("pt2: time-reversal symmetrised determinants are not supported (time_sym = f only)"); return 2; }
   if (h->T.model == MODEL_CHEM && !h->d_orbsym) { set_error("pt2: call sqmc_b200_system_orbital_symmetries first"); return 2; }
   if (!(eps_pt > 0.0)) { set_error("pt2: eps_pt must be > 0 (the screened sum, hci.f90:1143)"); return 2; }
   return h->NW == 1 ? pt2_impl<1>(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_out, nconn_out)

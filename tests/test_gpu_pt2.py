@@ -51,9 +51,23 @@ def test_c2_pt_matches_oracle(oracle, c2_space, eps_pt):
     assert abs(de - ode) < 1e-11 and de < 0
 
 
-def test_pt_rejects_unsupported_inputs(c2_space_ts):
+@pytest.mark.parametrize("eps_pt", [1e-5, 1e-6])
+def test_c2_time_sym_pt_matches_oracle(oracle, c2_space_ts, eps_pt):
+    """the shipped C2 input is time_sym = t: numerators carry the norm factors and z of chemistry.f90:6961-6971,7121-7134,
+    contributions of a determinant and of its time-reversed partner merge on the representative, H_aa is the
+    symmetrised diagonal element (hci.f90:1164-1166)"""
     import sqmc_b200 as sq
     s, r = c2_space_ts
     H = sq.SparseHamiltonian(sq.ChemSystem(C2_FCIDUMP, time_sym=True, z=1))
-    with pytest.raises(Exception, match="time_sym"):
-        H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 1e-5)
+    de, nconn = H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], eps_pt)
+    ode, onc = s.pt2(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], eps_pt)
+    assert nconn == onc
+    assert abs(de - ode) < 1e-11 and de < 0
+
+
+def test_pt_rejects_bad_arguments(c2_space):
+    import sqmc_b200 as sq
+    s, r = c2_space
+    H = sq.SparseHamiltonian(sq.ChemSystem(C2_FCIDUMP))
+    with pytest.raises(Exception, match="eps_pt"):
+        H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 0.0)
