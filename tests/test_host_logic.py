@@ -109,3 +109,19 @@ def test_splitmix_vector_is_rank_independent():
     x = spaces.splitmix_vector(1000)
     assert abs(np.linalg.norm(x) - 1) < 1e-14 and np.array_equal(x, spaces.splitmix_vector(1000))
     assert x.min() < 0 < x.max()
+
+
+def test_reference_input_files_are_parsed():
+    """sqmc_b200.hci.read_input on the two input layouts the reference ships"""
+    from sqmc_b200 import hci
+    c2 = hci.read_input(os.path.join(ROOT, "data", "C2_v2z_curve", "r1.24253", "i_1sigma_g"))
+    assert c2["hamiltonian_type"] == "chem" and (c2["nelec"], c2["nup"], c2["norb"]) == (8, 4, 26)
+    assert c2["time_sym"] is True and c2["z"] == 1 and c2["n_states"] == 2
+    assert (c2["eps_var"], c2["eps_pt"]) == (1e-3, 1e-7) and c2["eps_var_sched"] == [2e-3, 2e-3]     # 2*2e-3 repeat syntax
+    assert c2["orbital_symmetries"] == [1, 5, 3, 2, 1, 7, 6, 5, 1, 2, 3, 1, 6, 7, 5, 4, 1, 5, 3, 2, 8, 5, 1, 7, 6, 5]
+    assert c2["hf_symmetry"] == 1 and c2["n_mc"] == 0
+    heg = hci.read_input(os.path.join(ROOT, "tests", "golden", "heg_i_det"))
+    assert heg["hamiltonian_type"] == "heg" and (heg["n_dim"], heg["r_s"], heg["nelec"], heg["nup"]) == (3, 0.5, 14, 7)
+    assert heg["cutoff_radius"] == 1.49 and (heg["eps_var"], heg["eps_pt"], heg["n_states"]) == (1e-3, 2e-7, 1)
+    s = hci.eps_schedule(1e-3, [2e-3, 2e-3])
+    assert len(s) == 30 and s[0] == s[1] == 2e-3 and s[2] == s[29] == 1e-3
