@@ -631,6 +631,16 @@ __global__ void pt_term_kernel(ModelTables T, const uint64_t *a, const uint64_t 
   }
   term[t] = r;
 }
+// out[t] = sum of v[off[t] .. off[t+1]): the segments (contributions to one determinant) hold a handful of entries on
+// average, so one thread per segment in entry order -- deterministic, and 50x faster here than cub's block-per-segment
+// DeviceSegmentedReduce (profiles/r01_launches_pt2_summary.txt)
+__global__ void segment_sum_kernel(const double *v, const int32_t *off, int64_t nseg, double *out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nseg) return;
+  double acc = 0.0;
+  for (int32_t k = off[t]; k < off[t + 1]; k++) acc += v[k];
+  out[t] = acc;
+}
 // sort (a,b,v) by label and sum the values of equal determinants -> (ra, rb, rv), mout distinct determinants
 template <int NW>
 static int reduce_by_det(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, DevBuf<double> &v, int64_t m, DevBuf<uint64_t> &ra, DevBuf<uint64_t> &rb,
@@ -667,12 +677,8 @@ static int reduce_by_det(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, Dev
   set_i32_kernel<<<1, 1, 0, s>>>(sel.p + mout, (int32_t)m);  // closing offset of the last segment
   SQ_LAUNCH_CHECK();
   SQ_CHECK(rv.alloc(mout));
-  size_t tb2 = 0;
-  cub::DeviceSegmentedReduce::Sum(nullptr, tb2, sv.p, rv.p, (int)mout, sel.p, sel.p + 1, s);
-  DevBuf<char> tmp2;
-  SQ_CHECK(tmp2.alloc((int64_t)tb2 + 16));
-  SQ_CUDA(cub::DeviceSegmentedReduce::Sum(tmp2.p, tb2, sv.p, rv.p, (int)mout, sel.p, sel.p + 1, s));
-  g_launch_count += 1;
+  segment_sum_kernel<<<(unsigned)div_up(mout, 256), 256, 0, s>>>(sv.p, sel.p, mout, rv.p);
+  SQ_LAUNCH_CHECK();
   SQ_CHECK(ra.alloc(mout * NW));
   SQ_CHECK(rb.alloc(mout * NW));
   SQ_CHECK(gather_strings(NW, sa.p, sel.p, ra.p, mout, s));
