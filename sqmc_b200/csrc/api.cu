@@ -326,7 +326,30 @@ int sqmc_b200_matvec(sqmc_b200_handle *h, const double *x, double *y, int nvec, 
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
   if (ldx < h->n) { set_error("matvec: ldx < n"); return 2; }
-  for (int v = 0; v < nvec; v++) {
+  int v = 0;
+  // pairs of vectors share one pass over the matrix when it is in row-bundle order (two-vector kernel, csrc/bundle.cu)
+  if (h->bundle_R && nvec >= 2) {
+    cudaStream_t s = G.stream;
+    const int64_t n = h->n, nloc = h->row1 - h->row0;
+    DevBuf<double> xa, xb, ya, yb;
+    SQ_CHECK(xa.alloc(std::max<int64_t>(nloc, 1)));
+    SQ_CHECK(xb.alloc(std::max<int64_t>(nloc, 1)));
+    SQ_CHECK(ya.alloc(std::max<int64_t>(nloc, 1)));
+    SQ_CHECK(yb.alloc(std::max<int64_t>(nloc, 1)));
+    for (; v + 1 < nvec; v += 2) {
+      SQ_CHECK(upload_vector(h, x + (size_t)v * ldx));   // caller order -> internal order in d_x
+      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(xa.p, h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(upload_vector(h, x + (size_t)(v + 1) * ldx));
+      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(xb.p, h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(spmv_pair(h, xa.p, xb.p, ya.p, yb.p, s));
+      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_y, ya.p, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(download_result(h, y + (size_t)v * ldx));
+      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_y, yb.p, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(download_result(h, y + (size_t)(v + 1) * ldx));
+    }
+    (void)n;
+  }
+  for (; v < nvec; v++) {
     SQ_CHECK(upload_vector(h, x + (size_t)v * ldx));
     SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, G.stream));
     SQ_CHECK(download_result(h, y + (size_t)v * ldx));
