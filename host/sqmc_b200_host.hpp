@@ -155,6 +155,19 @@ inline void matrix_lanczos_sparse(model_system &S, std::vector<rk> &lowest_eigen
   if (highest_eigenvalue) *highest_eigenvalue = eig3[1];
   if (second_lowest_eigenvalue) *second_lowest_eigenvalue = eig3[2];
 }
+// davidson_sparse_single(n, lowest_eigenvector, lowest_eigenvalue, matrix_indices, nelem_nonzero, matrix_values,
+//                        highest_eigenvalue, initial_vector)   (more_tools.f90:3055)
+inline void davidson_sparse_single(model_system &S, std::vector<rk> &lowest_eigenvector, rk &lowest_eigenvalue, rk *highest_eigenvalue = nullptr,
+                                   const std::vector<rk> *initial_vector = nullptr) {
+  int64_t n = 0, nu = 0, nf = 0;
+  check(sqmc_b200_nnz(S.h, &n, &nu, &nf));
+  lowest_eigenvector.assign((size_t)n, 0.0);
+  rk eig2[2] = {0, 0};
+  int nit = 0, nlog = 0;
+  check(sqmc_b200_davidson_single(S.h, initial_vector ? initial_vector->data() : nullptr, lowest_eigenvector.data(), eig2, 1.0e-10, 50, &nit, nullptr, 0, &nlog));
+  lowest_eigenvalue = eig2[0];
+  if (highest_eigenvalue) *highest_eigenvalue = eig2[1];
+}
 // second_order_pt(ndets, dets_up, dets_dn, wts, diag_elems, var_energy, eps_pt, delta_e_2pt, ndets_connected)   (hci.f90:1100)
 // diag_elems is not needed (H_aa is evaluated on the device); determinants as 16-byte integers like the reference's integer(ik)
 inline void second_order_pt(model_system &S, int64_t ndets, const void *dets_up, const void *dets_dn, const std::vector<rk> &wts, rk var_energy,

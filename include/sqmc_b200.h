@@ -148,6 +148,13 @@ int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle);
 int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
 
+/* Replaces davidson_sparse_single (more_tools.f90:3055-3233; call sites chemistry.f90:6286,6290): one state, <= max_iter (50)
+ * vectors, no restart, the zero-denominator guard on the first element only (:3143).  v0: n-vector or NULL (unit vector
+ * on the first row).  eig2: lowest eigenvalue, and max(largest diagonal element, largest Ritz value) (the optional
+ * highest_eigenvalue of the reference).  ritz_log: the printed "Iteration, Eigenvalue=" values. */
+int sqmc_b200_davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter,
+                              int *n_iter_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+
 /* ---- Lanczos -------------------------------------------------------------------
  * Replaces matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver of the
  * k-space Hubbard path: <= min(n, max_iter = 50) vectors, full Gram-Schmidt pass per

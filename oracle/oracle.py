@@ -59,6 +59,8 @@ def lib():
         L.orc_davidson.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]
         L.orc_lanczos.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32]
         L.orc_lanczos.restype = i32
+        L.orc_davidson_single.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.orc_davidson_single.restype = i32
         L.orc_pt2.argtypes = [vp, i64, vp, vp, vp, C.c_double, C.c_double, vp]
         L.orc_pt2.restype = C.c_double
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
@@ -278,6 +280,23 @@ def davidson(counts, idx, val, n_states=1, v0=None):
         v0p = _p(v0)
     nl = lib().orc_davidson(n, n_states, _p(idx), _p(counts), _p(val), v0p, _p(evecs), _p(evals), _p(ritz), len(ritz), C.addressof(nmv))
     return dict(evals=evals, evecs=evecs.reshape(n_states, n).T, ritz=ritz[:min(nl, len(ritz))].reshape(-1, n_states), n_matvec=nmv.value)
+
+
+def davidson_single(counts, idx, val, v0=None):
+    """davidson_sparse_single (more_tools.f90:3055-3233) -> dict(lowest, highest, evec, ritz (printed values), n_iter)"""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(counts)
+    evec = np.zeros(n)
+    out3 = np.zeros(3)
+    ritz = np.zeros(64)
+    v0p = None
+    if v0 is not None:
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        v0p = _p(v0)
+    nit = lib().orc_davidson_single(n, _p(idx), _p(counts), _p(val), v0p, _p(evec), _p(out3), _p(ritz), len(ritz))
+    return dict(lowest=out3[0], highest=out3[1], evec=evec, n_iter=nit, ritz=ritz[:min(int(out3[2]), 64)].copy())
 
 
 def lanczos(counts, idx, val, v0=None):

@@ -1381,6 +1381,83 @@ int orc_davidson(long long n, int n_states, const i8b *indices, const i8b *count
   for (int i = 0; i < m; i++) ritz[i] = log[i];
   return (int)log.size();
 }
+// davidson_sparse_single (more_tools.f90:3055-3233): one state, <= min(n,50) vectors, no restart; the zero-denominator guard
+// acts on the FIRST element only (:3143-3144); also returns max(largest diagonal element, largest Ritz value) (:3109-3114,3181).
+// out2 = {lowest, highest, number of logged values}; ritz = the printed "Iteration, Eigenvalue=" values; returns the step count.
+int orc_davidson_single(long long n, const i8b *indices, const i8b *counts, const double *values, const double *v0, double *evec, double *out3,
+                        double *ritz, int ritz_cap) {
+  const double epsilon = 1.e-10;
+  if (n <= 1) { out3[0] = out3[1] = values[0]; out3[2] = 0; evec[0] = 0.0; return 0; }  // w is never set for n = 1 (:3215-3221)
+  const int iterations = (int)std::min<long long>(n, 50);
+  std::vector<std::vector<double>> v(iterations, std::vector<double>(n, 0.0)), Hv(iterations, std::vector<double>(n, 0.0));
+  std::vector<double> w(n), Hw(n), diag(n), hk((size_t)iterations * iterations, 0.0), evals, evecs;
+  auto dot = [&](const std::vector<double> &a, const std::vector<double> &b) {
+    double t = 0.0;
+    for (long long i = 0; i < n; i++) t += a[i] * b[i];
+    return t;
+  };
+  if (v0) {
+    double t = 0.0;
+    for (long long i = 0; i < n; i++) t += v0[i] * v0[i];
+    const double norm = 1.0 / std::sqrt(t);
+    for (long long i = 0; i < n; i++) v[0][i] = norm * v0[i];
+  } else {
+    v[0][0] = 1.0;
+  }
+  i8b ind = 0;
+  diag[0] = values[0];
+  double highest = diag[0];
+  for (long long i = 1; i < n; i++) { ind += counts[i - 1]; diag[i] = values[ind]; highest = std::max(highest, diag[i]); }
+  matvec_upper(n, indices, counts, values, v[0].data(), Hv[0].data());
+  double lowest = dot(v[0], Hv[0]), prev = lowest;
+  int nlog = 0;
+  if (nlog < ritz_cap) ritz[nlog] = lowest;
+  nlog++;
+  w = v[0]; Hw = Hv[0];
+  hk[0] = lowest;
+  bool converged = false;
+  int it = 2;
+  for (; it <= iterations; it++) {
+    std::vector<double> &vi = v[it - 1];
+    for (long long j = 0; j < n; j++) vi[j] = (Hw[j] - lowest * w[j]) / (lowest - diag[j]);
+    if (std::fabs(lowest - diag[0]) < 1e-8) vi[0] = -1.0;
+    double norm = dot(vi, vi);
+    if (norm < 1.e-12) converged = true;
+    for (int k = 0; k < it - 1; k++) {
+      const double c = dot(vi, v[k]);
+      for (long long j = 0; j < n; j++) vi[j] = vi[j] - c * v[k][j];
+    }
+    norm = dot(vi, vi);
+    const double ninv = 1.0 / std::sqrt(norm);
+    for (long long j = 0; j < n; j++) vi[j] = vi[j] * ninv;
+    matvec_upper(n, indices, counts, values, vi.data(), Hv[it - 1].data());
+    for (int k = 0; k < it; k++) {
+      const double e = dot(v[k], Hv[it - 1]);
+      hk[(size_t)(it - 1) * iterations + k] = e;
+      hk[(size_t)k * iterations + (it - 1)] = e;
+    }
+    std::vector<double> sub((size_t)it * it);
+    for (int a = 0; a < it; a++) for (int b = 0; b < it; b++) sub[(size_t)b * it + a] = hk[(size_t)b * iterations + a];
+    jacobi_eigh(it, sub, evals, evecs);
+    lowest = evals[0];
+    for (long long j = 0; j < n; j++) {
+      double t = 0.0, u = 0.0;
+      for (int k = 0; k < it; k++) { t += v[k][j] * evecs[k]; u += Hv[k][j] * evecs[k]; }
+      w[j] = t; Hw[j] = u;
+    }
+    highest = std::max(highest, evals[it - 1]);
+    if (std::fabs(lowest - prev) < epsilon) { converged = true; break; }
+    prev = lowest;
+    if (nlog < ritz_cap) ritz[nlog] = lowest;
+    nlog++;
+    if (converged) break;
+  }
+  it = std::min(it, iterations);
+  for (long long j = 0; j < n; j++) evec[j] = w[j];
+  out3[0] = lowest; out3[1] = highest; out3[2] = (double)nlog;
+  return it;
+}
+
 // matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver of the k-space Hubbard path: <= min(n,50) Lanczos
 // vectors, one Gram-Schmidt pass against all previous vectors per step (:1820-1826), the tridiagonal matrix diagonalised
 // every step (dsyev there, Jacobi here), stop when |E - E_prev| < 1e-10 (:1847) or the new vector vanishes (:1816).

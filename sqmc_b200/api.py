@@ -252,3 +252,21 @@ class SparseHamiltonian:
         de, nc = C.c_double(), C.c_int64()
         check(self._L.sqmc_b200_pt2(self._h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), C.byref(de), C.byref(nc)))
         return de.value, nc.value
+
+    def davidson_sparse_single(self, initial_vector=None, tol=1.0e-10, max_iter=50):
+        """davidson_sparse_single (more_tools.f90:3055-3233) on the resident matrix ->
+        dict(lowest_eigenvalue, highest_eigenvalue, lowest_eigenvector, ritz, n_iter)."""
+        n = self.n
+        evec = np.zeros(n)
+        eig2 = np.zeros(2)
+        ritz = np.zeros(max_iter + 2)
+        nit, nlog = C.c_int(), C.c_int()
+        v0p = None
+        if initial_vector is not None:
+            v0 = np.ascontiguousarray(initial_vector, dtype=np.float64).reshape(-1)
+            if len(v0) != n:
+                raise ValueError("initial_vector must have n entries")
+            v0p = _p(v0)
+        check(self._L.sqmc_b200_davidson_single(self._h, v0p, _p(evec), _p(eig2), float(tol), int(max_iter), C.byref(nit), _p(ritz), len(ritz),
+                                                C.byref(nlog)))
+        return dict(lowest_eigenvalue=eig2[0], highest_eigenvalue=eig2[1], lowest_eigenvector=evec, ritz=ritz[:nlog.value].copy(), n_iter=nit.value)

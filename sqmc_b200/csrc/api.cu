@@ -384,6 +384,14 @@ int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const voi
   return pt2(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_e, n_connected);
 }
 
+int sqmc_b200_davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter, int *n_iter_out,
+                              double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("davidson_single: null handle"); return 2; }
+  if (max_iter < 1) { set_error("davidson_single: max_iter must be positive"); return 2; }
+  return davidson_single(h, v0, evec, eig2, tol, max_iter, n_iter_out, ritz_log, ritz_log_cap, n_ritz_logged);
+}
+
 int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out,
                       double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());

@@ -434,6 +434,154 @@ __global__ void scale_copy_kernel(double *dst, const double *src, double c, int6
   if (j < n) dst[j] = src[j] * c;
 }
 
+// v = (Hw - E w) / (E - diag) with the zero-denominator guard on ONE element only (davidson_sparse_single, :3140-3144)
+__global__ void resid_precond_single_kernel(const double *Hw, const double *w, const double *diag, double E, double *v, int64_t n, int64_t guard) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double r = (Hw[j] - E * w[j]) / (E - diag[j]);
+  if (j == guard && fabs(E - diag[j]) < 1e-8) r = -1.0;
+  v[j] = r;
+}
+
+// ------------------------------------------------------------------ single-state Davidson
+// Statement-by-statement device version of davidson_sparse_single (more_tools.f90:3055-3233; called from
+// chemistry.f90:6286-6290): one state, <= min(n, max_iter = 50) vectors, no restart, the preconditioner guard on the first
+// (caller) element only, Ritz vector rebuilt from the whole basis every step, stop at |dE| < tol (1e-10).
+// eig2 = {lowest eigenvalue, max(largest diagonal element, largest Ritz value)}.
+int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter, int *n_iter_out, double *ritz_log,
+                    int ritz_log_cap, int *n_ritz_logged) {
+  if (!h->d_rowptr) { set_error("davidson_single: no matrix on this handle"); return 2; }
+  const int64_t n = h->n;
+  if (n_ritz_logged) *n_ritz_logged = 0;
+  if (n_iter_out) *n_iter_out = 0;
+  if (n == 1) {  // :3215-3218
+    double d = 0;
+    SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
+    eig2[0] = eig2[1] = d;
+    evec[0] = 0.0;   // the reference returns its unset work vector here
+    return 0;
+  }
+  Dav D;
+  D.h = h;
+  D.s = G.stream;
+  D.n = n;
+  D.nloc = h->row1 - h->row0;
+  D.ld = std::max<int64_t>(D.nloc, 1);
+  const int64_t nloc = D.nloc, ld = D.ld;
+  cudaStream_t s = D.s;
+  const int iterations = (int)std::min<int64_t>(n, max_iter);
+  SQ_CHECK(devbuf_alloc((void **)&D.V, (size_t)ld * iterations * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.HV, (size_t)ld * iterations * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.W, (size_t)ld * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.HW, (size_t)ld * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.diag, (size_t)ld * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.partial, (size_t)kDotBlocks * (iterations + 2) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * iterations * sizeof(double), s));
+  auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
+  auto HVc = [&](int c) { return D.HV + (int64_t)c * ld; };
+  SQ_CHECK(extract_diag(h, D.diag, s));
+  // largest diagonal element (:3109-3114) and the internal position of the first caller row (the guarded element)
+  double highest = -1e300;
+  int32_t first_internal = 0;
+  {
+    std::vector<double> hd(std::max<int64_t>(nloc, 1));
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(hd.data(), D.diag, nloc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaMemcpyAsync(&first_internal, h->d_iperm, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    for (int64_t j = 0; j < nloc; j++) highest = std::max(highest, hd[j]);
+    if (G.nranks > 1) {
+      SQ_CUDA(cudaMemcpyAsync(D.scal, &highest, sizeof(double), cudaMemcpyHostToDevice, s));
+      ncclResult_t r = ncclAllReduce(D.scal, D.scal, 1, ncclDouble, ncclMax, G.comm, s);
+      if (r != ncclSuccess) { set_error("davidson_single: ncclAllReduce failed: %s", ncclGetErrorString(r)); return 3; }
+      SQ_CHECK(D.fetch(D.scal, 1, &highest));
+    }
+  }
+  const int64_t guard = (first_internal >= h->row0 && first_internal < h->row1) ? first_internal - h->row0 : -1;
+  // initial vector (:3099-3105)
+  {
+    std::vector<double> e;
+    const double *src = v0;
+    if (!v0) { e.assign(n, 0.0); e[0] = 1.0; src = e.data(); }
+    SQ_CUDA(cudaMemcpyAsync(h->d_tmp, src, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    SQ_CHECK(permute_gather(h->d_tmp, h->d_perm, h->d_x, n, s));
+    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(Vc(0), h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    if (v0) {
+      SQ_CHECK(D.dots(Vc(0), 1, Vc(0), D.scal));
+      SQ_CHECK(D.normalize(Vc(0), D.scal));
+    }
+  }
+  std::vector<double> hk((size_t)iterations * iterations, 0.0), col(iterations + 8), evals, evecs;
+  SQ_CHECK(D.apply_h(Vc(0), HVc(0)));
+  SQ_CHECK(D.dots(Vc(0), 1, HVc(0), D.scal));
+  double lowest = 0, prev = 0;
+  SQ_CHECK(D.fetch(D.scal, 1, &lowest));
+  prev = lowest;
+  int nlogged = 0;
+  if (ritz_log && nlogged < ritz_log_cap) ritz_log[nlogged] = lowest;
+  nlogged++;
+  if (nloc > 0) {
+    SQ_CUDA(cudaMemcpyAsync(D.W, Vc(0), nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaMemcpyAsync(D.HW, HVc(0), nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  hk[0] = lowest;
+  bool converged = false;
+  int it = 2;
+  for (; it <= iterations; it++) {
+    const int c = it - 1;
+    if (nloc > 0) {
+      resid_precond_single_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.HW, D.W, D.diag, lowest, Vc(c), nloc, guard);
+      SQ_LAUNCH_CHECK();
+    }
+    SQ_CHECK(D.dots(Vc(c), 1, Vc(c), D.scal + iterations + 1));
+    for (int k = 0; k < c; k++) {  // Gram-Schmidt, each coefficient from the partly orthogonalised vector (:3150-3153)
+      SQ_CHECK(D.dots(Vc(c), 1, Vc(k), D.scal + iterations + 2));
+      SQ_CHECK(D.axpy_neg(Vc(c), Vc(k), D.scal + iterations + 2));
+    }
+    SQ_CHECK(D.dots(Vc(c), 1, Vc(c), D.scal + iterations + 2));
+    SQ_CHECK(D.normalize(Vc(c), D.scal + iterations + 2));
+    SQ_CHECK(D.apply_h(Vc(c), HVc(c)));
+    SQ_CHECK(D.dots(D.V, it, HVc(c), D.scal));
+    SQ_CUDA(cudaMemcpyAsync(D.scal + it, D.scal + iterations + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SQ_CHECK(D.fetch(D.scal, it + 1, col.data()));
+    if (col[it] < 1.e-12) converged = true;  // norm of the new direction before orthogonalisation (:3147-3148)
+    for (int k = 0; k < it; k++) { hk[(size_t)c * iterations + k] = col[k]; hk[(size_t)k * iterations + c] = col[k]; }
+    std::vector<double> sub((size_t)it * it);
+    for (int a = 0; a < it; a++)
+      for (int b = 0; b < it; b++) sub[(size_t)b * it + a] = hk[(size_t)b * iterations + a];
+    jacobi_eigh(it, sub, evals, evecs);
+    lowest = evals[0];
+    SQ_CUDA(cudaMemcpyAsync(D.coef, evecs.data(), it * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nloc > 0) {
+      combine_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.V, ld, it, D.coef, 1, D.W, nloc);
+      SQ_LAUNCH_CHECK();
+      combine_kernel<<<D.blocks(nloc), 256, 0, s>>>(D.HV, ld, it, D.coef, 1, D.HW, nloc);
+      SQ_LAUNCH_CHECK();
+    }
+    SQ_CUDA(cudaStreamSynchronize(s));  // evecs is reused next step
+    highest = std::max(highest, evals[it - 1]);
+    if (fabs(lowest - prev) < tol) { converged = true; break; }
+    prev = lowest;
+    if (ritz_log && nlogged < ritz_log_cap) ritz_log[nlogged] = lowest;
+    nlogged++;
+    if (converged) break;
+  }
+  it = std::min(it, iterations);
+  if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, D.W, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  SQ_CHECK(allgather_rows(h, h->d_x, s));
+  SQ_CHECK(permute_scatter(h->d_x, h->d_perm, h->d_tmp, n, s));
+  SQ_CUDA(cudaMemcpyAsync(evec, h->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  eig2[0] = lowest;
+  eig2[1] = highest;
+  if (n_iter_out) *n_iter_out = it;
+  if (n_ritz_logged) *n_ritz_logged = std::min(nlogged, ritz_log_cap);
+  return 0;
+}
+
 // ------------------------------------------------------------------ Lanczos
 // Statement-by-statement device version of matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver the k-space
 // Hubbard path uses: <= min(n, max_iter = 50) vectors, w = H v - beta v_prev - alpha v, one Gram-Schmidt pass of the new

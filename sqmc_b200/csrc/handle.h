@@ -233,6 +233,8 @@ int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_
 // davidson.cu
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
              int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter, int *n_iter_out, double *ritz_log,
+                    int ritz_log_cap, int *n_ritz_logged);
 int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out, double *ritz_log,
             int ritz_log_cap, int *n_ritz_logged);
 }  // namespace sqmc

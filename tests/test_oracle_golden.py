@@ -113,3 +113,18 @@ def test_heg_pt_reproduces_reference_log(oracle):
     assert nconn == gold["ndets_connected"]
     assert abs(de - gold["pt_correction"]) < 5e-10                  # printed with 9 decimals
     assert abs(r["energy"][0] + de - gold["total_energy"]) < 1e-9
+
+
+def test_davidson_single_against_dense(oracle, heg_space):
+    """davidson_sparse_single restatement (more_tools.f90:3055-3233) on the 277-determinant matrix of the reference log:
+    its printed eigenvalues coincide with davidson_sparse's golden ones (the solvers differ only in guard and restart)"""
+    gold = json.load(open(os.path.join(HERE, "golden", "heg_o_det_ref.json")))
+    s, r = heg_space
+    up, dn = r["up"][:277], r["dn"][:277]
+    cnt, idx, val = s.build_upper(up, dn)
+    A = oracle.upper_to_scipy(cnt, idx, val).toarray()
+    w = np.linalg.eigvalsh(A)
+    L = oracle.davidson_single(cnt, idx, val)
+    assert abs(L["lowest"] - w[0]) < 1e-9
+    assert np.max(np.abs(L["ritz"] - np.array(gold["ritz"][0][:len(L["ritz"])]))) < 5e-9      # o_det_ref, first HCI iteration
+    assert abs(L["highest"] - max(A.diagonal().max(), L["highest"])) == 0 and L["highest"] <= w[-1] + 1e-9
