@@ -110,3 +110,62 @@ def test_c2_hci_fixture_is_reproducible(oracle, c2_space_ts):
     assert r["ndet"].tolist() == gold["n_det"][:3]
     assert r["nnz"].tolist() == gold["nnz"][:3]
     assert np.max(np.abs(r["iter_energy"][:, 0] - np.array(gold["iter_energy"])[:3, 0])) < 1e-9
+
+
+@pytest.mark.parametrize("time_sym", [False, True])
+def test_pt2_numerators_equal_full_matrix_elements(oracle, time_sym):
+    """Independent check of the second-order PT restatement (parity of C2 PT is unpinned by the reference): with eps_pt -> 0
+    the screened sum must equal the textbook Epstein-Nesbet sum over ALL singles and doubles of the variational
+    determinants, with numerators built from the full (for time_sym: symmetrised) matrix elements -- i.e. the
+    contribution-by-contribution bookkeeping of find_important_connected_dets_chem (norm factors, z, merging of a
+    determinant with its time-reversed partner) adds up to <a|H|psi>."""
+    S = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=time_sym, z=1, hf_symmetry=1)
+    r = S.hci(5e-2, n_states=1, max_iters=1)
+    up, dn, w, e = r["up"], r["dn"], r["wts"][:, 0], r["energy"][0]
+    n = len(up)
+    assert 10 < n < 200
+    de, nconn = S.pt2(up, dn, w, e, 1e-13)
+    V = {(int(u[0]), int(d[0])) for u, d in zip(up, dn)}
+    norb = 26
+
+    def excitations(u, d):
+        occu = [o for o in range(norb) if u >> o & 1]; viru = [o for o in range(norb) if not u >> o & 1]
+        occd = [o for o in range(norb) if d >> o & 1]; vird = [o for o in range(norb) if not d >> o & 1]
+        out = set()
+        for p in occu:
+            for q in viru:
+                out.add((u ^ (1 << p) | (1 << q), d))
+        for p in occd:
+            for q in vird:
+                out.add((u, d ^ (1 << p) | (1 << q)))
+        for p, q in itertools.combinations(occu, 2):
+            for a, b in itertools.combinations(viru, 2):
+                out.add((u ^ (1 << p) ^ (1 << q) | (1 << a) | (1 << b), d))
+        for p, q in itertools.combinations(occd, 2):
+            for a, b in itertools.combinations(vird, 2):
+                out.add((u, d ^ (1 << p) ^ (1 << q) | (1 << a) | (1 << b)))
+        for p in occu:
+            for a in viru:
+                nu = u ^ (1 << p) | (1 << a)
+                for q in occd:
+                    for b in vird:
+                        out.add((nu, d ^ (1 << q) | (1 << b)))
+        return out
+
+    ext = set()
+    for u, d in V:
+        for a, b in excitations(u, d):
+            if time_sym and a > b:
+                a, b = b, a
+            if (a, b) not in V:
+                ext.add((a, b))
+    ext = sorted(ext)
+    m = len(ext)
+    au = oracle.dets_to_u64([a for a, b in ext])
+    ad = oracle.dets_to_u64([b for a, b in ext])
+    num = np.zeros(m)
+    for i in range(n):
+        num += S.elements(au, ad, np.repeat(up[i:i + 1], m, axis=0), np.repeat(dn[i:i + 1], m, axis=0)) * w[i]
+    haa = S.elements(au, ad, au, ad)
+    ref = float(np.sum(num ** 2 / (e - haa)))
+    assert abs(de - ref) < 1e-12 and de < -1e-2
