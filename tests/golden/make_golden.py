@@ -76,6 +76,14 @@ def heg_from_reference_log():
                 coefs.append({"up": int(t[1]), "dn": int(t[2]), "coef": float(t[3])})
             break
     out["final_coefficients"] = coefs
+    # second golden log of the same system: src/e2e_tests/heg/o_st_ref (semistochastic PT; its deterministic first stage)
+    st = "/root/reference/src/e2e_tests/heg/o_st_ref"
+    if os.path.exists(st):
+        for i, ln in enumerate(open(st).read().splitlines()):
+            m = re.search(r"PT_correction, eps_pt_big, ndets_connected for short deterministic run=\s*(\S+)\s+(\S+)\s+(\d+)", ln)
+            if m:
+                out["pt_big"] = {"source": "src/e2e_tests/heg/o_st_ref", "pt_correction": float(m.group(1)), "eps_pt_big": float(m.group(2)),
+                                 "ndets_connected": int(m.group(3)), "line": i + 1}
     json.dump(out, open(os.path.join(HERE, "heg_o_det_ref.json"), "w"), indent=1)
     print("wrote heg_o_det_ref.json:", out["n_det"], out["nnz"])
 

@@ -25,6 +25,9 @@ def test_heg_pt_reproduces_reference_log(oracle):
     assert abs(r["energy"][0] + de - 58.275966889) < 1e-9
     ode, onc = S.pt2(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 2e-7)
     assert onc == nconn and abs(ode - de) < 1e-12
+    # second golden threshold: the deterministic stage of the semistochastic-PT test (src/e2e_tests/heg/o_st_ref:432)
+    de2, nconn2 = H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 8.192e-4)
+    assert nconn2 == 13159 and abs(de2 - (-0.000199339)) < 5e-10
 
 
 def test_heg_pt_fully_on_gpu():

@@ -113,6 +113,10 @@ def test_heg_pt_reproduces_reference_log(oracle):
     assert nconn == gold["ndets_connected"]
     assert abs(de - gold["pt_correction"]) < 5e-10                  # printed with 9 decimals
     assert abs(r["energy"][0] + de - gold["total_energy"]) < 1e-9
+    # the semistochastic-PT test of the same system pins the deterministic stage at a second threshold (o_st_ref:432)
+    big = json.load(open(os.path.join(HERE, "golden", "heg_o_det_ref.json")))["pt_big"]
+    de2, nconn2 = S.pt2(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], big["eps_pt_big"])
+    assert nconn2 == big["ndets_connected"] == 13159 and abs(de2 - big["pt_correction"]) < 5e-10
 
 
 def test_davidson_single_against_dense(oracle, heg_space):
