@@ -74,3 +74,15 @@ def test_pt_rejects_bad_arguments(c2_space):
     H = sq.SparseHamiltonian(sq.ChemSystem(C2_FCIDUMP))
     with pytest.raises(Exception, match="eps_pt"):
         H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 0.0)
+
+
+def test_heg_two_word_strings_pt(oracle):
+    """81 plane-wave orbitals: determinant strings span both 64-bit words (NW = 2 instantiation of the PT pipeline)"""
+    import sqmc_b200 as sq
+    S = oracle.System.heg(3, 0.5, 14, 7, 2.5)
+    r = S.hci(2e-3, n_states=1, max_iters=1)
+    H = sq.SparseHamiltonian(sq.HegSystem(3, 0.5, 14, 7, 2.5))
+    de, nconn = H.second_order_pt(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 2e-5)
+    ode, onc = S.pt2(r["up"], r["dn"], r["wts"][:, 0], r["energy"][0], 2e-5)
+    assert nconn == onc and onc > len(r["up"])
+    assert abs(de - ode) < 1e-12 and de < 0
