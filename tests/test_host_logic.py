@@ -125,3 +125,62 @@ def test_reference_input_files_are_parsed():
     assert heg["cutoff_radius"] == 1.49 and (heg["eps_var"], heg["eps_pt"], heg["n_states"]) == (1e-3, 2e-7, 1)
     s = hci.eps_schedule(1e-3, [2e-3, 2e-3])
     assert len(s) == 30 and s[0] == s[1] == 2e-3 and s[2] == s[29] == 1e-3
+
+
+class _OracleBackedHamiltonian:
+    """Duck-typed stand-in for SparseHamiltonian whose heavy steps are the CPU oracle: lets the host-side driver loop
+    (sqmc_b200.hci.perform_hci) be checked without a GPU.  Test infrastructure only."""
+
+    def __init__(self, S, O):
+        self.S, self.O = S, O
+        self.mat = None
+
+    def diagonal(self, up, dn):
+        return self.S.elements(up, dn, up, dn)
+
+    def get_next_det_list(self, up, dn, coeffs, min_h, eps):
+        return self.S.select(up, dn, coeffs, min_h, eps)
+
+    def generate_sparse_ham_upper_triangular(self, up, dn, ndet_old=0):
+        self.mat = self.S.build_upper(up, dn)
+        return len(self.mat[1])
+
+    def davidson_sparse(self, n_states=1, initial_vector=None):
+        return self.O.davidson(*self.mat, n_states=n_states, v0=initial_vector)
+
+    def second_order_pt(self, up, dn, wts, e, eps_pt):
+        return self.S.pt2(up, dn, wts, e, eps_pt)
+
+
+def test_perform_hci_driver_loop_reproduces_reference_log(oracle):
+    """the Python mirror of perform_hci (schedule, selection coefficients, stopping rules, PT call) driven by the oracle:
+    the reference's HEG end-to-end input must give its golden log (o_det_ref:261-437)"""
+    import json
+    import types
+    from sqmc_b200 import hci
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "heg_o_det_ref.json")))
+    cfg = hci.read_input(os.path.join(ROOT, "tests", "golden", "heg_i_det"))
+    S = oracle.System.heg(cfg["n_dim"], cfg["r_s"], cfg["nelec"], cfg["nup"], cfg["cutoff_radius"])
+    system = types.SimpleNamespace(hf_up=(1 << cfg["nup"]) - 1, hf_dn=(1 << (cfg["nelec"] - cfg["nup"])) - 1, time_sym=False)
+    res = hci.perform_hci(_OracleBackedHamiltonian(S, oracle), system, cfg["eps_var"], cfg["eps_var_sched"], n_states=cfg["n_states"],
+                          eps_pt=cfg["eps_pt"])
+    assert [it["n_det"] for it in res["iterations"]][:2] == gold["n_det"] and [it["nnz"] for it in res["iterations"]][:2] == gold["nnz"]
+    assert len(res["up"]) == gold["pt"]["ndets"] and abs(res["energy"][0] - gold["pt"]["variational_energy"]) < 5e-9
+    de, nconn = res["pt"][0]
+    assert nconn == gold["pt"]["ndets_connected"] and abs(res["energy"][0] + de - gold["pt"]["total_energy"]) < 1e-9
+
+
+def test_perform_hci_driver_loop_two_states_matches_oracle_loop(oracle):
+    """n_states = 2 with an eps_var schedule (the shipped C2 input): the Python loop and the oracle's own perform_hci
+    restatement must walk through the same determinant counts and energies"""
+    import json
+    import types
+    from conftest import C2_FCIDUMP, C2_ORBSYM
+    from sqmc_b200 import hci
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "c2_s1_hci.json")))["runs"]["n_states=2"]
+    S = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=True, z=1, hf_symmetry=1)
+    tab = S.chem_tables()   # the HF determinant in the reordered orbital numbering (chemistry.f90:694-805)
+    system = types.SimpleNamespace(hf_up=tab["hf_up"], hf_dn=tab["hf_dn"], time_sym=True)
+    res = hci.perform_hci(_OracleBackedHamiltonian(S, oracle), system, 1e-3, [2e-3, 2e-3], n_states=2)
+    assert [it["n_det"] for it in res["iterations"]] == gold["n_det"]
+    assert np.max(np.abs(np.array([it["energy"] for it in res["iterations"]]) - np.array(gold["iter_energy"]))) < 1e-8
