@@ -371,8 +371,14 @@ static int decode_t(sqmc_b200_handle *h, int cap, cudaStream_t s) {
 int bundle_encode(sqmc_b200_handle *h) { return bundle_encode_r(h, bundle_want()); }
 int bundle_encode_r(sqmc_b200_handle *h, int R) {
   const int64_t nloc = h->row1 - h->row0;
-  if (!R || h->bundle_R || h->wcsr || !h->d_rowptr || nloc == 0 || h->nnz_local == 0) return 0;
+  if (!R || h->bundle_R || h->wcsr || !h->d_rowptr) return 0;
   if (h->n >= (1ll << (31 - kBShift))) return 0;
+  if (nloc == 0 || h->nnz_local == 0) {
+    // a rank without rows still switches layout: every rank must take the same (collective) code path in the two-vector H.v
+    h->bundle_R = R;
+    h->bundle_cap = 1024;
+    return 0;
+  }
   cudaStream_t s = G.stream;
   if (!h->d_diag) {  // Davidson's preconditioner and the projector read the diagonal: keep a copy
     SQ_CUDA(cudaMalloc(&h->d_diag, nloc * sizeof(double)));
@@ -412,8 +418,10 @@ int bundle_decode(sqmc_b200_handle *h) {
   if (!h->bundle_R) return 0;
   cudaStream_t s = G.stream;
   const int R = h->bundle_R, cap = h->bundle_cap;
-  int rc = R == 2 ? decode_t<2>(h, cap, s) : R == 4 ? decode_t<4>(h, cap, s) : decode_t<8>(h, cap, s);
-  if (rc) return rc;
+  if (h->row1 - h->row0 > 0 && h->nnz_local > 0) {
+    int rc = R == 2 ? decode_t<2>(h, cap, s) : R == 4 ? decode_t<4>(h, cap, s) : decode_t<8>(h, cap, s);
+    if (rc) return rc;
+  }
   SQ_CUDA(cudaStreamSynchronize(s));
   h->bundle_R = 0;
   return 0;
