@@ -23,13 +23,33 @@ def eps_schedule(eps_var, eps_var_sched=()):
     return np.maximum(sched, eps_var)
 
 
-def perform_hci(H, system, eps_var, eps_var_sched=(), n_states=1, max_iters=50, eps_pt=None, log=None):
+def sort_by_label(up, dn, wts):
+    """the variational wavefunction sorted by (up, dn) as 128-bit integers: what the reference does before the checkpoint
+    dump and the PT (hci.f90:569-596, merge_sort2_up_dn)"""
+    order = np.lexsort((dn[:, 0], dn[:, 1], up[:, 0], up[:, 1]))
+    return up[order], dn[order], wts[order]
+
+
+def perform_hci(H, system, eps_var, eps_var_sched=(), n_states=1, max_iters=50, eps_pt=None, log=None, wf_dir=None, dump_wf_var=False):
     """-> dict(up, dn, wts (n, n_states), energy (n_states,), iterations=[{n_det, nnz, energy}], pt=[(delta_e, ndets_connected)]).
-    H: SparseHamiltonian of `system` (chem / heg).  log: optional callable receiving one line of text per event."""
+    H: SparseHamiltonian of `system` (chem / heg).  log: optional callable receiving one line of text per event.
+    wf_dir: directory of the `wf_eps_var=...` checkpoint: if the file of this eps_var exists the variational stage is
+    skipped and the wavefunction is read from it (hci.f90:194-231); with dump_wf_var it is written after the stage
+    (:601-625).  The returned wavefunction is sorted by label like the reference's."""
+    import os
+    from . import formats
     from .api import dets_to_u64
     say = log or (lambda *_: None)
     sched = eps_schedule(eps_var, eps_var_sched)
     eps_last = sched[29]
+    wf_path = os.path.join(wf_dir, formats.wf_filename(float(np.min(sched)))) if wf_dir else None
+    if wf_path and os.path.exists(wf_path):
+        say("Reading variational wavefn from %s" % wf_path)
+        ck = formats.read_wf(wf_path)
+        if ck["wts"].shape[1] != n_states:
+            raise ValueError("perform_hci: checkpoint holds %d states, run asks for %d" % (ck["wts"].shape[1], n_states))
+        out = dict(up=ck["up"], dn=ck["dn"], wts=ck["wts"], energy=np.array(ck["energies"]), iterations=[], pt=[], from_checkpoint=True)
+        return _pt_stage(H, out, n_states, eps_pt, say)
     hf_up, hf_dn = int(system.hf_up), int(system.hf_dn)
     if getattr(system, "time_sym", False) and hf_dn < hf_up:
         hf_up, hf_dn = hf_dn, hf_up
@@ -68,8 +88,17 @@ def perform_hci(H, system, eps_var, eps_var_sched=(), n_states=1, max_iters=50, 
         old_energy = energy.copy()
         if md < 1.0e-5 and eps == eps_last:
             break
-    out = dict(up=up, dn=dn, wts=wts, energy=energy, iterations=iterations, pt=[])
+    up, dn, wts = sort_by_label(up, dn, wts)
+    out = dict(up=up, dn=dn, wts=wts, energy=energy, iterations=iterations, pt=[], from_checkpoint=False)
+    if wf_path and dump_wf_var:
+        say("Writing variational wavefn to %s" % wf_path)
+        formats.write_wf(wf_path, up, dn, wts, energy)
+    return _pt_stage(H, out, n_states, eps_pt, say)
+
+
+def _pt_stage(H, out, n_states, eps_pt, say):
     if eps_pt is not None and eps_pt > 0:
+        up, dn, wts, energy = out["up"], out["dn"], out["wts"], out["energy"]
         for s in range(n_states):
             de, nconn = H.second_order_pt(up, dn, wts[:, s], energy[s], eps_pt)
             out["pt"].append((de, nconn))
@@ -141,8 +170,9 @@ def read_input(path):
     return cfg
 
 
-def run_input(path, fcidump=None, device=0, log=print):
-    """Run a reference `hci` input file on the GPU path: system set-up, variational loop, deterministic PT."""
+def run_input(path, fcidump=None, device=0, log=print, wf_dir=None):
+    """Run a reference `hci` input file on the GPU path: system set-up, variational loop, deterministic PT.
+    wf_dir: where the `wf_eps_var=...` checkpoint is looked for / dumped (the reference uses the working directory)."""
     import os
     from . import ChemSystem, HegSystem, SparseHamiltonian
     cfg = read_input(path)
@@ -153,6 +183,7 @@ def run_input(path, fcidump=None, device=0, log=print):
     else:
         system = HegSystem(cfg["n_dim"], cfg["r_s"], cfg["nelec"], cfg["nup"], cfg["cutoff_radius"])
     H = SparseHamiltonian(system, device=device)
-    res = perform_hci(H, system, cfg["eps_var"], cfg["eps_var_sched"], n_states=cfg["n_states"], eps_pt=cfg["eps_pt"], log=log)
+    res = perform_hci(H, system, cfg["eps_var"], cfg["eps_var_sched"], n_states=cfg["n_states"], eps_pt=cfg["eps_pt"], log=log,
+                      wf_dir=wf_dir, dump_wf_var=cfg["dump_wf_var"])
     res["config"] = cfg
     return res

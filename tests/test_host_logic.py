@@ -184,3 +184,28 @@ def test_perform_hci_driver_loop_two_states_matches_oracle_loop(oracle):
     res = hci.perform_hci(_OracleBackedHamiltonian(S, oracle), system, 1e-3, [2e-3, 2e-3], n_states=2)
     assert [it["n_det"] for it in res["iterations"]] == gold["n_det"]
     assert np.max(np.abs(np.array([it["energy"] for it in res["iterations"]]) - np.array(gold["iter_energy"]))) < 1e-8
+
+
+def test_perform_hci_checkpoint_dump_and_resume(oracle, tmp_path):
+    """dump_wf_var: the variational stage writes wf_eps_var=1.00E-3 (label-sorted, hci.f90:569-625); a second run finds it,
+    skips the stage (:194-231) and obtains the same PT correction"""
+    import json
+    import types
+    from sqmc_b200 import formats, hci
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "heg_o_det_ref.json")))
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    system = types.SimpleNamespace(hf_up=(1 << 7) - 1, hf_dn=(1 << 7) - 1, time_sym=False)
+    H = _OracleBackedHamiltonian(S, oracle)
+    first = hci.perform_hci(H, system, 1e-3, n_states=1, eps_pt=8.192e-4, wf_dir=str(tmp_path), dump_wf_var=True)
+    path = tmp_path / "wf_eps_var=1.00E-3"
+    assert path.exists() and not first["from_checkpoint"]
+    ck = formats.read_wf(path)
+    lab = [(int(u[1]) << 64 | int(u[0]), int(d[1]) << 64 | int(d[0])) for u, d in zip(ck["up"], ck["dn"])]
+    assert lab == sorted(lab) and len(lab) == 9475
+    calls = {"select": 0}
+    orig = H.get_next_det_list
+    H.get_next_det_list = lambda *a: (calls.__setitem__("select", calls["select"] + 1), orig(*a))[1]
+    second = hci.perform_hci(H, system, 1e-3, n_states=1, eps_pt=8.192e-4, wf_dir=str(tmp_path), dump_wf_var=True)
+    assert second["from_checkpoint"] and calls["select"] == 0 and second["iterations"] == []
+    assert second["pt"][0] == first["pt"][0]
+    assert second["pt"][0][1] == gold["pt_big"]["ndets_connected"] and abs(second["pt"][0][0] - gold["pt_big"]["pt_correction"]) < 5e-10
