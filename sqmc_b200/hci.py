@@ -104,6 +104,9 @@ def _pt_stage(H, out, n_states, eps_pt, say):
             out["pt"].append((de, nconn))
             say("state %d: ndets, ndets_connected, Variational, PT, Total Energies= %d %d %.9f %.9f %.9f"
                 % (s + 1, len(up), nconn, energy[s], de, energy[s] + de))
+            # the two lines the reference's own end-to-end checker greps (src/e2e_tests/e2e_check.py; hci.f90 log format)
+            say("Variational energy=%31.9f" % energy[s])
+            say("Second-order PT energy lowering=%18.9f" % de)
     return out
 
 

@@ -209,3 +209,23 @@ def test_perform_hci_checkpoint_dump_and_resume(oracle, tmp_path):
     assert second["from_checkpoint"] and calls["select"] == 0 and second["iterations"] == []
     assert second["pt"][0] == first["pt"][0]
     assert second["pt"][0][1] == gold["pt_big"]["ndets_connected"] and abs(second["pt"][0][0] - gold["pt_big"]["pt_correction"]) < 5e-10
+
+
+def test_driver_output_passes_the_reference_e2e_checker(oracle):
+    """src/e2e_tests/e2e_check.py greps 'Variational energy=' and 'Second-order PT energy lowering=' from a run's output and
+    compares them with o_det_ref (1 % tolerance): the same regular expressions applied to the driver's log"""
+    import json
+    import re
+    import types
+    from sqmc_b200 import hci
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "heg_o_det_ref.json")))["pt"]
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    system = types.SimpleNamespace(hf_up=(1 << 7) - 1, hf_dn=(1 << 7) - 1, time_sym=False)
+    lines = []
+    hci.perform_hci(_OracleBackedHamiltonian(S, oracle), system, 1e-3, n_states=1, eps_pt=2e-7, log=lines.append)
+    text = "\n".join(lines)
+    ev = float(re.search(r"Variational energy.*=\s*([-+]?[0-9]*\.?[0-9]+)", text).group(1))
+    pt = float(re.search(r"Second-order PT energy lowering.*=\s*([-+]?[0-9]*\.?[0-9]+)", text).group(1))
+    assert "Variational energy=                   58.276906085" in text          # o_det_ref:434, character for character
+    assert "Second-order PT energy lowering=      -0.000939196" in text          # o_det_ref:435
+    assert abs(ev - gold["variational_energy"]) < 1e-9 and abs(pt - gold["pt_correction"]) < 1e-9
