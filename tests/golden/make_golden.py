@@ -11,6 +11,10 @@
                        C2 r1.24253 time_sym=f: sizes, nnz, energies and a SHA-256 of the final determinant list.
   c2_small_space.npz   2000 lowest-energy A_g determinants of C2 + the oracle's upper-triangular H.
 
+  heg_i_det            INPUT DATA, not code: the reference's end-to-end test input src/e2e_tests/heg/i_det, kept verbatim
+                       (like the FCIDUMPs under data/) so that the run which must reproduce o_det_ref reads the very
+                       same file; refreshed by this script when the reference is present.
+
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import json
@@ -129,7 +133,16 @@ def c2_sched_from_oracle():
     print("wrote c2_hci_sched.json", out["n_det"], out["nnz"])
 
 
+def heg_input_file():
+    src = "/root/reference/src/e2e_tests/heg/i_det"
+    if os.path.exists(src):
+        import shutil
+        shutil.copyfile(src, os.path.join(HERE, "heg_i_det"))
+        print("copied heg_i_det")
+
+
 if __name__ == "__main__":
+    heg_input_file()
     heg_from_reference_log()
     c2_from_oracle()
     c2_sched_from_oracle()
