@@ -153,6 +153,12 @@ int sqmc_b200_finalize(void) {
   return 0;
 }
 
+// frees a partially constructed handle (and its device tables) when a system_* constructor fails half way
+struct HandleGuard {
+  sqmc_b200_handle *h;
+  ~HandleGuard() { if (h) sqmc_b200_free(h); }
+  sqmc_b200_handle *release() { sqmc_b200_handle *q = h; h = nullptr; return q; }
+};
 static sqmc_b200_handle *new_handle(int model, int norb, int nup, int ndn) {
   sqmc_b200_handle *h = new sqmc_b200_handle();
   memset(&h->T, 0, sizeof(h->T));
@@ -173,6 +179,7 @@ int sqmc_b200_system_chem(sqmc_b200_handle **out, int norb, int nup, int ndn, co
   if (time_sym && nup != ndn) { set_error("system_chem: time_sym needs nup == ndn (chemistry.f90:186)"); return 2; }
   if (time_sym && z != 1 && z != -1) { set_error("system_chem: z must be +1 or -1 (chemistry.f90:190)"); return 2; }
   sqmc_b200_handle *h = new_handle(MODEL_CHEM, norb, nup, ndn);
+  HandleGuard guard{h};
   int n1 = norb + 1;
   SQ_CUDA(cudaMalloc(&h->d_integrals, nint * sizeof(double)));
   SQ_CUDA(cudaMalloc(&h->d_combine_2, (size_t)n1 * n1 * sizeof(int32_t)));
@@ -188,9 +195,9 @@ int sqmc_b200_system_chem(sqmc_b200_handle **out, int norb, int nup, int ndn, co
   // nuclear_nuclear_energy = integrals(integral_index(norb+1,norb+1,norb+1,norb+1)) (chemistry.f90:398)
   int64_t a = combine_2[(size_t)(n1 - 1) * n1 + (n1 - 1)];
   int64_t idx = (a * (a - 1)) / 2 + a;
-  if (idx < 1 || idx > nint) { set_error("system_chem: integrals array shorter than the nuclear-energy index"); delete h; return 2; }
+  if (idx < 1 || idx > nint) { set_error("system_chem: integrals array shorter than the nuclear-energy index"); return 2; }
   h->T.enuc = integrals[idx - 1];
-  *out = h;
+  *out = guard.release();
   return 0;
 }
 
@@ -199,12 +206,13 @@ int sqmc_b200_system_heg(sqmc_b200_handle **out, int norb, int n_dim, const doub
   SQ_CHECK(require_init());
   if (norb < 1 || norb > 127 || (n_dim != 2 && n_dim != 3)) { set_error("system_heg: bad norb/n_dim"); return 2; }
   sqmc_b200_handle *h = new_handle(MODEL_HEG, norb, nup, ndn);
+  HandleGuard guard{h};
   SQ_CUDA(cudaMalloc(&h->d_kvec, (size_t)norb * n_dim * sizeof(double)));
   SQ_CUDA(cudaMemcpy(h->d_kvec, k_vectors, (size_t)norb * n_dim * sizeof(double), cudaMemcpyHostToDevice));
   h->T.k_vectors = h->d_kvec;
   h->T.n_dim = n_dim;
   h->T.length_cell = length_cell;
-  *out = h;
+  *out = guard.release();
   return 0;
 }
 
@@ -214,6 +222,7 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const in
   int ns = l_x * l_y;
   if (ns < 1 || ns > 127) { set_error("system_hubbardk: bad lattice"); return 2; }
   sqmc_b200_handle *h = new_handle(MODEL_HUBBARDK, ns, nup, ndn);
+  HandleGuard guard{h};
   SQ_CUDA(cudaMalloc(&h->d_hkvec, (size_t)2 * ns * sizeof(int32_t)));
   SQ_CUDA(cudaMalloc(&h->d_kenergies, (size_t)ns * sizeof(double)));
   SQ_CUDA(cudaMemcpy(h->d_hkvec, k_vectors, (size_t)2 * ns * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -223,7 +232,7 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const in
   h->T.ubyn = ubyn;
   h->T.l_x = l_x;
   h->T.l_y = l_y;
-  *out = h;
+  *out = guard.release();
   return 0;
 }
 
@@ -281,25 +290,30 @@ int sqmc_b200_build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
 }
 int sqmc_b200_export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
   SQ_CHECK(require_init());
+  if (!h) { set_error("export_upper: null handle"); return 2; }
   return export_upper(h, counts, indices, values);
 }
 int sqmc_b200_import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values) {
   SQ_CHECK(require_init());
+  if (!h) { set_error("import_upper: null handle"); return 2; }
   return import_upper(h, n, counts, indices, values);
 }
 int sqmc_b200_nnz(sqmc_b200_handle *h, int64_t *n, int64_t *nnz_upper, int64_t *nnz_full) {
+  if (!h) { set_error("nnz: null handle"); return 2; }
   if (n) *n = h->n;
   if (nnz_upper) *nnz_upper = h->nnz_upper;
   if (nnz_full) *nnz_full = h->nnz_full;
   return 0;
 }
 int sqmc_b200_local_rows(sqmc_b200_handle *h, int64_t *n_local_rows, int64_t *nnz_full_local) {
+  if (!h) { set_error("local_rows: null handle"); return 2; }
   if (n_local_rows) *n_local_rows = h->row1 - h->row0;
   if (nnz_full_local) *nnz_full_local = h->nnz_local;
   return 0;
 }
 int sqmc_b200_diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag) {
   SQ_CHECK(require_init());
+  if (!h) { set_error("diagonal: null handle"); return 2; }
   return diagonal(h, n, dets_up, dets_dn, diag);
 }
 
@@ -416,6 +430,7 @@ int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle) {
 int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol,
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());
+  if (!h) { set_error("davidson: null handle"); return 2; }
   return davidson(h, n_states, v0, evecs, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged);
 }
 
@@ -465,10 +480,7 @@ int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int6
   std::vector<int32_t> c;
   std::vector<double> v;
   int64_t L = 0;
-  if (h->wcsr) {
-    SQ_CHECK(wcsr_get_row(h, p, c, v));
-    L = (int64_t)c.size();
-  } else if (h->bundle_R) {
+  if (h->bundle_R) {
     SQ_CHECK(bundle_get_row(h, p, c, v));
     L = (int64_t)c.size();
   } else {
@@ -482,12 +494,19 @@ int sqmc_b200_get_row(sqmc_b200_handle *h, int64_t caller_row, int64_t cap, int6
   }
   *len = L;
   if (L > cap) { set_error("get_row: row has %lld entries, capacity %lld", (long long)L, (long long)cap); return 2; }
-  std::vector<std::pair<int64_t, double>> e(L);
-  for (int64_t k = 0; k < L; k++) {
-    int32_t cj = 0;
-    SQ_CUDA(cudaMemcpy(&cj, h->d_perm + c[k], sizeof(int32_t), cudaMemcpyDeviceToHost));
-    e[k] = {(int64_t)cj + 1, v[k]};
+  // internal columns -> caller columns in one device gather (perm lives on the device)
+  std::vector<int32_t> cc(L);
+  if (L > 0) {
+    DevBuf<int32_t> d_in, d_out;
+    SQ_CHECK(d_in.alloc(L));
+    SQ_CHECK(d_out.alloc(L));
+    SQ_CUDA(cudaMemcpyAsync(d_in.p, c.data(), L * sizeof(int32_t), cudaMemcpyHostToDevice, G.stream));
+    SQ_CHECK(gather_i32(h->d_perm, d_in.p, d_out.p, L, G.stream));
+    SQ_CUDA(cudaMemcpyAsync(cc.data(), d_out.p, L * sizeof(int32_t), cudaMemcpyDeviceToHost, G.stream));
+    SQ_CUDA(cudaStreamSynchronize(G.stream));
   }
+  std::vector<std::pair<int64_t, double>> e(L);
+  for (int64_t k = 0; k < L; k++) e[k] = {(int64_t)cc[k] + 1, v[k]};
   std::sort(e.begin(), e.end(), [](const std::pair<int64_t, double> &a, const std::pair<int64_t, double> &b) { return a.first < b.first; });
   for (int64_t k = 0; k < L; k++) { cols[k] = e[k].first; vals[k] = e[k].second; }
   return 0;
@@ -498,6 +517,7 @@ int sqmc_b200_partition_rows(const int64_t *work_prefix, int64_t n, int nranks, 
   return 0;
 }
 int sqmc_b200_build_times(sqmc_b200_handle *h, double *ms8) {
+  if (!h || !ms8) { set_error("build_times: null argument"); return 2; }
   for (int i = 0; i < 8; i++) ms8[i] = h->build_ms[i];
   return 0;
 }

@@ -603,10 +603,8 @@ void free_matrix(sqmc_b200_handle *h) {
   };
   F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
   F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_x2); F(h->d_y2); F(h->d_split_lo); F(h->d_split_hi);
-  F(h->d_gA_off); F(h->d_eA); F(h->d_gB_off); F(h->d_eBpos); F(h->d_bidx); F(h->d_binv);
-  wcsr_free(h);
+  F(h->d_diag);
   h->bundle_R = 0;
-  h->nA = h->nB = 0;
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
   h->row_starts.clear();
 }
@@ -790,11 +788,6 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_LAUNCH_CHECK();
   SQ_CUDA(cudaStreamSynchronize(s));
   EBb.release();
-  DevBuf<int32_t> eB_sorted_keep, bidx_keep;
-  if (!ts) {  // keep the beta-major view for the WCSR layout (entries == rows when there is no time-reversal expansion)
-    eB_sorted_keep.p = eB_sorted.take();
-    bidx_keep.p = bidx.take();
-  }
   eB_sorted.release();
   bidx.release();
 
@@ -899,7 +892,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
 
   // ---- final arrays (capacity = candidate upper bound)
   h->capacity = std::max<int64_t>(Tloc, 1);
-  // + kSlack entries: the WCSR kernel's masked 128-bit loads may touch up to 2 steps past the last entry
+  // + kSlack entries: the 128-bit stream loads of the H.v kernels may touch a few entries past the last one
   SQ_CHECK(big_malloc((void **)&h->d_cols, (h->capacity + kSlack) * sizeof(int32_t)));
   SQ_CHECK(big_malloc((void **)&h->d_vals, (h->capacity + kSlack) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(h->d_cols + h->capacity, 0, kSlack * sizeof(int32_t), s));
@@ -1056,23 +1049,9 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     }
   }
   HM.mark("nnz reduce + shrink");
-  if (!ts) {
-    h->nA = nA;
-    h->nB = nB;
-    h->d_gA_off = gA_off.take();
-    h->d_eA = eA.take();
-    h->d_gB_off = gB_off.take();
-    h->d_eBpos = eB_sorted_keep.take();
-    h->d_bidx = bidx_keep.take();
-    SQ_CUDA(cudaMalloc(&h->d_binv, n * sizeof(int32_t)));
-    invert_perm_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_bidx, h->d_binv, n);
-    SQ_LAUNCH_CHECK();
-  }
-  HM.mark("keep group structure");
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
   HM.mark("work vectors + bins");
-  SQ_CHECK(wcsr_convert(h));
   SQ_CHECK(bundle_encode(h));
   HM.mark("bundle encode");
   cudaEventRecord(ev[4], s);
@@ -1134,44 +1113,13 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
 // ------------------------------------------------------------------ export / import (compatibility paths, host side)
 int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values) {
   if (!h->d_rowptr) { set_error("export_upper: no matrix"); return 2; }
-  if (!h->wcsr) {
-    const int was_bundled = h->bundle_R;
-    SQ_CHECK(bundle_decode(h));  // the exporter walks plain rows; re-ordered again afterwards
-    int rc = export_upper_device(h, counts, indices, values);
-    if (rc) return rc;
-    if (was_bundled) {
-      SQ_CHECK(bundle_encode_r(h, was_bundled));
-      SQ_CUDA(cudaStreamSynchronize(G.stream));
-    }
-    return 0;
-  }
-  // opt-in window-staged layout: decoded on the host (inspection path of an experimental layout)
-  const int64_t nloc = h->row1 - h->row0;
-  std::vector<int64_t> rowptr(nloc + 1);
-  std::vector<int32_t> cols, perm(h->n);
-  std::vector<double> vals;
-  SQ_CHECK(wcsr_decode_host(h, rowptr, cols, vals));
-  SQ_CUDA(cudaMemcpy(perm.data(), h->d_perm, h->n * 4, cudaMemcpyDeviceToHost));
-  std::vector<std::pair<int32_t, int64_t>> rows(nloc);
-  for (int64_t q = 0; q < nloc; q++) rows[q] = {perm[h->row0 + q], q};
-  std::sort(rows.begin(), rows.end());
-  int64_t k = 0;
-  std::vector<std::pair<int32_t, double>> tmp;
-  for (int64_t rr = 0; rr < nloc; rr++) {
-    int32_t ci = rows[rr].first;
-    int64_t q = rows[rr].second;
-    tmp.clear();
-    for (int64_t e = rowptr[q]; e < rowptr[q + 1]; e++) {
-      int32_t cj = perm[cols[e]];
-      if (cj >= ci) tmp.push_back({cj, vals[e]});
-    }
-    std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b) { return a.first < b.first; });
-    counts[rr] = (int64_t)tmp.size();
-    for (auto &t : tmp) {
-      indices[k] = (int64_t)t.first + 1;
-      values[k] = t.second;
-      k++;
-    }
+  const int was_bundled = h->bundle_R;
+  SQ_CHECK(bundle_decode(h));  // the exporter walks plain rows; re-ordered again afterwards
+  int rc = export_upper_device(h, counts, indices, values);
+  if (rc) return rc;
+  if (was_bundled) {
+    SQ_CHECK(bundle_encode_r(h, was_bundled));
+    SQ_CUDA(cudaStreamSynchronize(G.stream));
   }
   return 0;
 }

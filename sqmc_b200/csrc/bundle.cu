@@ -10,7 +10,7 @@
 // [rowptr[bR], rowptr[bR+R])) but are re-ordered by (column, row) and the column word carries the row-in-bundle in its
 // low 3 bits (stored = column << 3 | r).  The byte count is unchanged (12 B per entry) and the encoding is an in-place
 // permutation inside each segment, so it is undone exactly (bundle_decode) whenever a consumer wants plain CSR rows
-// (export_upper, import, WCSR conversion); get_row reads a bundle and filters.  One warp multiplies one bundle and keeps
+// (export_upper, import); get_row reads a bundle and filters.  One warp multiplies one bundle and keeps
 // R running sums per lane (predicated adds: the kernel has ~80% idle issue slots).
 #include <cub/cub.cuh>
 
@@ -367,11 +367,11 @@ static int decode_t(sqmc_b200_handle *h, int cap, cudaStream_t s) {
   return 0;
 }
 
-// plain CSR -> bundles (no-op when disabled, already bundled, WCSR active or the column word has no room for the tag)
+// plain CSR -> bundles (no-op when disabled, already bundled or the column word has no room for the tag)
 int bundle_encode(sqmc_b200_handle *h) { return bundle_encode_r(h, bundle_want()); }
 int bundle_encode_r(sqmc_b200_handle *h, int R) {
   const int64_t nloc = h->row1 - h->row0;
-  if (!R || h->bundle_R || h->wcsr || !h->d_rowptr) return 0;
+  if (!R || h->bundle_R || !h->d_rowptr) return 0;
   if (h->n >= (1ll << (31 - kBShift))) return 0;
   if (nloc == 0 || h->nnz_local == 0) {
     // a rank without rows still switches layout: every rank must take the same (collective) code path in the two-vector H.v

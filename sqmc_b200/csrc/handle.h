@@ -85,34 +85,6 @@ static const int kNumBins = 6;
 
 }  // namespace sqmc
 
-namespace sqmc {
-// One part of the window-staged layout ("WCSR", csrc/wcsr.cu): rows cut into tiles of <= kTileRows rows of
-// one row group; inside a tile the entries are ordered (column window, row, column) and stored as
-// packed (row_local << 16 | col_local) + f64 value; a window is a piece (<= kWinMax columns) of one
-// column group whose slice of x is staged in shared memory by a bulk async copy.  Work items are
-// (window, <= kItemMax consecutive entries); one warp consumes an item.
-struct WItem {
-  int32_t col0, len;  // staged columns [col0, col0+len), col0 and len even
-  int32_t k0, k1;     // entries [k0, k1) relative to the tile's first entry
-};
-struct WPart {
-  int64_t nrows = 0, ntiles = 0, nitems = 0, ent0 = 0, nnz = 0;
-  int32_t *tile_row0 = nullptr;   // [ntiles] first row (part-local numbering)
-  int32_t *tile_nrows = nullptr;  // [ntiles]
-  int64_t *tile_ent0 = nullptr;   // [ntiles+1] first entry of the tile, relative to ent0
-  int64_t *tile_item0 = nullptr;  // [ntiles+1] first work item of the tile
-  WItem *items = nullptr;         // [nitems]
-  int64_t *rowptr = nullptr;      // [nrows+1] CSR offsets before conversion, relative to ent0 (conversion only)
-  int32_t *colwin = nullptr;      // [ncols] column -> global window id (conversion only)
-  int32_t *gwin_col0 = nullptr, *gwin_len = nullptr;  // global window table (conversion only)
-  int64_t ngwin = 0;
-};
-static const int kTileRows = 256;
-static const int kWWarps = 16;     // warps per CTA of the WCSR kernel
-static const int kWinMax = 512;    // max columns per staged window (4 KB of x)
-static const int kItemMax = 2048;  // max entries per work item
-}  // namespace sqmc
-
 struct sqmc_b200_handle {
   sqmc::ModelTables T;  // device pointers inside
   int NW = 1;
@@ -147,24 +119,9 @@ struct sqmc_b200_handle {
   // nranks>1: per local row the sub-range [split_lo, split_hi) of its (ascending) entries whose columns this rank owns
   int64_t *d_split_lo = nullptr, *d_split_hi = nullptr;
 
-  // ---- group structure of the determinant list (kept for the WCSR layout; non-time-sym builds only) ----
-  int64_t nA = 0, nB = 0;
-  int64_t *d_gA_off = nullptr;   // [nA+1] alpha-group offsets (internal rows)
-  int32_t *d_eA = nullptr;       // [n] internal row -> alpha group
-  int64_t *d_gB_off = nullptr;   // [nB+1] beta-group offsets (beta-major positions)
-  int32_t *d_eBpos = nullptr;    // [n] beta-major position -> beta group
-  int32_t *d_bidx = nullptr;     // [n] beta-major position -> internal row
-  int32_t *d_binv = nullptr;     // [n] internal row -> beta-major position
   // ---- row-bundle ordering (csrc/bundle.cu; active when bundle_R > 0: d_cols holds column << 3 | row-in-bundle) ----
   int bundle_R = 0, bundle_cap = 0;
-  // ---- WCSR layout (active when wcsr == true; then d_cols holds packed indices) ----
-  bool wcsr = false;
-  sqmc::WPart WA, WB;
-  int32_t *d_browL = nullptr;      // [nloc] local beta-major row -> internal row
-  int32_t *d_browL_inv = nullptr;  // [nloc] (internal row - row0) -> local beta-major row
-  double *d_diag = nullptr;        // [nloc] diagonal of the local rows
-  double *d_xb = nullptr;          // [n] x in beta-major order
-  double *d_yb = nullptr;          // [nloc] partial y of the same-beta part, local beta-major order
+  double *d_diag = nullptr;        // [nloc] diagonal of the local rows (copied out before the entries are re-ordered)
 
   // ---- work buffers ----
   double *d_x = nullptr;   // n (global length, internal order)
@@ -204,6 +161,7 @@ int spmv_setup_bins(sqmc_b200_handle *h);
 int spmv_launch(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
 int permute_gather(const double *src, const int32_t *idx, double *dst, int64_t n, cudaStream_t s);   // dst[i] = src[idx[i]]
 int permute_scatter(const double *src, const int32_t *idx, double *dst, int64_t n, cudaStream_t s);  // dst[idx[i]] = src[i]
+int gather_i32(const int32_t *src, const int32_t *idx, int32_t *dst, int64_t n, cudaStream_t s);         // dst[i] = src[idx[i]]
 int scale_array(double *a, int64_t n, double r, cudaStream_t s);
 int projector_epilogue(double *deltaw, const double *w, double c, int64_t n, cudaStream_t s);  // deltaw += c*w
 int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-place allgather of row blocks
@@ -216,13 +174,7 @@ int spmv_gather_multiply(sqmc_b200_handle *h, double *x_full, double *y_dev, cud
 // convert.cu
 int export_upper_device(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values);
 int import_upper_device(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
-// wcsr.cu
-int wcsr_convert(sqmc_b200_handle *h);      // CSR -> WCSR in place when the space is dense enough (or SQMC_WCSR=1)
-int wcsr_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
-int wcsr_decode_host(sqmc_b200_handle *h, std::vector<int64_t> &rowptr, std::vector<int32_t> &cols, std::vector<double> &vals);
-void wcsr_free(sqmc_b200_handle *h);
-int wcsr_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
-int extract_diag(sqmc_b200_handle *h, double *diag_dev, cudaStream_t s);
+int extract_diag(sqmc_b200_handle *h, double *diag_dev, cudaStream_t s);  // diagonal of the local rows (spmv.cu)
 // bundle.cu
 int bundle_encode(sqmc_b200_handle *h);  // plain CSR -> row bundles in place (SQMC_BUNDLE=2|4|8), no-op otherwise
 int bundle_encode_r(sqmc_b200_handle *h, int R);  // same with an explicit bundle size

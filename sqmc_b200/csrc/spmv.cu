@@ -167,7 +167,6 @@ static int launch_cta_bin(sqmc_b200_handle *h, const double *x, double *y, cudaS
 // y_dev: local rows (row1-row0), x_dev: global length n, both internal order
 int spmv_launch(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
-  if (h->wcsr) return wcsr_spmv(h, x, y, s);
   if (h->bundle_R) return bundle_spmv(h, x, y, s);
   SQ_CHECK(launch_vec_bins<0>(h, x, y, s));
   return launch_cta_bin(h, x, y, s);
@@ -204,7 +203,7 @@ int spmv_gather_multiply(sqmc_b200_handle *h, double *x, double *y, cudaStream_t
   // determinants): the NCCL kernels compete for SMs/L2 with the SpMV and the row has to be visited twice.
   static int overlap = -1;
   if (overlap < 0) { const char *e = getenv("SQMC_OVERLAP"); overlap = (e && atoi(e) > 0) ? 1 : 0; }
-  if (h->wcsr || h->bundle_R || nloc == 0 || !overlap) {
+  if (h->bundle_R || nloc == 0 || !overlap) {
     SQ_CHECK(allgather_rows(h, x, s));
     return spmv_launch(h, x, y, s);
   }
@@ -227,6 +226,36 @@ int spmv_gather_multiply(sqmc_b200_handle *h, double *x, double *y, cudaStream_t
   return launch_cta_bin(h, x, y, s);  // rows > 4096 entries: whole row after the gather
 }
 
+// ---------------------------------------------------------------- diagonal of the local rows
+__global__ void extract_diag_kernel(const int64_t *rowptr, const int32_t *cols, const double *vals, int64_t row0, int64_t nloc, double *diag) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nloc) return;
+  int64_t lo = rowptr[q], hi = rowptr[q + 1];
+  const int32_t target = (int32_t)(row0 + q);
+  double d = 0.0;
+  while (lo < hi) {  // columns of a plain row are ascending
+    int64_t mid = (lo + hi) >> 1;
+    int32_t c = cols[mid];
+    if (c == target) { d = vals[mid]; break; }
+    if (c < target) lo = mid + 1;
+    else hi = mid;
+  }
+  diag[q] = d;
+}
+// the copy kept in the handle when the entries are re-ordered (bundle.cu), else read from the plain rows
+int extract_diag(sqmc_b200_handle *h, double *diag_dev, cudaStream_t s) {
+  const int64_t nloc = h->row1 - h->row0;
+  if (nloc == 0) return 0;
+  if (h->d_diag) {
+    SQ_CUDA(cudaMemcpyAsync(diag_dev, h->d_diag, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  if (h->bundle_R) { set_error("extract_diag: re-ordered matrix without a kept diagonal"); return 4; }
+  extract_diag_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(h->d_rowptr, h->d_cols, h->d_vals, h->row0, nloc, diag_dev);
+  SQ_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------- small vector helpers
 __global__ void gather_kernel(const double *src, const int32_t *idx, double *dst, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -243,6 +272,16 @@ __global__ void scale_kernel(double *a, int64_t n, double r) {
 __global__ void axpy_kernel(double *y, const double *x, double c, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) y[i] = y[i] + c * x[i];
+}
+__global__ void gather_i32_kernel(const int32_t *src, const int32_t *idx, int32_t *dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+int gather_i32(const int32_t *src, const int32_t *idx, int32_t *dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  gather_i32_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(src, idx, dst, n);
+  SQ_LAUNCH_CHECK();
+  return 0;
 }
 int permute_gather(const double *src, const int32_t *idx, double *dst, int64_t n, cudaStream_t s) {
   if (n == 0) return 0;
@@ -308,7 +347,7 @@ __global__ void deinterleave2_kernel(const double *in2, double *a, double *b, in
 
 int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *HVa, double *HVb, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0;
-  if (!h->bundle_R) {  // plain rows / WCSR: two single-vector products
+  if (!h->bundle_R) {  // plain rows: two single-vector products
     if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Va, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
     SQ_CHECK(spmv_gather_multiply(h, h->d_x, HVa, s));
     if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Vb, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));

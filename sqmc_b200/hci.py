@@ -69,6 +69,12 @@ def perform_hci(H, system, eps_var, eps_var_sched=(), n_states=1, max_iters=50, 
         coeffs = np.max(np.abs(wts), axis=1) if it > 1 else wts[:, 0].copy()
         nu, nd, min_h_new = H.get_next_det_list(up, dn, coeffs, min_h, eps)
         n_new = n_old + len(nu)
+        if n_new == n_old:
+            # hci.f90:413-417 "Cycling hci iteration because ndets_global_new==ndets_global_old": no rebuild, no Davidson;
+            # min_H_already_done was already updated inside get_next_det_list (hci.f90:1014-1016)
+            min_h = min_h_new
+            say("Cycling hci iteration because ndets_global_new==ndets_global_old")
+            continue
         if n_new <= int(1.00001 * n_old) and eps == eps_last:
             break
         up, dn = np.concatenate([up, nu]), np.concatenate([dn, nd])

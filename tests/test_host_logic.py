@@ -186,6 +186,39 @@ def test_perform_hci_driver_loop_two_states_matches_oracle_loop(oracle):
     assert np.max(np.abs(np.array([it["energy"] for it in res["iterations"]]) - np.array(gold["iter_energy"]))) < 1e-8
 
 
+def test_perform_hci_cycles_when_selection_finds_nothing_new(oracle):
+    """hci.f90:413-417: an iteration whose selection adds no determinant (a repeated eps_var in the schedule) is cycled --
+    no H build, no Davidson, no extra iteration entry -- before the exit tests are looked at"""
+    import types
+    from sqmc_b200 import hci
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    system = types.SimpleNamespace(hf_up=(1 << 7) - 1, hf_dn=(1 << 7) - 1, time_sym=False)
+
+    class Counting(_OracleBackedHamiltonian):
+        builds = 0
+        empty_selections = 0
+
+        def get_next_det_list(self, up, dn, coeffs, min_h, eps):
+            r = super().get_next_det_list(up, dn, coeffs, min_h, eps)
+            Counting.empty_selections += int(len(r[0]) == 0)
+            return r
+
+        def generate_sparse_ham_upper_triangular(self, up, dn, ndet_old=0):
+            Counting.builds += 1
+            return super().generate_sparse_ham_upper_triangular(up, dn, ndet_old=ndet_old)
+
+    log = []
+    res = hci.perform_hci(Counting(S, oracle), system, 1e-3, [4e-3] * 6, n_states=1, log=log.append)
+    assert Counting.empty_selections >= 1, "the schedule was meant to repeat an eps_var until nothing new is found"
+    assert any("Cycling hci iteration" in ln for ln in log)
+    assert Counting.builds == len(res["iterations"])          # cycled iterations built nothing and logged nothing
+    counts = [it["n_det"] for it in res["iterations"]]
+    assert counts == sorted(set(counts))                       # every logged iteration grew the list
+    # same final space and energy as the oracle's own perform_hci restatement with the same schedule
+    ref = S.hci(1e-3, eps_var_sched=[4e-3] * 6, n_states=1)
+    assert len(res["up"]) == len(ref["up"]) and abs(res["energy"][0] - ref["energy"][0]) < 1e-9
+
+
 def test_perform_hci_checkpoint_dump_and_resume(oracle, tmp_path):
     """dump_wf_var: the variational stage writes wf_eps_var=1.00E-3 (label-sorted, hci.f90:569-625); a second run finds it,
     skips the stage (:194-231) and obtains the same PT correction"""
