@@ -155,6 +155,30 @@ int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, doub
 int sqmc_b200_davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter,
                               int *n_iter_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
 
+/* ---- the caller's data distribution under MPI ----------------------------------------
+ * The reference deals determinants to MPI ranks by hash (get_det_owner, mpi_routines.f90:419-445; do_walk.f90:1760-1807)
+ * and every rank passes / receives only ITS slice of a vector, in ascending caller index:
+ *   walk:      fast_sparse_matrix_multiply_local_band(..., vector = walk_wt(my_locations_of_imp_dets(1:my_nimp)), answer = deltaw)
+ *              + mpi_redscatt_real_dparray(deltaw(1:n_imp), imp_core_mask)         (do_walk.f90:2259-2260, mpi_routines.f90:1592)
+ *   Davidson:  davidson_sparse_mpi2 on local_det_map%ndets-long vectors             (more_tools.f90:2525, 2842-2861)
+ * set_ownership: owner_of_row(1:n) = rank (0-based) owning each determinant of the list last passed to build_h /
+ *   import_upper (every rank passes the same map; the library keeps its own row sharding and moves data between the two
+ *   distributions over NVLink).  n_owned_out = my_nimp.  Must be repeated after every build_h.
+ * matvec_local / projector_local: x_local, y_local = the owned slices (n_owned entries per vector, leading dimension
+ *   ld_local); only those bytes cross PCIe.  Collective: every rank calls with its own slice.
+ * davidson_local: v0_local / evecs_local are n_owned x n_states, leading dimension n_owned.
+ * With one rank the slice is the whole vector.  register_host page-locks a caller buffer once (the projector runs every
+ * Monte Carlo step on the same arrays). */
+int sqmc_b200_set_ownership(sqmc_b200_handle *h, const int32_t *owner_of_row, int64_t *n_owned_out);
+int sqmc_b200_matvec_local(sqmc_b200_handle *h, const double *x_local, double *y_local, int nvec, int64_t ld_local);
+int sqmc_b200_projector_local(sqmc_b200_handle *h, double tau, double e_trial, const double *w_local, double *deltaw_local);
+int sqmc_b200_davidson_local(sqmc_b200_handle *h, int n_states, const double *v0_local, double *evecs_local, double *evals, double tol,
+                             int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+int sqmc_b200_register_host(void *ptr, int64_t bytes);
+int sqmc_b200_unregister_host(void *ptr);
+/* how vectors travel between GPUs on this handle: 0 = single rank, 1 = NVLink peer-memory stores, 2 = NCCL (fallback) */
+int sqmc_b200_exchange_mode(sqmc_b200_handle *h);
+
 /* ---- Lanczos -------------------------------------------------------------------
  * Replaces matrix_lanczos_sparse (more_tools.f90:1742-1883), the eigensolver of the
  * k-space Hubbard path: <= min(n, max_iter = 50) vectors, full Gram-Schmidt pass per
@@ -167,10 +191,10 @@ int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, doubl
 
 /* ---- device-resident entry points (used by bench.py for the HBM-resident leg)
  * x_dev/y_dev are device pointers in the library's INTERNAL row order (length n for x,
- * n_local_rows for y).  Under nranks>1 only this rank's row block of x_dev needs to be valid on
- * entry: the call first all-gathers the owners' blocks in place over NCCL (what Davidson does with
+ * n_local_rows for y).  Under nranks>1 only this rank's row block of x_dev is read: the call first
+ * gathers every rank's block into the library's exchange buffer over NVLink (what Davidson does with
  * every new basis vector; the reference: zero-padded MPI_ALLREDUCE, more_tools.f90:2647), then
- * multiplies.  stream is a cudaStream_t (NULL = the library's own stream). */
+ * multiplies; x_dev itself is not written.  stream is a cudaStream_t (NULL = the library's own stream). */
 int sqmc_b200_matvec_dev(sqmc_b200_handle *h, double *x_dev, double *y_dev, void *stream);
 /* average device time (ms) of the last sqmc_b200_matvec_dev launches is measured by the caller with events */
 int sqmc_b200_device_malloc(void **p, int64_t bytes);

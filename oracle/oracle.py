@@ -335,3 +335,57 @@ def upper_to_scipy(counts, idx, val):
     U = sp.coo_matrix((val, (rows, cols)), shape=(n, n)).tocsr()
     D = sp.diags(U.diagonal())
     return (U + U.T - D).tocsr()
+
+
+# ----------------------------------------------------------------------------- MPI data distribution of the reference
+_M128 = (1 << 128) - 1
+_DJB_PRIME = 309485009821345068724781371
+_DJB_OFFSET = 144066263297769815596495629667062367629
+
+
+def _s128(x):
+    """two's complement value of a 128-bit pattern"""
+    return x - (1 << 128) if x >> 127 else x
+
+
+def djb_hash(up, dn):
+    """djb_hash (mpi_routines.f90:354-379) on integer(16) words: 16 rounds per word of
+    hash = (ishft(hash,5) + hash) + ishft(ieor(tmp, Z'5555555555555555') * prime, -j), j = 0, 8, ..., 120, with
+    tmp = up for word 1 and dn + offset for word 2; 128-bit wrap-around, ishft = logical shift.  Parity unpinned: the
+    reference ships no hash values; restated to produce realistic ownership maps for the distributed-slice tests."""
+    h = _DJB_PRIME
+    for i, w in enumerate((int(up), int(dn))):
+        tmp = (w + _DJB_OFFSET) & _M128 if i == 1 else w & _M128
+        t = ((tmp ^ 0x5555555555555555) * _DJB_PRIME) & _M128
+        for j in range(0, 128, 8):
+            h = (((h << 5) & _M128) + h + (t >> j)) & _M128
+    return _s128(h)
+
+
+def det_owner(up, dn, ncores):
+    """get_det_owner (mpi_routines.f90:419-445) + hash (:257-289): coreid = abs(mod(djb_hash(det), ncores)); 0 for one core.
+    up, dn: (n,2) uint64 arrays or python ints -> int32[n]"""
+    def ints(a):
+        a = np.asarray(a)
+        return u64_to_ints(a) if (a.dtype == np.uint64 and a.ndim == 2) else [int(v) for v in a]
+    ups, dns = ints(up), ints(dn)
+    if ncores == 1:
+        return np.zeros(len(ups), dtype=np.int32)
+    return np.array([abs(djb_hash(a, b)) % ncores for a, b in zip(ups, dns)], dtype=np.int32)
+
+
+def matvec_local_band_redscatt(counts, idx, val, owner, x_slices):
+    """What the ncores>1 branch of walk does (do_walk.f90:2259-2260): every core multiplies its column band of the
+    shuffled matrix (from_upper_triangular_to_band_shuffle, more_tools.f90:3371-3471: all rows x the columns it owns)
+    with its own slice of the vector -> an n-long partial answer (fast_sparse_matrix_multiply_local_band, :3562-3587);
+    MPI_REDUCE_SCATTER sums the partials and hands every core the rows it owns (mpi_routines.f90:1592).
+    x_slices[c] = core c's slice (its determinants in ascending list order) -> list of result slices."""
+    owner = np.asarray(owner)
+    n = len(counts)
+    ncores = len(x_slices)
+    total = np.zeros(n)
+    for c in range(ncores):
+        xc = np.zeros(n)
+        xc[owner == c] = x_slices[c]
+        total = total + matvec_upper(counts, idx, val, xc)       # band of core c times its slice; partials summed in core order
+    return [total[owner == c].copy() for c in range(ncores)]

@@ -20,6 +20,8 @@ SYMBOLS = [
     "sqmc_b200_device_free", "sqmc_b200_memcpy_h2d", "sqmc_b200_memcpy_d2h", "sqmc_b200_device_sync",
     "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
     "sqmc_b200_hci_new_dets", "sqmc_b200_set_hf_to_psit",
+    "sqmc_b200_set_ownership", "sqmc_b200_matvec_local", "sqmc_b200_projector_local", "sqmc_b200_davidson_local",
+    "sqmc_b200_register_host", "sqmc_b200_unregister_host", "sqmc_b200_exchange_mode",
 ]
 
 
@@ -74,6 +76,13 @@ def load():
     L.sqmc_b200_hci_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, vp]
     L.sqmc_b200_hci_new_dets.argtypes = [vp, vp, vp]
     L.sqmc_b200_set_hf_to_psit.argtypes = [vp, i32]
+    L.sqmc_b200_set_ownership.argtypes = [vp, vp, vp]
+    L.sqmc_b200_matvec_local.argtypes = [vp, vp, vp, i32, i64]
+    L.sqmc_b200_projector_local.argtypes = [vp, dbl, dbl, vp, vp]
+    L.sqmc_b200_davidson_local.argtypes = [vp, i32, vp, vp, vp, dbl, i32, vp, vp, i32, vp]
+    L.sqmc_b200_register_host.argtypes = [vp, i64]
+    L.sqmc_b200_unregister_host.argtypes = [vp]
+    L.sqmc_b200_exchange_mode.argtypes = [vp]
     _lib = L
     return L
 

@@ -50,6 +50,7 @@ class SparseHamiltonian:
         self._h = C.c_void_p()
         self.system = system
         self.n = 0
+        self.n_owned = 0
         L = self._L
         if isinstance(system, systems.ChemSystem):
             integrals = np.ascontiguousarray(system.integrals, dtype=np.float64)
@@ -206,6 +207,56 @@ class SparseHamiltonian:
         dw = np.zeros_like(w)
         check(self._L.sqmc_b200_projector(self._h, float(tau), float(e_trial), _p(w), _p(dw)))
         return dw
+
+    # ---- the caller's data distribution (MPI ranks own hashed subsets of the determinants) ----
+    def set_ownership(self, owner_of_row):
+        """owner_of_row[i] = rank owning determinant i of the list last built (get_det_owner, mpi_routines.f90:419).
+        -> number of determinants this rank owns (my_nimp).  Repeat after every build."""
+        o = np.ascontiguousarray(owner_of_row, dtype=np.int32)
+        if len(o) != self.n:
+            raise SqmcError("set_ownership: owner_of_row must have n entries")
+        m = C.c_int64()
+        check(self._L.sqmc_b200_set_ownership(self._h, _p(o), C.byref(m)))
+        self.n_owned = m.value
+        return m.value
+
+    def matvec_local(self, x_local, out=None):
+        """fast_sparse_matrix_multiply_local_band + mpi_redscatt_real_dparray (do_walk.f90:2259-2260): owned slice in, owned slice out."""
+        x = np.ascontiguousarray(x_local, dtype=np.float64)
+        y = np.zeros_like(x) if out is None else out
+        check(self._L.sqmc_b200_matvec_local(self._h, _p(x), _p(y), 1, max(self.n_owned, 1)))
+        return y
+
+    def projector_step_local(self, tau, e_trial, w_local, out=None):
+        w = np.ascontiguousarray(w_local, dtype=np.float64)
+        dw = np.zeros_like(w) if out is None else out
+        check(self._L.sqmc_b200_projector_local(self._h, float(tau), float(e_trial), _p(w), _p(dw)))
+        return dw
+
+    def davidson_sparse_local(self, n_states=1, initial_vector_local=None, tol=1.0e-10, max_vec_per_state=50):
+        """davidson_sparse_mpi2 (more_tools.f90:2525): vectors are the owned slices (n_owned x n_states)."""
+        m = self.n_owned
+        v0 = None
+        if initial_vector_local is not None:
+            v0 = np.asfortranarray(np.asarray(initial_vector_local, dtype=np.float64).reshape(m, n_states))
+        evecs = np.zeros((max(m, 1), n_states), order="F")
+        evals = np.zeros(n_states)
+        cap = 1024
+        ritz = np.zeros(cap * n_states)
+        nmv, nlog = C.c_int(), C.c_int()
+        check(self._L.sqmc_b200_davidson_local(self._h, n_states, _p(v0), _p(evecs), _p(evals), float(tol), int(max_vec_per_state),
+                                               C.byref(nmv), _p(ritz), cap, C.byref(nlog)))
+        k = min(nlog.value, cap)
+        return dict(evals=evals, evecs=np.ascontiguousarray(evecs[:m]), ritz=ritz[:k * n_states].reshape(k, n_states), n_matvec=nmv.value)
+
+    def register_host(self, array):
+        check(self._L.sqmc_b200_register_host(_p(array), array.nbytes))
+
+    def unregister_host(self, array):
+        check(self._L.sqmc_b200_unregister_host(_p(array)))
+
+    def exchange_mode(self):
+        return {0: "single", 1: "nvlink-peer-stores", 2: "nccl"}[self._L.sqmc_b200_exchange_mode(self._h)]
 
     # ---- Davidson ----------------------------------------------------------
     def davidson_sparse(self, n_states=1, initial_vector=None, tol=1.0e-10, max_vec_per_state=50):

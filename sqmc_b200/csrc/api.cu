@@ -112,9 +112,6 @@ int sqmc_b200_init(int device, int rank, int nranks, const void *id128) {
   G.nranks = nranks < 1 ? 1 : nranks;
   G.sm_count = prop.multiProcessorCount;
   SQ_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
-  SQ_CUDA(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
-  SQ_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
-  SQ_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
   {
     const char *pe = getenv("SQMC_POOL");
     sqmc::g_use_pool = !(pe && atoi(pe) == 0);
@@ -144,11 +141,6 @@ int sqmc_b200_finalize(void) {
   G.comm = nullptr;
   if (G.stream) cudaStreamDestroy(G.stream);
   G.stream = nullptr;
-  if (G.comm_stream) cudaStreamDestroy(G.comm_stream);
-  G.comm_stream = nullptr;
-  if (G.ev_fork) cudaEventDestroy(G.ev_fork);
-  if (G.ev_join) cudaEventDestroy(G.ev_join);
-  G.ev_fork = G.ev_join = nullptr;
   G.inited = false;
   return 0;
 }
@@ -239,6 +231,7 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const in
 int sqmc_b200_free(sqmc_b200_handle *h) {
   if (!h) return 0;
   free_matrix(h);
+  p2p_release(h);
   if (h->d_orbsym) cudaFree(h->d_orbsym);
   for (int k = 0; k < 2; k++) {
     if (h->d_hb_val[k]) cudaFree(h->d_hb_val[k]);
@@ -431,14 +424,60 @@ int sqmc_b200_davidson(sqmc_b200_handle *h, int n_states, const double *v0, doub
                        int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());
   if (!h) { set_error("davidson: null handle"); return 2; }
-  return davidson(h, n_states, v0, evecs, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged);
+  return davidson(h, n_states, v0, evecs, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged, false);
+}
+
+// ---- the caller's data distribution (owned slices in, owned slices out)
+int sqmc_b200_set_ownership(sqmc_b200_handle *h, const int32_t *owner_of_row, int64_t *n_owned_out) {
+  SQ_CHECK(require_init());
+  if (!h || !owner_of_row) { set_error("set_ownership: null argument"); return 2; }
+  return set_ownership(h, owner_of_row, n_owned_out);
+}
+int sqmc_b200_matvec_local(sqmc_b200_handle *h, const double *x_local, double *y_local, int nvec, int64_t ld_local) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("matvec_local: no matrix on this handle"); return 2; }
+  if (!h->own_set) { set_error("matvec_local: call sqmc_b200_set_ownership first"); return 2; }
+  if (ld_local < h->my_n) { set_error("matvec_local: ld_local < number of owned determinants"); return 2; }
+  for (int v = 0; v < nvec; v++) SQ_CHECK(matvec_local(h, x_local + (size_t)v * ld_local, y_local + (size_t)v * ld_local));
+  return 0;
+}
+int sqmc_b200_projector_local(sqmc_b200_handle *h, double tau, double e_trial, const double *w_local, double *deltaw_local) {
+  SQ_CHECK(require_init());
+  if (!h || !h->d_rowptr) { set_error("projector_local: no matrix on this handle"); return 2; }
+  if (!h->own_set) { set_error("projector_local: call sqmc_b200_set_ownership first"); return 2; }
+  return projector_local(h, tau, e_trial, w_local, deltaw_local);
+}
+int sqmc_b200_davidson_local(sqmc_b200_handle *h, int n_states, const double *v0_local, double *evecs_local, double *evals, double tol,
+                             int max_vec_per_state, int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
+  SQ_CHECK(require_init());
+  if (!h) { set_error("davidson_local: null handle"); return 2; }
+  return davidson(h, n_states, v0_local, evecs_local, evals, tol, max_vec_per_state, n_matvec_out, ritz_log, ritz_log_cap, n_ritz_logged, true);
+}
+// page-lock a caller buffer once so that the per-step H2D / D2H of the projector run at PCIe speed
+int sqmc_b200_register_host(void *ptr, int64_t bytes) {
+  SQ_CHECK(require_init());
+  if (!ptr || bytes <= 0) { set_error("register_host: bad arguments"); return 2; }
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("register_host: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+int sqmc_b200_unregister_host(void *ptr) {
+  if (!ptr) return 0;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("unregister_host: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+int sqmc_b200_exchange_mode(sqmc_b200_handle *h) {  // 0 single rank, 1 NVLink peer stores, 2 NCCL
+  if (!h || G.nranks == 1) return 0;
+  return h->p2p.on ? 1 : 2;
 }
 
 int sqmc_b200_matvec_dev(sqmc_b200_handle *h, double *x_dev, double *y_dev, void *stream) {
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("matvec_dev: no matrix on this handle"); return 2; }
   cudaStream_t s = stream ? (cudaStream_t)stream : G.stream;
-  return spmv_gather_multiply(h, x_dev, y_dev, s);
+  return spmv_block(h, x_dev + h->row0, y_dev, s);
 }
 int sqmc_b200_device_malloc(void **p, int64_t bytes) {
   SQ_CHECK(require_init());

@@ -602,7 +602,9 @@ void free_matrix(sqmc_b200_handle *h) {
     p = nullptr;
   };
   F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
-  F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_x2); F(h->d_y2); F(h->d_split_lo); F(h->d_split_hi);
+  F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_x2); F(h->d_xi2); F(h->d_y2);
+  F(h->d_shuf_of_internal); F(h->d_dest_rank); F(h->d_dest_pos); F(h->d_my_internal);
+  h->own_set = false; h->my_n = 0; h->own_count.clear(); h->own_off.clear();
   F(h->d_diag);
   h->bundle_R = 0;
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
@@ -610,6 +612,7 @@ void free_matrix(sqmc_b200_handle *h) {
 }
 
 static int alloc_work_vectors(sqmc_b200_handle *h) {
+  SQ_CHECK(p2p_setup(h, h->n));  // collective: (re)maps the peers' exchange buffers when the vectors outgrew them
   SQ_CUDA(cudaMalloc(&h->d_x, std::max<int64_t>(h->n, 1) * sizeof(double)));
   SQ_CUDA(cudaMalloc(&h->d_y, std::max<int64_t>(h->row1 - h->row0, 1) * sizeof(double)));
   SQ_CUDA(cudaMalloc(&h->d_tmp, std::max<int64_t>(h->n, 1) * sizeof(double)));

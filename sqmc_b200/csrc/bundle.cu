@@ -326,8 +326,6 @@ static int bundle_want() {
     const char *e = getenv("SQMC_BUNDLE");
     int v = e ? atoi(e) : 4;
     want = (v == 2 || v == 4 || v == 8) ? v : 0;
-    const char *o = getenv("SQMC_OVERLAP");
-    if (o && atoi(o) > 0) want = 0;  // the overlapped H.v splits plain rows by column ownership
   }
   return want;
 }

@@ -96,11 +96,16 @@ static void jacobi_eigh(int n, std::vector<double> a, std::vector<double> &evals
   for (int i = 0; i < n; i++) evecs[(size_t)i * n + i] = 1.0;
   auto A = [&](int i, int j) -> double & { return a[(size_t)j * n + i]; };
   auto V = [&](int i, int j) -> double & { return evecs[(size_t)j * n + i]; };
+  double frob = 0.0;
+  for (int p = 0; p < n; p++)
+    for (int q = 0; q < n; q++) frob += A(p, q) * A(p, q);
+  // stop when the off-diagonal part is below rounding relative to the matrix (an absolute test sweeps until underflow)
+  const double stop = std::max(frob * 1e-34, 1e-300);
   for (int sweep = 0; sweep < 100; sweep++) {
     double off = 0.0;
     for (int p = 0; p < n; p++)
       for (int q = p + 1; q < n; q++) off += A(p, q) * A(p, q);
-    if (off < 1e-300) break;
+    if (off <= stop) break;
     for (int p = 0; p < n; p++)
       for (int q = p + 1; q < n; q++) {
         double apq = A(p, q);
@@ -135,6 +140,49 @@ static void jacobi_eigh(int n, std::vector<double> a, std::vector<double> &evals
     for (int i = 0; i < n; i++) v2[(size_t)j * n + i] = V(i, order[j]);
   }
   evecs.swap(v2);
+}
+
+__global__ void set_unit_kernel(double *v, const int32_t *iperm, int32_t caller_row, int64_t row0, int64_t row1) {
+  const int32_t p = iperm[caller_row];
+  if (p >= row0 && p < row1) v[p - row0] = 1.0;
+}
+// H(1,1) of a one-determinant space: the rank that owns the row holds it (more_tools.f90:2235-2238)
+static int single_element(sqmc_b200_handle *h, double *out) {
+  cudaStream_t s = G.stream;
+  DevBuf<double> t;
+  SQ_CHECK(t.alloc(1));
+  if (h->row1 - h->row0 > 0) SQ_CUDA(cudaMemcpyAsync(t.p, h->d_vals, sizeof(double), cudaMemcpyDeviceToDevice, s));
+  else SQ_CUDA(cudaMemsetAsync(t.p, 0, sizeof(double), s));
+  if (G.nranks > 1) {
+    ncclResult_t r = ncclAllReduce(t.p, t.p, 1, ncclDouble, ncclSum, G.comm, s);
+    if (r != ncclSuccess) { set_error("davidson: ncclAllReduce failed: %s", ncclGetErrorString(r)); return 3; }
+  }
+  SQ_CUDA(cudaMemcpyAsync(out, t.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+// host vector (whole vector in caller order, or the owned slice when local_io) -> this rank's row block
+static int load_block(sqmc_b200_handle *h, const double *host, bool local_io, double *block, cudaStream_t s) {
+  const int64_t n = h->n, nloc = h->row1 - h->row0;
+  if (local_io) {
+    SQ_CHECK(load_local_vector(h, host, s));
+  } else {
+    SQ_CUDA(cudaMemcpyAsync(h->d_tmp, host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    SQ_CHECK(permute_gather(h->d_tmp, h->d_perm, h->d_x, n, s));
+  }
+  if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(block, h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+// this rank's row block -> host (whole vector in caller order on every rank, or the owned slice when local_io)
+static int store_block(sqmc_b200_handle *h, const double *block, bool local_io, double *host, cudaStream_t s) {
+  const int64_t n = h->n, nloc = h->row1 - h->row0;
+  if (local_io) return store_local_vector(h, block, host, s);
+  if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, block, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  SQ_CHECK(allgather_rows(h, h->d_x, s));  // the reference publishes final vectors with an n-long allreduce (:2856)
+  SQ_CHECK(permute_scatter(h->d_x, h->d_perm, h->d_tmp, n, s));
+  SQ_CUDA(cudaMemcpyAsync(host, h->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
 }
 
 // optional phase timing (SQMC_DAV_PROFILE=1): host clock around synchronised phases, printed to stderr
@@ -207,10 +255,9 @@ struct Dav {
     SQ_LAUNCH_CHECK();
     return 0;
   }
-  // HVc = H * Vc (Vc is the local block; gathered into the handle's x buffer first)
+  // HVc = H * Vc (Vc is the local block; the other ranks' blocks are gathered first)
   int apply_h(const double *Vc, double *HVc) {
-    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Vc, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SQ_CHECK(spmv_gather_multiply(h, h->d_x, HVc, s));
+    SQ_CHECK(spmv_block(h, Vc, HVc, s));
     nmv++;
     return 0;
   }
@@ -227,11 +274,22 @@ struct Dav {
 };
 
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
-             int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
+             int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged, bool local_io) {
   if (!h->d_rowptr) { set_error("davidson: no matrix on this handle"); return 2; }
   const int64_t n = h->n;
   if (n_states < 1 || n_states > n) { set_error("davidson: bad n_states"); return 2; }
+  if (local_io && !h->own_set) { set_error("davidson_local: call sqmc_b200_set_ownership first"); return 2; }
   if (max_vec <= 0) max_vec = 50;
+  const int64_t host_ld = local_io ? h->my_n : n;  // leading dimension of v0 / evecs
+  if (n == 1) {  // more_tools.f90:2235-2238
+    double d = 0;
+    SQ_CHECK(single_element(h, &d));
+    evals[0] = d;
+    if (!local_io || h->my_n > 0) evecs[0] = 1.0;
+    if (n_matvec_out) *n_matvec_out = 0;
+    if (n_ritz_logged) *n_ritz_logged = 0;
+    return 0;
+  }
   int nlogged = 0;
   auto log_ritz = [&](const double *e) {
     if (ritz_log && nlogged < ritz_log_cap)
@@ -268,9 +326,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   if (v0) {
     for (int i = 0; i < n_states; i++) {
       // caller order -> internal order, local block
-      SQ_CUDA(cudaMemcpyAsync(h->d_tmp, v0 + (size_t)i * n, n * sizeof(double), cudaMemcpyHostToDevice, s));
-      SQ_CHECK(permute_gather(h->d_tmp, h->d_perm, h->d_x, n, s));
-      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(Vc(i), h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      SQ_CHECK(load_block(h, v0 + (size_t)i * host_ld, local_io, Vc(i), s));
       SQ_CHECK(D.dots(Vc(i), 1, Vc(i), D.scal));
       SQ_CHECK(D.normalize(Vc(i), D.scal));
       if (i > 0) {
@@ -283,15 +339,10 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
       }
     }
   } else {
-    // unit vectors on the first n_states CALLER rows (v(i,i)=1)
-    std::vector<double> e(n, 0.0);
+    // unit vectors on the first n_states CALLER rows (v(i,i)=1); V is zeroed above
     for (int i = 0; i < n_states; i++) {
-      std::fill(e.begin(), e.end(), 0.0);
-      e[i] = 1.0;
-      SQ_CUDA(cudaMemcpyAsync(h->d_tmp, e.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
-      SQ_CHECK(permute_gather(h->d_tmp, h->d_perm, h->d_x, n, s));
-      if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(Vc(i), h->d_x + h->row0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      SQ_CUDA(cudaStreamSynchronize(s));
+      set_unit_kernel<<<1, 1, 0, s>>>(Vc(i), h->d_iperm, i, h->row0, h->row1);
+      SQ_LAUNCH_CHECK();
     }
   }
 
@@ -300,15 +351,6 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   std::vector<double> h_krylov((size_t)m * m, 0.0), col(m + 8);
   auto HK = [&](int i, int j) -> double & { return h_krylov[(size_t)j * m + i]; };
 
-  if (n == 1) {  // more_tools.f90:2235-2238
-    double d = 0;
-    SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
-    evals[0] = d;
-    evecs[0] = 1.0;
-    if (n_matvec_out) *n_matvec_out = 0;
-    if (n_ritz_logged) *n_ritz_logged = 0;
-    return 0;
-  }
   SQ_CHECK(extract_diag(h, D.diag, s));
   {
     std::vector<int> first(n_states);
@@ -408,13 +450,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   // ---- results: evals + eigenvectors in caller order
   PT.start();
   for (int q = 0; q < n_states; q++) evals[q] = lowest[q];
-  for (int q = 0; q < n_states; q++) {
-    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, D.W + (int64_t)q * ld, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SQ_CHECK(allgather_rows(h, h->d_x, s));  // the reference publishes final vectors with an n-long allreduce (:2856)
-    SQ_CHECK(permute_scatter(h->d_x, h->d_perm, h->d_tmp, n, s));
-    SQ_CUDA(cudaMemcpyAsync(evecs + (size_t)q * n, h->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    SQ_CUDA(cudaStreamSynchronize(s));
-  }
+  for (int q = 0; q < n_states; q++) SQ_CHECK(store_block(h, D.W + (int64_t)q * ld, local_io, evecs + (size_t)q * host_ld, s));
   PT.stop(5);  // eigenvector download
   if (PT.on)
     fprintf(stderr, "[sqmc_b200 davidson] n=%lld matvecs=%d  setup %.1f ms | residual+GS %.1f | H.v %.1f | krylov %.1f | ritz %.1f | download %.1f\n",
@@ -456,7 +492,7 @@ int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double 
   if (n_iter_out) *n_iter_out = 0;
   if (n == 1) {  // :3215-3218
     double d = 0;
-    SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
+    SQ_CHECK(single_element(h, &d));
     eig2[0] = eig2[1] = d;
     evec[0] = 0.0;   // the reference returns its unset work vector here
     return 0;
@@ -596,7 +632,7 @@ int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, d
   if (n_iter_out) *n_iter_out = 0;
   if (n == 1) {  // :1874-1876
     double d = 0;
-    SQ_CUDA(cudaMemcpy(&d, h->d_vals, sizeof(double), cudaMemcpyDeviceToHost));
+    SQ_CHECK(single_element(h, &d));
     eig3[0] = eig3[1] = eig3[2] = d;
     evec[0] = 1.0;
     return 0;

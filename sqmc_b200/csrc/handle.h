@@ -19,8 +19,6 @@ struct Global {
   int sm_count = 148;
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;  // all library work is issued on this stream unless a stream is passed in
-  cudaStream_t comm_stream = nullptr;  // NCCL all-gather of x overlapped with the local-column part of H.v
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 extern Global G;
 
@@ -80,6 +78,18 @@ struct HostMarks {
   }
 };
 
+// ---- peer-memory vector exchange (csrc/p2p.cu) ----
+static const int kMaxRanks = 16;
+struct P2P {
+  bool on = false;            // peers' slabs are mapped: exchanges use NVLink stores; otherwise NCCL
+  void *slab = nullptr;       // this rank's slab: flags | x[2] (two interleaved vectors each) | xs[2] | y
+  void *peer[kMaxRanks] = {nullptr};
+  int64_t cap = 0;            // doubles per vector slot
+  size_t bytes = 0;
+  unsigned long long epoch_x = 0, epoch_y = 0, epoch_bar = 0;
+  cudaStream_t last_stream = nullptr;
+};
+
 // number of degree bins for the SpMV (sub-warp vector sizes 2,4,8,16,32 + CTA-per-row)
 static const int kNumBins = 6;
 
@@ -116,18 +126,26 @@ struct sqmc_b200_handle {
   // ---- SpMV degree bins: row lists (local row ids) ----
   int32_t *d_bin_rows = nullptr;  // concatenated lists
   int64_t bin_off[sqmc::kNumBins + 1] = {0};
-  // nranks>1: per local row the sub-range [split_lo, split_hi) of its (ascending) entries whose columns this rank owns
-  int64_t *d_split_lo = nullptr, *d_split_hi = nullptr;
 
   // ---- row-bundle ordering (csrc/bundle.cu; active when bundle_R > 0: d_cols holds column << 3 | row-in-bundle) ----
   int bundle_R = 0, bundle_cap = 0;
   double *d_diag = nullptr;        // [nloc] diagonal of the local rows (copied out before the entries are re-ordered)
 
+  // ---- peer-memory exchange + the caller's data distribution (sqmc_b200_set_ownership) ----
+  sqmc::P2P p2p;
+  bool own_set = false;
+  std::vector<int64_t> own_count, own_off;  // per rank: determinants owned / offset of its slice in the slice-concatenated order
+  int64_t my_n = 0;                         // determinants this rank owns
+  int32_t *d_shuf_of_internal = nullptr;    // [n] internal row -> position in the slice-concatenated order
+  int32_t *d_dest_rank = nullptr;           // [nloc] owner rank of the local row's determinant
+  int32_t *d_dest_pos = nullptr;            // [nloc] its position inside the owner's slice
+  int32_t *d_my_internal = nullptr;         // [my_n] internal row of the k-th determinant this rank owns
   // ---- work buffers ----
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
   double *d_tmp = nullptr; // n (caller order staging)
-  double *d_x2 = nullptr;  // 2n: two vectors interleaved (global length), allocated on first use by the two-vector H.v
+  double *d_x2 = nullptr;  // 2n: two vectors interleaved (global length; NCCL fallback of the two-vector H.v only)
+  double *d_xi2 = nullptr; // 2*local rows: this rank's block of two interleaved vectors
   double *d_y2 = nullptr;  // 2*local rows
   // ---- heat-bath selection (select.cu) ----
   int32_t *d_orbsym = nullptr;        // [norb] orbital irreps (chem), set by sqmc_b200_system_orbital_symmetries
@@ -168,9 +186,24 @@ int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s);  // in-
 int allgather_rows_k(sqmc_b200_handle *h, double *x_full, int k, cudaStream_t s);  // same for k interleaved vectors
 // HVa = H Va, HVb = H Vb (local blocks) with ONE pass over the matrix when it is in row-bundle order
 int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *HVa, double *HVb, cudaStream_t s);
-// all-gather x (own block valid on entry) and multiply; under nranks>1 the all-gather runs on the comm stream while the
-// local-column part of every row is multiplied, the remote-column part follows
-int spmv_gather_multiply(sqmc_b200_handle *h, double *x_full, double *y_dev, cudaStream_t s);
+// whole vector (k interleaved vectors) on this rank from every rank's row block: NVLink peer stores, else NCCL
+int gather_vector(sqmc_b200_handle *h, const double *block, int k, cudaStream_t s, const double **full);
+// y = H x, x given as this rank's row block (gathered first under nranks > 1)
+int spmv_block(sqmc_b200_handle *h, const double *block, double *y_dev, cudaStream_t s);
+// p2p.cu
+int p2p_setup(sqmc_b200_handle *h, int64_t n);
+void p2p_release(sqmc_b200_handle *h);
+int p2p_gather(sqmc_b200_handle *h, const double *src, int64_t count, int64_t off, int which, cudaStream_t s, double **full_out);
+int p2p_to_owners(sqmc_b200_handle *h, const double *src, const int32_t *owner, const int32_t *pos, int64_t count, cudaStream_t s, double **y_out);
+int p2p_barrier(sqmc_b200_handle *h, cudaStream_t s);
+int p2p_check(sqmc_b200_handle *h, cudaStream_t s);
+double *p2p_x(sqmc_b200_handle *h, int r, int b);
+// local.cu: the caller's data distribution (owned slices in / out)
+int set_ownership(sqmc_b200_handle *h, const int32_t *owner_host, int64_t *n_owned_out);
+int load_local_vector(sqmc_b200_handle *h, const double *host_slice, cudaStream_t s);                       // -> whole vector, internal order, in h->d_x
+int store_local_vector(sqmc_b200_handle *h, const double *block, double *host_slice, cudaStream_t s);       // this rank's row block -> owners -> host
+int matvec_local(sqmc_b200_handle *h, const double *x_local, double *y_local);
+int projector_local(sqmc_b200_handle *h, double tau, double e_trial, const double *w_local, double *deltaw_local);
 // convert.cu
 int export_upper_device(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values);
 int import_upper_device(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
@@ -183,8 +216,9 @@ int bundle_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStr
 int bundle_spmm2(sqmc_b200_handle *h, const double *x2_dev, double *y2_dev, cudaStream_t s);  // two interleaved vectors
 int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 // davidson.cu
+// local_io: v0 / evecs are this rank's owned slices (my_n x n_states, leading dimension my_n) instead of full vectors
 int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs, double *evals, double tol, int max_vec,
-             int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged);
+             int *n_matvec_out, double *ritz_log, int ritz_log_cap, int *n_ritz_logged, bool local_io);
 int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter, int *n_iter_out, double *ritz_log,
                     int ritz_log_cap, int *n_ritz_logged);
 int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, double tol, int max_iter, int *n_iter_out, double *ritz_log,

@@ -70,47 +70,36 @@ int spmv_setup_bins(sqmc_b200_handle *h) {
   return 0;
 }
 
-// MODE 0: y = whole row.  MODE 1: y = entries [lo,hi) (columns owned by this rank).  MODE 2: y += the rest of the row.
-template <int VS, int MODE>
+template <int VS>
 __global__ void __launch_bounds__(256) spmv_vec_kernel(const int32_t *__restrict__ rows, int64_t nrows, const int64_t *__restrict__ rowptr,
                                                        const int32_t *__restrict__ cols, const double *__restrict__ vals,
-                                                       const double *__restrict__ x, double *__restrict__ y, const int64_t *__restrict__ split_lo,
-                                                       const int64_t *__restrict__ split_hi) {
+                                                       const double *__restrict__ x, double *__restrict__ y) {
   const Policies P;
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / VS;
   const int l = threadIdx.x & (VS - 1);
   const bool valid = gid < nrows;
   int32_t row = 0;
-  int64_t b0 = 0, e0 = 0, b1 = 0, e1 = 0;  // up to two segments
+  int64_t k = 0, e = 0;
   if (valid) {
     row = rows[gid];
-    if (MODE == 0) { b0 = rowptr[row]; e0 = rowptr[row + 1]; }
-    else if (MODE == 1) { b0 = split_lo[row]; e0 = split_hi[row]; }
-    else { b0 = rowptr[row]; e0 = split_lo[row]; b1 = split_hi[row]; e1 = rowptr[row + 1]; }
+    k = rowptr[row] + l;
+    e = rowptr[row + 1];
   }
   double acc = 0.0;
-#pragma unroll
-  for (int seg = 0; seg < (MODE == 2 ? 2 : 1); seg++) {
-    int64_t k = (seg == 0 ? b0 : b1) + l;
-    const int64_t e = seg == 0 ? e0 : e1;
-    // 4-way unrolled: the four column loads and four value loads are independent, then four gathers
-    for (; k + 3 * VS < e; k += 4 * VS) {
-      int32_t c0 = ld_col(cols + k, P), c1 = ld_col(cols + k + VS, P), c2 = ld_col(cols + k + 2 * VS, P), c3 = ld_col(cols + k + 3 * VS, P);
-      double v0 = ld_val(vals + k, P), v1 = ld_val(vals + k + VS, P), v2 = ld_val(vals + k + 2 * VS, P), v3 = ld_val(vals + k + 3 * VS, P);
-      double x0 = ld_x(x + c0, P), x1 = ld_x(x + c1, P), x2 = ld_x(x + c2, P), x3 = ld_x(x + c3, P);
-      acc += v0 * x0;
-      acc += v1 * x1;
-      acc += v2 * x2;
-      acc += v3 * x3;
-    }
-    for (; k < e; k += VS) acc += ld_val(vals + k, P) * ld_x(x + ld_col(cols + k, P), P);
+  // 4-way unrolled: the four column loads and four value loads are independent, then four gathers
+  for (; k + 3 * VS < e; k += 4 * VS) {
+    int32_t c0 = ld_col(cols + k, P), c1 = ld_col(cols + k + VS, P), c2 = ld_col(cols + k + 2 * VS, P), c3 = ld_col(cols + k + 3 * VS, P);
+    double v0 = ld_val(vals + k, P), v1 = ld_val(vals + k + VS, P), v2 = ld_val(vals + k + 2 * VS, P), v3 = ld_val(vals + k + 3 * VS, P);
+    double x0 = ld_x(x + c0, P), x1 = ld_x(x + c1, P), x2 = ld_x(x + c2, P), x3 = ld_x(x + c3, P);
+    acc += v0 * x0;
+    acc += v1 * x1;
+    acc += v2 * x2;
+    acc += v3 * x3;
   }
+  for (; k < e; k += VS) acc += ld_val(vals + k, P) * ld_x(x + ld_col(cols + k, P), P);
 #pragma unroll
   for (int o = VS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, VS);
-  if (valid && l == 0) {
-    if (MODE == 2) y[row] = y[row] + acc;
-    else y[row] = acc;
-  }
+  if (valid && l == 0) y[row] = acc;
 }
 
 __global__ void __launch_bounds__(256) spmv_cta_kernel(const int32_t *__restrict__ rows, int64_t nrows, const int64_t *__restrict__ rowptr,
@@ -136,23 +125,21 @@ __global__ void __launch_bounds__(256) spmv_cta_kernel(const int32_t *__restrict
   }
 }
 
-template <int VS, int MODE>
+template <int VS>
 static int launch_vec(sqmc_b200_handle *h, int bin, const double *x, double *y, cudaStream_t s) {
   int64_t nr = h->bin_off[bin + 1] - h->bin_off[bin];
   if (nr == 0) return 0;
   int64_t threads = nr * VS;
-  spmv_vec_kernel<VS, MODE><<<(unsigned)div_up(threads, 256), 256, 0, s>>>(h->d_bin_rows + h->bin_off[bin], nr, h->d_rowptr, h->d_cols, h->d_vals, x, y,
-                                                                            h->d_split_lo, h->d_split_hi);
+  spmv_vec_kernel<VS><<<(unsigned)div_up(threads, 256), 256, 0, s>>>(h->d_bin_rows + h->bin_off[bin], nr, h->d_rowptr, h->d_cols, h->d_vals, x, y);
   SQ_LAUNCH_CHECK();
   return 0;
 }
-template <int MODE>
 static int launch_vec_bins(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
-  SQ_CHECK((launch_vec<2, MODE>(h, 0, x, y, s)));
-  SQ_CHECK((launch_vec<4, MODE>(h, 1, x, y, s)));
-  SQ_CHECK((launch_vec<8, MODE>(h, 2, x, y, s)));
-  SQ_CHECK((launch_vec<16, MODE>(h, 3, x, y, s)));
-  SQ_CHECK((launch_vec<32, MODE>(h, 4, x, y, s)));
+  SQ_CHECK((launch_vec<2>(h, 0, x, y, s)));
+  SQ_CHECK((launch_vec<4>(h, 1, x, y, s)));
+  SQ_CHECK((launch_vec<8>(h, 2, x, y, s)));
+  SQ_CHECK((launch_vec<16>(h, 3, x, y, s)));
+  SQ_CHECK((launch_vec<32>(h, 4, x, y, s)));
   return 0;
 }
 static int launch_cta_bin(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
@@ -168,62 +155,39 @@ static int launch_cta_bin(sqmc_b200_handle *h, const double *x, double *y, cudaS
 int spmv_launch(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
   if (h->bundle_R) return bundle_spmv(h, x, y, s);
-  SQ_CHECK(launch_vec_bins<0>(h, x, y, s));
+  SQ_CHECK(launch_vec_bins(h, x, y, s));
   return launch_cta_bin(h, x, y, s);
 }
 
-// per local row: the sub-range of its ascending columns that falls into [row0, row1)
-__global__ void split_rows_kernel(const int64_t *rowptr, const int32_t *cols, int64_t nloc, int32_t row0, int32_t row1, int64_t *lo_out, int64_t *hi_out) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= nloc) return;
-  const int64_t b = rowptr[r], e = rowptr[r + 1];
-  int64_t lo = b, hi = e;
-  while (lo < hi) {  // first column >= row0
-    int64_t mid = (lo + hi) >> 1;
-    if (cols[mid] < row0) lo = mid + 1;
-    else hi = mid;
+// Make the whole vector (k interleaved vectors) available on this rank.  `block` = this rank's row block
+// (nloc*k doubles).  One GPU: nothing to do.  Several GPUs: every rank stores its block into every rank's x buffer
+// over NVLink (csrc/p2p.cu), or -- when peer memory could not be mapped -- NCCL all-gathers into the handle's buffer.
+int gather_vector(sqmc_b200_handle *h, const double *block, int k, cudaStream_t s, const double **full) {
+  const int64_t nloc = h->row1 - h->row0;
+  if (G.nranks == 1) { *full = block; return 0; }
+  if (h->p2p.on) {
+    double *f = nullptr;
+    SQ_CHECK(p2p_gather(h, block, nloc * k, h->row0 * k, 0, s, &f));
+    *full = f;
+    return 0;
   }
-  const int64_t first = lo;
-  hi = e;
-  while (lo < hi) {  // first column >= row1
-    int64_t mid = (lo + hi) >> 1;
-    if (cols[mid] < row1) lo = mid + 1;
-    else hi = mid;
+  double *buf = h->d_x;
+  if (k == 2) {
+    if (!h->d_x2) SQ_CUDA(cudaMalloc(&h->d_x2, std::max<int64_t>(h->n, 1) * 2 * sizeof(double)));
+    buf = h->d_x2;
   }
-  lo_out[r] = first;
-  hi_out[r] = lo;
+  if (nloc > 0 && block != buf + h->row0 * k) SQ_CUDA(cudaMemcpyAsync(buf + h->row0 * k, block, nloc * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  SQ_CHECK(allgather_rows_k(h, buf, k, s));
+  *full = buf;
+  return 0;
 }
 
-int spmv_gather_multiply(sqmc_b200_handle *h, double *x, double *y, cudaStream_t s) {
+// y = H x with x given as this rank's row block
+int spmv_block(sqmc_b200_handle *h, const double *block, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
-  if (G.nranks == 1) return spmv_launch(h, x, y, s);
-  const int64_t nloc = h->row1 - h->row0;
-  // Overlapping the all-gather with the local-column part is OPT-IN (SQMC_OVERLAP=1): measured on 8 B200s
-  // (profiles/r01_scaling.txt) the plain gather-then-multiply is faster (3.27-3.40 ms vs 3.58 ms per H.v at 10^7
-  // determinants): the NCCL kernels compete for SMs/L2 with the SpMV and the row has to be visited twice.
-  static int overlap = -1;
-  if (overlap < 0) { const char *e = getenv("SQMC_OVERLAP"); overlap = (e && atoi(e) > 0) ? 1 : 0; }
-  if (h->bundle_R || nloc == 0 || !overlap) {
-    SQ_CHECK(allgather_rows(h, x, s));
-    return spmv_launch(h, x, y, s);
-  }
-  if (!h->d_split_lo) {
-    SQ_CUDA(cudaMalloc(&h->d_split_lo, nloc * sizeof(int64_t)));
-    SQ_CUDA(cudaMalloc(&h->d_split_hi, nloc * sizeof(int64_t)));
-    split_rows_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(h->d_rowptr, h->d_cols, nloc, (int32_t)h->row0, (int32_t)h->row1, h->d_split_lo, h->d_split_hi);
-    SQ_LAUNCH_CHECK();
-  }
-  // fork: the all-gather of the other ranks' blocks runs on the comm stream ...
-  SQ_CUDA(cudaEventRecord(G.ev_fork, s));
-  SQ_CUDA(cudaStreamWaitEvent(G.comm_stream, G.ev_fork, 0));
-  SQ_CHECK(allgather_rows(h, x, G.comm_stream));
-  SQ_CUDA(cudaEventRecord(G.ev_join, G.comm_stream));
-  // ... while the columns this rank owns (already valid in x) are multiplied
-  SQ_CHECK(launch_vec_bins<1>(h, x, y, s));
-  // join: the remaining columns need the gathered vector
-  SQ_CUDA(cudaStreamWaitEvent(s, G.ev_join, 0));
-  SQ_CHECK(launch_vec_bins<2>(h, x, y, s));
-  return launch_cta_bin(h, x, y, s);  // rows > 4096 entries: whole row after the gather
+  const double *full = nullptr;
+  SQ_CHECK(gather_vector(h, block, 1, s, &full));
+  return spmv_launch(h, full, y, s);
 }
 
 // ---------------------------------------------------------------- diagonal of the local rows
@@ -310,18 +274,7 @@ int projector_epilogue(double *deltaw, const double *w, double c, int64_t n, cud
 
 // in-place all-gather of the rank-owned row blocks of a global-length vector
 // (the reference emulates this with a zero-padded MPI_ALLREDUCE, more_tools.f90:2647,2772)
-int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s) {
-  if (G.nranks == 1) return 0;
-  ncclGroupStart();
-  for (int r = 0; r < G.nranks; r++) {
-    int64_t c = h->row_starts[r + 1] - h->row_starts[r];
-    if (c == 0) continue;
-    ncclBroadcast(x_full + h->row_starts[r], x_full + h->row_starts[r], c, ncclDouble, r, G.comm, s);
-  }
-  ncclResult_t r = ncclGroupEnd();
-  if (r != ncclSuccess) { set_error("allgather_rows: NCCL error %s", ncclGetErrorString(r)); return 3; }
-  return 0;
-}
+int allgather_rows(sqmc_b200_handle *h, double *x_full, cudaStream_t s) { return allgather_rows_k(h, x_full, 1, s); }
 
 int allgather_rows_k(sqmc_b200_handle *h, double *x_full, int k, cudaStream_t s) {
   if (G.nranks == 1) return 0;
@@ -348,21 +301,20 @@ __global__ void deinterleave2_kernel(const double *in2, double *a, double *b, in
 int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *HVa, double *HVb, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0;
   if (!h->bundle_R) {  // plain rows: two single-vector products
-    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Va, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    SQ_CHECK(spmv_gather_multiply(h, h->d_x, HVa, s));
-    if (nloc > 0) SQ_CUDA(cudaMemcpyAsync(h->d_x + h->row0, Vb, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    return spmv_gather_multiply(h, h->d_x, HVb, s);
+    SQ_CHECK(spmv_block(h, Va, HVa, s));
+    return spmv_block(h, Vb, HVb, s);
   }
-  if (!h->d_x2) {
-    SQ_CUDA(cudaMalloc(&h->d_x2, std::max<int64_t>(h->n, 1) * 2 * sizeof(double)));
+  if (!h->d_y2) {
+    SQ_CUDA(cudaMalloc(&h->d_xi2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
     SQ_CUDA(cudaMalloc(&h->d_y2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
   }
   if (nloc > 0) {
-    interleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(Va, Vb, h->d_x2 + 2 * h->row0, nloc);
+    interleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(Va, Vb, h->d_xi2, nloc);
     SQ_LAUNCH_CHECK();
   }
-  SQ_CHECK(allgather_rows_k(h, h->d_x2, 2, s));
-  SQ_CHECK(bundle_spmm2(h, h->d_x2, h->d_y2, s));
+  const double *full = nullptr;
+  SQ_CHECK(gather_vector(h, h->d_xi2, 2, s, &full));
+  SQ_CHECK(bundle_spmm2(h, full, h->d_y2, s));
   if (nloc > 0) {
     deinterleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(h->d_y2, HVa, HVb, nloc);
     SQ_LAUNCH_CHECK();
