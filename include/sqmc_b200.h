@@ -132,7 +132,7 @@ int sqmc_b200_projector(sqmc_b200_handle *h, double tau, double e_trial, const d
 /* values *= ratio: the tau rescaling of do_walk.f90:2179,2919 */
 int sqmc_b200_scale_values(sqmc_b200_handle *h, double ratio);
 /* Storage-order hint for H.v (no reference counterpart; results of every other call are unchanged):
- * rows_per_bundle = 0 keeps plain CSR rows; 2, 4 or 8 re-orders the entries of that many consecutive
+ * rows_per_bundle = 0 keeps plain CSR rows; 2 or 4 re-orders the entries of that many consecutive
  * rows by column in place (csrc/bundle.cu) so that the gathers of x coalesce.  The environment variable
  * SQMC_BUNDLE sets the default applied after every build / import. */
 int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle);

@@ -410,8 +410,8 @@ int sqmc_b200_lanczos(sqmc_b200_handle *h, const double *v0, double *evec, doubl
 int sqmc_b200_set_row_bundle(sqmc_b200_handle *h, int rows_per_bundle) {
   SQ_CHECK(require_init());
   if (!h || !h->d_rowptr) { set_error("set_row_bundle: no matrix on this handle"); return 2; }
-  if (rows_per_bundle != 0 && rows_per_bundle != 2 && rows_per_bundle != 4 && rows_per_bundle != 8) {
-    set_error("set_row_bundle: rows_per_bundle must be 0, 2, 4 or 8");
+  if (rows_per_bundle != 0 && rows_per_bundle != 2 && rows_per_bundle != 4) {
+    set_error("set_row_bundle: rows_per_bundle must be 0, 2 or 4");
     return 2;
   }
   SQ_CHECK(bundle_decode(h));

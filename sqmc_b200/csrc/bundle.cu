@@ -4,14 +4,23 @@
 // a 32-lane gather of x touches ~30 distinct 32-byte sectors because one row's columns are spread over the whole vector.
 // Neighbouring rows of the alpha-major order (same alpha string, adjacent beta strings) connect to NEIGHBOURING columns,
 // so the entries of R consecutive rows, merged in column order, gather from far fewer sectors per 32 entries
-// (measured on C2: 28 -> 21 (R=2) -> 16.5 (R=4) -> 12.8 (R=8) sectors, 22 -> 6.9 128-byte lines for R=8).
+// (measured on C2: 28 -> 21 (R=2) -> 16.5 (R=4) sectors).
 //
-// Layout: a bundle = R consecutive local rows; its entries keep their place in cols/vals (the bundle's segment is
-// [rowptr[bR], rowptr[bR+R])) but are re-ordered by (column, row) and the column word carries the row-in-bundle in its
-// low 3 bits (stored = column << 3 | r).  The byte count is unchanged (12 B per entry) and the encoding is an in-place
-// permutation inside each segment, so it is undone exactly (bundle_decode) whenever a consumer wants plain CSR rows
-// (export_upper, import); get_row reads a bundle and filters.  One warp multiplies one bundle and keeps
-// R running sums per lane (predicated adds: the kernel has ~80% idle issue slots).
+// Layout (format 2): a bundle = R consecutive local rows (R = 2 or 4); its entries keep their place in cols/vals (the
+// bundle's segment is [rowptr[bR], rowptr[bR+R])) but
+//   * are re-ordered by (column, row) -- the "merged order";
+//   * the column word carries the row-in-bundle ONE-HOT in its low 4 bits (stored = column << 4 | 1 << r), so the
+//     kernel routes a product to its row sum with a 0.0 / 1.0 multiplier built from one bit (LOP3 + IMAD + DFMA per row
+//     sum) instead of compare + add + two selects;
+//   * inside every 16-byte-aligned block of 128 entries the merged order is stored TRANSPOSED (storage slot 4*l + u holds
+//     merged entry 32*u + l): one 128-bit load hands lane l the entries l, l+32, l+64, l+96 of the block, i.e. the four
+//     column words (and two such loads the four values) it needs, while each gather of x still covers 32 CONSECUTIVE
+//     merged entries (the coalescing the bundles exist for).  Entries in front of the first aligned block (<= 3) and
+//     after the last full block (<= 127) stay in merged order and are read with scalar loads.
+// The byte count is unchanged (12 B per entry) and the encoding is an in-place permutation inside each segment, so it is
+// undone exactly (bundle_decode) whenever a consumer wants plain CSR rows (export_upper, incremental build); get_row
+// reads one bundle and filters.  One warp multiplies one bundle; the block loop is software pipelined with two named
+// register sets (next block's 128-bit loads are issued between the current block's gathers and its arithmetic).
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -22,10 +31,28 @@
 
 namespace sqmc {
 
-static const int kBShift = 3;       // low bits of the stored column word = row within the bundle
+static const int kBShift = 4;       // low bits of the stored column word = one-hot row within the bundle
 static const int kBCapMax = 16384;  // entries of one bundle staged in shared memory by encode/decode (12 B each)
 
 static inline unsigned bblocks(int64_t n, int t = 256) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(div_up(n, t), 0x7fffffff)); }
+
+// storage slot of merged entry i of a segment that starts at global entry index e0 and holds L entries
+struct Sigma {
+  int h;          // entries in front of the first 4-aligned index
+  int64_t nblk;   // full 128-entry blocks
+  __host__ __device__ Sigma(int64_t e0, int64_t L) {
+    h = (int)((4 - (e0 & 3)) & 3);
+    if (h > L) h = (int)L;
+    nblk = (L - h) / 128;
+  }
+  __host__ __device__ int64_t operator()(int64_t i) const {
+    const int64_t q = i - h;
+    if (q < 0 || q >= nblk * 128) return i;
+    const int64_t j = q >> 7;
+    const int t = (int)(q & 127);
+    return h + (j << 7) + 4 * (t & 31) + (t >> 5);
+  }
+};
 
 __global__ void bundle_len_kernel(const int64_t *rowptr, int64_t nloc, int R, int64_t nb, int64_t *len) {
   int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -34,7 +61,7 @@ __global__ void bundle_len_kernel(const int64_t *rowptr, int64_t nloc, int R, in
   len[b] = rowptr[r1] - rowptr[b * R];
 }
 
-// ------------------------------------------------------------------ encode: plain rows -> (column,row)-ordered bundle
+// ------------------------------------------------------------------ encode: plain rows -> (column,row)-merged, tagged, block-transposed
 template <int R>
 __global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, int32_t *cols, double *vals, int cap,
                                                             int len_lo, bool take_longer) {
@@ -42,25 +69,41 @@ __global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__res
   double *sv = reinterpret_cast<double *>(bsm);
   int32_t *sc = reinterpret_cast<int32_t *>(sv + cap);
   __shared__ int64_t rp[R + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t b = blockIdx.x; b < nb; b += gridDim.x) {
     if (threadIdx.x <= R) rp[threadIdx.x] = rowptr[min(b * R + (int64_t)threadIdx.x, nloc)];
     __syncthreads();
     const int64_t base = rp[0];
-    const int L = (int)min(rp[R] - base, (int64_t)0x7fffffff);
-    // this launch handles bundles with len_lo < length <= cap (and the longer, tag-only ones when take_longer):
+    const int64_t Ltot = rp[R] - base;
+    // this launch handles bundles with len_lo < length <= cap (and the longer ones when take_longer):
     // short bundles run with a small shared-memory footprint, i.e. several CTAs per SM
-    if (rp[R] - base <= len_lo || (rp[R] - base > cap && !take_longer)) { __syncthreads(); continue; }
-    int off[R + 1];
-#pragma unroll
-    for (int r = 0; r <= R; r++) off[r] = (int)(rp[r] - base);
-    if (rp[R] - base > cap) {  // too long to stage: tag only, rows stay contiguous
-      for (int64_t i = threadIdx.x; i < rp[R] - base; i += blockDim.x) {
+    if (Ltot <= len_lo || (Ltot > cap && !take_longer)) { __syncthreads(); continue; }
+    const Sigma S(base, Ltot);
+    if (Ltot > cap) {
+      // too long to stage: rows stay contiguous (merged order = natural order), tags + block transposition only.
+      // pass 1: tags; pass 2: one warp transposes one 128-entry block through registers (reads precede writes)
+      for (int64_t i = threadIdx.x; i < Ltot; i += blockDim.x) {
         int r = 0;
 #pragma unroll
         for (int q = 1; q < R; q++) r += (base + i >= rp[q]);
-        cols[base + i] = (cols[base + i] << kBShift) | r;
+        cols[base + i] = (cols[base + i] << kBShift) | (1 << r);
+      }
+      __syncthreads();
+      for (int64_t j = warp; j < S.nblk; j += nwarp) {
+        const int64_t o = base + S.h + (j << 7);
+        int32_t c[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { c[u] = cols[o + 32 * u + lane]; v[u] = vals[o + 32 * u + lane]; }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) { cols[o + 4 * lane + u] = c[u]; vals[o + 4 * lane + u] = v[u]; }
       }
     } else {
+      const int L = (int)Ltot;
+      int off[R + 1];
+#pragma unroll
+      for (int r = 0; r <= R; r++) off[r] = (int)(rp[r] - base);
       for (int i = threadIdx.x; i < L; i += blockDim.x) { sc[i] = cols[base + i]; sv[i] = vals[base + i]; }
       __syncthreads();
       for (int i = threadIdx.x; i < L; i += blockDim.x) {
@@ -82,15 +125,16 @@ __global__ void __launch_bounds__(512) bundle_encode_kernel(const int64_t *__res
           }
           pos += lo - off[q];
         }
-        cols[base + pos] = (c << kBShift) | r;
-        vals[base + pos] = sv[i];
+        const int64_t st = S(pos);
+        cols[base + st] = (c << kBShift) | (1 << r);
+        vals[base + st] = sv[i];
       }
     }
     __syncthreads();
   }
 }
 
-// ------------------------------------------------------------------ decode: exact inverse (stable partition by row tag)
+// ------------------------------------------------------------------ decode: exact inverse (stable partition of the merged order by row tag)
 template <int R>
 __global__ void __launch_bounds__(256) bundle_decode_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, int32_t *cols, double *vals, int cap) {
   extern __shared__ __align__(8) unsigned char bsm[];
@@ -102,23 +146,37 @@ __global__ void __launch_bounds__(256) bundle_decode_kernel(const int64_t *__res
     if (threadIdx.x <= R) rp[threadIdx.x] = rowptr[min(b * R + (int64_t)threadIdx.x, nloc)];
     __syncthreads();
     const int64_t base = rp[0];
-    if (rp[R] - base > cap) {
-      for (int64_t i = threadIdx.x; i < rp[R] - base; i += blockDim.x) cols[base + i] = cols[base + i] >> kBShift;
+    const int64_t Ltot = rp[R] - base;
+    const Sigma S(base, Ltot);
+    if (Ltot > cap) {
+      for (int64_t j = w; j < S.nblk; j += nw) {  // undo the block transposition, then drop the tags
+        const int64_t o = base + S.h + (j << 7);
+        int32_t c[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { c[u] = cols[o + 4 * lane + u]; v[u] = vals[o + 4 * lane + u]; }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) { cols[o + 32 * u + lane] = c[u]; vals[o + 32 * u + lane] = v[u]; }
+      }
+      __syncthreads();
+      for (int64_t i = threadIdx.x; i < Ltot; i += blockDim.x) cols[base + i] = cols[base + i] >> kBShift;
     } else {
-      const int L = (int)(rp[R] - base);
+      const int L = (int)Ltot;
       for (int i = threadIdx.x; i < L; i += blockDim.x) { sc[i] = cols[base + i]; sv[i] = vals[base + i]; }
       __syncthreads();
       for (int r = w; r < R; r += nw) {
         int64_t out = rp[r];
         for (int i0 = 0; i0 < L; i0 += 32) {
           const int i = i0 + lane;
-          const int32_t word = i < L ? sc[i] : -1;
-          const bool m = i < L && (word & ((1 << kBShift) - 1)) == r;
+          const int st = i < L ? (int)S(i) : 0;
+          const int32_t word = i < L ? sc[st] : 0;
+          const bool m = i < L && ((word >> r) & 1);
           const unsigned bal = __ballot_sync(0xffffffffu, m);
           if (m) {
             const int64_t p = out + __popc(bal & ((1u << lane) - 1));
             cols[p] = word >> kBShift;
-            vals[p] = sv[i];
+            vals[p] = sv[st];
           }
           out += __popc(bal);
         }
@@ -129,211 +187,165 @@ __global__ void __launch_bounds__(256) bundle_decode_kernel(const int64_t *__res
 }
 
 // ------------------------------------------------------------------ H.v on bundles: one warp per bundle, R sums per lane
-// branch-free on purpose: written as `if (f == r) acc[r] += p` the compiler emits a jump table and the warp diverges
-template <int R, int Q>
-__device__ __forceinline__ void badd_one(double (&acc)[R], int f, double p) {
+// MODE 1: product routed with a 0.0 / 1.0 multiplier built from the one-hot bit (exact: p*1+a and p*0+a round like a+p and a)
+// MODE 0: compare + predicated add (what ptxas turns into DADD + FSEL pairs); kept for A/B measurements
+template <int R, int MODE, int Q>
+__device__ __forceinline__ void badd_one(double (&acc)[R], int32_t word, double p) {
   if constexpr (Q < R) {
-    asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %2, %3;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc[Q]) : "d"(p), "r"(f), "n"(Q));
-    badd_one<R, Q + 1>(acc, f, p);
-  }
-}
-template <int R>
-__device__ __forceinline__ void badd(double (&acc)[R], int32_t word, double p) {
-  badd_one<R, 0>(acc, word & ((1 << kBShift) - 1), p);
-}
-
-template <int R>
-__global__ void __launch_bounds__(256) spmv_bundle_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
-                                                          const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
-  const Policies P;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= nb) return;
-  const int64_t r0 = b * R;
-  const int64_t e = rowptr[min(r0 + R, nloc)];
-  int64_t k = rowptr[r0] + lane;
-  double acc[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
-  for (; k + 96 < e; k += 128) {
-    const int32_t c0 = ld_col(cols + k, P), c1 = ld_col(cols + k + 32, P), c2 = ld_col(cols + k + 64, P), c3 = ld_col(cols + k + 96, P);
-    const double v0 = ld_val(vals + k, P), v1 = ld_val(vals + k + 32, P), v2 = ld_val(vals + k + 64, P), v3 = ld_val(vals + k + 96, P);
-    const double x0 = ld_x(x + (c0 >> kBShift), P), x1 = ld_x(x + (c1 >> kBShift), P), x2 = ld_x(x + (c2 >> kBShift), P), x3 = ld_x(x + (c3 >> kBShift), P);
-    badd<R>(acc, c0, v0 * x0);
-    badd<R>(acc, c1, v1 * x1);
-    badd<R>(acc, c2, v2 * x2);
-    badd<R>(acc, c3, v3 * x3);
-  }
-  for (; k < e; k += 32) {
-    const int32_t c = ld_col(cols + k, P);
-    badd<R>(acc, c, ld_val(vals + k, P) * ld_x(x + (c >> kBShift), P));
-  }
-  double mine = 0.0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    double a = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == r) mine = a;
-  }
-  if (lane < R && r0 + lane < nloc) y[r0 + lane] = mine;
-}
-
-// software-pipelined variant: the column/value loads of block i+1 are issued while the gathers of block i are in flight,
-// so a warp always has a block of the 12 B/entry streams outstanding (the plain loop alternates stream and gather phases
-// and, once the gathers coalesce, runs out of memory-level parallelism rather than L1TEX throughput)
-template <int R, int U>
-__global__ void __launch_bounds__(256) spmv_bundle_pipe_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
-                                                               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
-  const Policies P;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= nb) return;
-  const int64_t r0 = b * R;
-  const int64_t e = rowptr[min(r0 + R, nloc)];
-  int64_t kb = rowptr[r0];  // warp-uniform block start
-  double acc[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
-  int32_t c[U];
-  double v[U];
-  bool have = kb + 32 * U <= e;
-  if (have) {
-#pragma unroll
-    for (int u = 0; u < U; u++) c[u] = ld_col(cols + kb + lane + 32 * u, P);
-#pragma unroll
-    for (int u = 0; u < U; u++) v[u] = ld_val(vals + kb + lane + 32 * u, P);
-  }
-  while (have) {
-    double xx[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) xx[u] = ld_x(x + (c[u] >> kBShift), P);
-    const int64_t kn = kb + 32 * U;
-    const bool hn = kn + 32 * U <= e;
-    int32_t cn[U];
-    double vn[U];
-    if (hn) {
-#pragma unroll
-      for (int u = 0; u < U; u++) cn[u] = ld_col(cols + kn + lane + 32 * u, P);
-#pragma unroll
-      for (int u = 0; u < U; u++) vn[u] = ld_val(vals + kn + lane + 32 * u, P);
+    if constexpr (MODE == 1) {
+      const int hi = (word & (1 << Q)) * (0x3FF00000 >> Q);  // 0x3FF00000 = high word of 1.0
+      acc[Q] = fma(p, __hiloint2double(hi, 0), acc[Q]);
+    } else {
+      asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.s32 q, t, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc[Q]) : "d"(p), "r"(word), "n"(1 << Q));
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) badd<R>(acc, c[u], v[u] * xx[u]);
-#pragma unroll
-    for (int u = 0; u < U; u++) { c[u] = cn[u]; v[u] = vn[u]; }
-    kb = kn;
-    have = hn;
+    badd_one<R, MODE, Q + 1>(acc, word, p);
   }
-  for (int64_t k = kb + lane; k < e; k += 32) {
-    const int32_t cc = ld_col(cols + k, P);
-    badd<R>(acc, cc, ld_val(vals + k, P) * ld_x(x + (cc >> kBShift), P));
-  }
-  double mine = 0.0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    double a = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == r) mine = a;
-  }
-  if (lane < R && r0 + lane < nloc) y[r0 + lane] = mine;
+}
+template <int R, int MODE>
+__device__ __forceinline__ void badd(double (&acc)[R], int32_t word, double p) {
+  badd_one<R, MODE, 0>(acc, word, p);
 }
 
-// two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x2 / y2 hold the two vectors
-// interleaved (x2[2*col + k]), so one 16-byte gather serves both and the matrix is streamed once:
-// algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)
+__device__ __forceinline__ int4 ld_col4(const int32_t *p, const Policies &P) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(P.stream));
+  return r;
+}
+__device__ __forceinline__ double2 ld_val2(const double *p, const Policies &P) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(P.stream));
+  return r;
+}
 __device__ __forceinline__ double2 bld_x2(const double *p, const Policies &P) {
   double2 r;
   asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(P.x));
   return r;
 }
-template <int R, int U>
-__global__ void __launch_bounds__(256) spmm2_bundle_pipe_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
-                                                                const double *__restrict__ vals, const double *__restrict__ x2, double *__restrict__ y2) {
+
+struct Blk {  // one lane's share of a 128-entry block: merged entries lane, lane+32, lane+64, lane+96
+  int4 c;
+  double2 v01, v23;
+};
+__device__ __forceinline__ void blk_load(Blk &B, const int32_t *cols, const double *vals, int64_t o, int lane, const Policies &P) {
+  B.c = ld_col4(cols + o + 4 * lane, P);
+  B.v01 = ld_val2(vals + o + 4 * lane, P);
+  B.v23 = ld_val2(vals + o + 4 * lane + 2, P);
+}
+
+// NV = 1: y = H x.  NV = 2: two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x / y hold the
+// two vectors interleaved (x[2*col + k]), one 16-byte gather serves both and the matrix is streamed once
+// (algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)).
+template <int R, int MODE, int NV, int MINB>
+__global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
+                                                              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
   const Policies P;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= nb) return;
   const int64_t r0 = b * R;
-  const int64_t e = rowptr[min(r0 + R, nloc)];
-  int64_t kb = rowptr[r0];
-  double acc0[R], acc1[R];
+  const int64_t e0 = rowptr[r0], e1 = rowptr[min(r0 + R, nloc)];
+  const Sigma S(e0, e1 - e0);
+  double acc[R], acc2[NV == 2 ? R : 1];
 #pragma unroll
-  for (int r = 0; r < R; r++) { acc0[r] = 0.0; acc1[r] = 0.0; }
-  int32_t c[U];
-  double v[U];
-  bool have = kb + 32 * U <= e;
-  if (have) {
+  for (int r = 0; r < R; r++) acc[r] = 0.0;
 #pragma unroll
-    for (int u = 0; u < U; u++) c[u] = ld_col(cols + kb + lane + 32 * u, P);
-#pragma unroll
-    for (int u = 0; u < U; u++) v[u] = ld_val(vals + kb + lane + 32 * u, P);
-  }
-  while (have) {
-    double2 xx[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) xx[u] = bld_x2(x2 + 2 * (int64_t)(c[u] >> kBShift), P);
-    const int64_t kn = kb + 32 * U;
-    const bool hn = kn + 32 * U <= e;
-    int32_t cn[U];
-    double vn[U];
-    if (hn) {
-#pragma unroll
-      for (int u = 0; u < U; u++) cn[u] = ld_col(cols + kn + lane + 32 * u, P);
-#pragma unroll
-      for (int u = 0; u < U; u++) vn[u] = ld_val(vals + kn + lane + 32 * u, P);
+  for (int r = 0; r < (NV == 2 ? R : 1); r++) acc2[r] = 0.0;
+
+  auto one = [&](int32_t cw, double v) {
+    if (NV == 1) {
+      badd<R, MODE>(acc, cw, v * ld_x(x + (cw >> kBShift), P));
+    } else {
+      const double2 xv = bld_x2(x + 2 * (int64_t)(cw >> kBShift), P);
+      badd<R, MODE>(acc, cw, v * xv.x);
+      badd<(NV == 2 ? R : 1), MODE>(acc2, cw, v * xv.y);
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      badd<R>(acc0, c[u], v[u] * xx[u].x);
-      badd<R>(acc1, c[u], v[u] * xx[u].y);
+  };
+  // entries in front of the first aligned block (<= 3) and behind the last full block (<= 127): merged order, scalar loads
+  if (lane < S.h) one(ld_col(cols + e0 + lane, P), ld_val(vals + e0 + lane, P));
+  for (int64_t k = e0 + S.h + (S.nblk << 7) + lane; k < e1; k += 32) one(ld_col(cols + k, P), ld_val(vals + k, P));
+
+  const int64_t o0 = e0 + S.h;
+  auto work = [&](const Blk &B, double (&xa)[4], double (&xb)[4]) {
+    badd<R, MODE>(acc, B.c.x, B.v01.x * xa[0]);
+    badd<R, MODE>(acc, B.c.y, B.v01.y * xa[1]);
+    badd<R, MODE>(acc, B.c.z, B.v23.x * xa[2]);
+    badd<R, MODE>(acc, B.c.w, B.v23.y * xa[3]);
+    if (NV == 2) {
+      badd<(NV == 2 ? R : 1), MODE>(acc2, B.c.x, B.v01.x * xb[0]);
+      badd<(NV == 2 ? R : 1), MODE>(acc2, B.c.y, B.v01.y * xb[1]);
+      badd<(NV == 2 ? R : 1), MODE>(acc2, B.c.z, B.v23.x * xb[2]);
+      badd<(NV == 2 ? R : 1), MODE>(acc2, B.c.w, B.v23.y * xb[3]);
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) { c[u] = cn[u]; v[u] = vn[u]; }
-    kb = kn;
-    have = hn;
+  };
+  auto gather = [&](const Blk &B, double (&xa)[4], double (&xb)[4]) {
+    if (NV == 1) {
+      xa[0] = ld_x(x + (B.c.x >> kBShift), P);
+      xa[1] = ld_x(x + (B.c.y >> kBShift), P);
+      xa[2] = ld_x(x + (B.c.z >> kBShift), P);
+      xa[3] = ld_x(x + (B.c.w >> kBShift), P);
+    } else {
+      double2 t;
+      t = bld_x2(x + 2 * (int64_t)(B.c.x >> kBShift), P); xa[0] = t.x; xb[0] = t.y;
+      t = bld_x2(x + 2 * (int64_t)(B.c.y >> kBShift), P); xa[1] = t.x; xb[1] = t.y;
+      t = bld_x2(x + 2 * (int64_t)(B.c.z >> kBShift), P); xa[2] = t.x; xb[2] = t.y;
+      t = bld_x2(x + 2 * (int64_t)(B.c.w >> kBShift), P); xa[3] = t.x; xb[3] = t.y;
+    }
+  };
+  // software pipeline over the full blocks with two named register sets: gathers of the current block, then the next
+  // block's 128-bit stream loads, then the current block's arithmetic (the loads are asm volatile: their order is kept)
+  Blk A, B;
+  double xa[4], xb[4];
+  const int64_t nblk = S.nblk;
+  if (nblk > 0) blk_load(A, cols, vals, o0, lane, P);
+  int64_t j = 0;
+  for (; j + 2 <= nblk; j += 2) {
+    gather(A, xa, xb);
+    blk_load(B, cols, vals, o0 + ((j + 1) << 7), lane, P);
+    work(A, xa, xb);
+    gather(B, xa, xb);
+    if (j + 2 < nblk) blk_load(A, cols, vals, o0 + ((j + 2) << 7), lane, P);
+    work(B, xa, xb);
   }
-  for (int64_t k = kb + lane; k < e; k += 32) {
-    const int32_t cc = ld_col(cols + k, P);
-    const double vv = ld_val(vals + k, P);
-    const double2 xv = bld_x2(x2 + 2 * (int64_t)(cc >> kBShift), P);
-    badd<R>(acc0, cc, vv * xv.x);
-    badd<R>(acc1, cc, vv * xv.y);
+  if (j < nblk) {
+    gather(A, xa, xb);
+    work(A, xa, xb);
   }
+
   double m0 = 0.0, m1 = 0.0;
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    double a0 = acc0[r], a1 = acc1[r];
+    double a0 = acc[r], a1 = NV == 2 ? acc2[NV == 2 ? r : 0] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      if (NV == 2) a1 += __shfl_xor_sync(0xffffffffu, a1, o);
     }
     if (lane == r) { m0 = a0; m1 = a1; }
   }
   if (lane < R && r0 + lane < nloc) {
-    y2[2 * (r0 + lane)] = m0;
-    y2[2 * (r0 + lane) + 1] = m1;
+    if (NV == 1) {
+      y[r0 + lane] = m0;
+    } else {
+      y[2 * (r0 + lane)] = m0;
+      y[2 * (r0 + lane) + 1] = m1;
+    }
   }
 }
 
 // ------------------------------------------------------------------ host side
-// default: bundles of 4 rows (measured best on B200, profiles/r01_bundle_experiment.txt); SQMC_BUNDLE=0|2|4|8 overrides
+// default: bundles of 4 rows (measured best on B200, profiles/r01_bundle_experiment.txt); SQMC_BUNDLE=0|2|4 overrides.
+// Read per call (a getenv is ~100 ns) so that one process can A/B layouts on one resident matrix.
 static int bundle_want() {
-  static int want = -1;
-  if (want < 0) {
-    const char *e = getenv("SQMC_BUNDLE");
-    int v = e ? atoi(e) : 4;
-    want = (v == 2 || v == 4 || v == 8) ? v : 0;
-  }
-  return want;
+  const char *e = getenv("SQMC_BUNDLE");
+  const int v = e ? atoi(e) : 4;
+  return (v == 2 || v == 4) ? v : 0;
 }
-// blocks of 32 entries per lane kept in flight by the pipelined kernel (SQMC_BUNDLE_PIPE=0|2|4, default 4)
-static int bundle_pipe() {  // read per launch (a getenv is ~100 ns) so that scripts/bundle_inproc.py can A/B on one resident matrix
-  const char *e = getenv("SQMC_BUNDLE_PIPE");
-  const int pipe = e ? atoi(e) : 4;
-  return (pipe == 0 || pipe == 2 || pipe == 4) ? pipe : 4;
+// kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 1 = 0/1-multiplier routing, 0 = predicated adds; MINB = CTAs/SM the
+// register allocation is bounded for).  A/B results in profiles/r02_bundle_kernel_ab.txt.
+static int bundle_variant() {
+  const char *e = getenv("SQMC_BUNDLE_KERNEL");
+  const int v = e ? atoi(e) : 14;
+  return (v == 4 || v == 5 || v == 14 || v == 15) ? v : 14;
 }
 
 template <int R>
@@ -370,21 +382,21 @@ int bundle_encode(sqmc_b200_handle *h) { return bundle_encode_r(h, bundle_want()
 int bundle_encode_r(sqmc_b200_handle *h, int R) {
   const int64_t nloc = h->row1 - h->row0;
   if (!R || h->bundle_R || !h->d_rowptr) return 0;
+  if (R != 2 && R != 4) { set_error("bundle_encode: rows per bundle must be 2 or 4"); return 2; }
   if (h->n >= (1ll << (31 - kBShift))) return 0;
+  cudaStream_t s = G.stream;
+  if (!h->d_diag && nloc > 0) {  // Davidson's preconditioner and the projector read the diagonal: keep a copy
+    double *dst = nullptr;
+    SQ_CUDA(cudaMalloc(&dst, nloc * sizeof(double)));
+    int rc = extract_diag(h, dst, s);  // reads the plain rows (d_diag is still unset)
+    if (rc) { cudaFree(dst); return rc; }
+    h->d_diag = dst;
+  }
   if (nloc == 0 || h->nnz_local == 0) {
     // a rank without rows still switches layout: every rank must take the same (collective) code path in the two-vector H.v
     h->bundle_R = R;
     h->bundle_cap = 1024;
     return 0;
-  }
-  cudaStream_t s = G.stream;
-  if (!h->d_diag) {  // Davidson's preconditioner and the projector read the diagonal: keep a copy
-    SQ_CUDA(cudaMalloc(&h->d_diag, nloc * sizeof(double)));
-    double *dst = h->d_diag;
-    h->d_diag = nullptr;  // extract_diag copies from d_diag when it is set
-    int rc = extract_diag(h, dst, s);
-    h->d_diag = dst;
-    if (rc) return rc;
   }
   // staging capacity = longest bundle (rounded up), capped
   const int64_t nb = div_up(nloc, (int64_t)R);
@@ -405,7 +417,7 @@ int bundle_encode_r(sqmc_b200_handle *h, int R) {
   int cap = (int)std::min<int64_t>(kBCapMax, std::max<int64_t>(1024, (maxlen + 1023) / 1024 * 1024));
   if (const char *ce = getenv("SQMC_BUNDLE_CAP")) cap = std::max(64, std::min(cap, atoi(ce)));  // test hook: force the tag-only path
   h->bundle_cap = cap;
-  int rc = R == 2 ? encode_t<2>(h, cap, s) : R == 4 ? encode_t<4>(h, cap, s) : encode_t<8>(h, cap, s);
+  int rc = R == 2 ? encode_t<2>(h, cap, s) : encode_t<4>(h, cap, s);
   if (rc) return rc;
   h->bundle_R = R;
   return 0;
@@ -417,7 +429,7 @@ int bundle_decode(sqmc_b200_handle *h) {
   cudaStream_t s = G.stream;
   const int R = h->bundle_R, cap = h->bundle_cap;
   if (h->row1 - h->row0 > 0 && h->nnz_local > 0) {
-    int rc = R == 2 ? decode_t<2>(h, cap, s) : R == 4 ? decode_t<4>(h, cap, s) : decode_t<8>(h, cap, s);
+    int rc = R == 2 ? decode_t<2>(h, cap, s) : decode_t<4>(h, cap, s);
     if (rc) return rc;
   }
   SQ_CUDA(cudaStreamSynchronize(s));
@@ -425,45 +437,30 @@ int bundle_decode(sqmc_b200_handle *h) {
   return 0;
 }
 
-int bundle_spmv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
+template <int NV>
+static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0;
   const int R = h->bundle_R;
   const int64_t nb = div_up(nloc, (int64_t)R);
   if (nb == 0) return 0;
   const unsigned grid = (unsigned)div_up(nb * 32, (int64_t)256);
-  const int pipe = bundle_pipe();
-#define SQ_BL(KERN) KERN<<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y)
-  if (pipe == 4) {
-    if (R == 2) SQ_BL((spmv_bundle_pipe_kernel<2, 4>)); else if (R == 4) SQ_BL((spmv_bundle_pipe_kernel<4, 4>)); else SQ_BL((spmv_bundle_pipe_kernel<8, 4>));
-  } else if (pipe == 2) {
-    if (R == 2) SQ_BL((spmv_bundle_pipe_kernel<2, 2>)); else if (R == 4) SQ_BL((spmv_bundle_pipe_kernel<4, 2>)); else SQ_BL((spmv_bundle_pipe_kernel<8, 2>));
+  const int var = bundle_variant();
+#define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y)
+  if (R == 4) {
+    if (var == 14) SQ_BL(4, 1, 4); else if (var == 15) SQ_BL(4, 1, 5); else if (var == 4) SQ_BL(4, 0, 4); else SQ_BL(4, 0, 5);
   } else {
-    if (R == 2) SQ_BL(spmv_bundle_kernel<2>); else if (R == 4) SQ_BL(spmv_bundle_kernel<4>); else SQ_BL(spmv_bundle_kernel<8>);
+    if (var == 14) SQ_BL(2, 1, 4); else if (var == 15) SQ_BL(2, 1, 5); else if (var == 4) SQ_BL(2, 0, 4); else SQ_BL(2, 0, 5);
   }
 #undef SQ_BL
   SQ_LAUNCH_CHECK();
   return 0;
 }
+int bundle_spmv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) { return launch_hv<1>(h, x, y, s); }
 
 // y2 = H x2 for two interleaved vectors; only on bundled matrices (the caller falls back to two H.v otherwise)
 int bundle_spmm2(sqmc_b200_handle *h, const double *x2, double *y2, cudaStream_t s) {
-  const int64_t nloc = h->row1 - h->row0;
-  const int R = h->bundle_R;
-  if (!R) { set_error("bundle_spmm2: matrix is not in row-bundle order"); return 2; }
-  const int64_t nb = div_up(nloc, (int64_t)R);
-  if (nb == 0) return 0;
-  const unsigned grid = (unsigned)div_up(nb * 32, (int64_t)256);
-  const char *ue = getenv("SQMC_SPMM_PIPE");
-  const int U = ue ? atoi(ue) : 4;  // measured at 10^7 dets: 25.7 ms per pair with 4 blocks in flight, 29.8 ms with 2
-#define SQ_BM(KERN) KERN<<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x2, y2)
-  if (U == 4) {
-    if (R == 2) SQ_BM((spmm2_bundle_pipe_kernel<2, 4>)); else if (R == 4) SQ_BM((spmm2_bundle_pipe_kernel<4, 4>)); else SQ_BM((spmm2_bundle_pipe_kernel<8, 2>));
-  } else {
-    if (R == 2) SQ_BM((spmm2_bundle_pipe_kernel<2, 2>)); else if (R == 4) SQ_BM((spmm2_bundle_pipe_kernel<4, 2>)); else SQ_BM((spmm2_bundle_pipe_kernel<8, 2>));
-  }
-#undef SQ_BM
-  SQ_LAUNCH_CHECK();
-  return 0;
+  if (!h->bundle_R) { set_error("bundle_spmm2: matrix is not in row-bundle order"); return 2; }
+  return launch_hv<2>(h, x2, y2, s);
 }
 
 // one row out of a bundled matrix (get_row): read the bundle's segment and keep the entries tagged with this row
@@ -483,8 +480,11 @@ int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_
   }
   cols.clear();
   vals.clear();
-  for (int64_t k = 0; k < L; k++)
-    if ((c[k] & ((1 << kBShift) - 1)) == r) { cols.push_back(c[k] >> kBShift); vals.push_back(v[k]); }
+  const Sigma S(rp[0], L);
+  for (int64_t i = 0; i < L; i++) {  // merged order: ascending columns within the row
+    const int64_t st = S(i);
+    if ((c[st] >> r) & 1) { cols.push_back(c[st] >> kBShift); vals.push_back(v[st]); }
+  }
   return 0;
 }
 

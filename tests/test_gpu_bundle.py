@@ -42,7 +42,7 @@ def test_bundles_match_oracle_and_round_trip_exactly(oracle, c2_space, space, ca
     plain = H.export_upper()
     rows = [1, 2, n // 3, n // 2, n - 1, n]
     plain_rows = [H.get_row(r) for r in rows]
-    for R in (2, 4, 8, 0, 4):
+    for R in (2, 4, 0, 2, 4):
         H.set_row_bundle(R)
         y = H.matvec(x)
         assert np.max(np.abs(y - y_ref)) <= 1e-10 * max(1.0, np.max(np.abs(y_ref))), R
@@ -64,7 +64,7 @@ def test_bundled_davidson_and_projector(oracle, c2_space):
     H = sq.SparseHamiltonian(sq.ChemSystem(C2_FCIDUMP, time_sym=False, z=1))
     H.generate_sparse_ham_upper_triangular(up, dn)
     energies = []
-    for R in (0, 2, 4, 8):
+    for R in (0, 2, 4):
         H.set_row_bundle(R)
         d = H.davidson_sparse(n_states=1)
         energies.append(float(d["evals"][0]))
@@ -73,7 +73,7 @@ def test_bundled_davidson_and_projector(oracle, c2_space):
     w = np.abs(ref["evecs"][:, 0]) + 0.01
     _, dw_ref = oracle.projector_step(cnt, idx, -tau * val, tau, ref["evals"][0], w)
     H.scale_values(-tau)
-    for R in (4, 0, 8):
+    for R in (4, 0, 2):
         H.set_row_bundle(R)
         dw = H.projector_step(tau, ref["evals"][0], w)
         assert np.max(np.abs(dw - dw_ref)) <= 1e-12 * np.max(np.abs(dw_ref)) + 1e-15
@@ -114,7 +114,7 @@ def test_tiny_spaces_in_every_layout(oracle, heg_space, n):
     x = np.linspace(-1.0, 1.0, n) + 0.25
     yref = oracle.matvec_upper(cnt, idx, val, x)
     ref = oracle.davidson(cnt, idx, val, n_states=1)
-    for R in (4, 8, 2, 0):
+    for R in (4, 2, 0):
         H.set_row_bundle(R)
         assert np.max(np.abs(H.matvec(x) - yref)) <= 1e-12 * max(np.max(np.abs(yref)), 1e-300)
         e = H.export_upper()
