@@ -232,6 +232,26 @@ __global__ void nm1_runs_kernel(const uint64_t *Ea, const int64_t *gA_off, int64
   run_hi[id] = (int32_t)lo;
 }
 
+// neighbour groups of every alpha group = the members of the runs of its (N-1)-electron keys, plus the group itself
+__global__ void nbr_count_kernel(const int32_t *run_lo, const int32_t *run_hi, int64_t nA, int nel, int32_t *cnt) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= nA) return;
+  int c = 1;
+  for (int e = 0; e < nel; e++) c += run_hi[g * nel + e] - run_lo[g * nel + e] - 1;  // every run contains the group itself once
+  cnt[g] = c;
+}
+__global__ void nbr_fill_kernel(const int32_t *run_lo, const int32_t *run_hi, const int32_t *K_grp, int64_t nA, int nel, const int64_t *off, int32_t *nbr) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= nA) return;
+  int64_t o = off[g];
+  nbr[o++] = (int32_t)g;
+  for (int e = 0; e < nel; e++)
+    for (int32_t r = run_lo[g * nel + e]; r < run_hi[g * nel + e]; r++) {
+      const int32_t g2 = K_grp[r];
+      if (g2 != (int32_t)g) nbr[o++] = g2;
+    }
+}
+
 // ------------------------------------------------------------------ candidate generation
 struct ConnView {
   // expanded entries in alpha-major order
@@ -244,9 +264,9 @@ struct ConnView {
   const uint64_t *EBa;     // a-string in beta-major order
   const uint32_t *EBrep;   // rep in beta-major order
   const int32_t *rowE;     // row -> its unswapped entry
-  // neighbour runs
-  const int32_t *run_lo, *run_hi, *K_grp;
-  int nel;
+  // per alpha group: its own index and the groups of the strings one excitation away, ascending
+  const int64_t *nbr_off;
+  const int32_t *nbr;
 };
 
 // Tiled candidate generation: one CTA per tile of <= 256 consecutive entries of ONE alpha-group, one thread per entry
@@ -264,9 +284,14 @@ static const int kConnTile = 256;
 static const int kConnStage = 1024;  // beta strings staged per step
 
 // W32: norb <= 32 -> strings are compared as 32-bit words (POPC is a quarter-rate instruction: one instead of two per test)
-template <int NW, bool FILL, bool W32>
+// SORTED (no time-reversal expansion: entries == rows): the candidate groups are visited in ascending order and the row
+// itself is emitted in its place inside its own group, so the "alpha part" of a row comes out in ascending column order;
+// the same-beta up-doubles follow as a second ascending run (alen = length of the first run).  The two runs are merged
+// when the evaluated row is copied to its final place -- no per-row sort.  Otherwise (time-reversed partners in the
+// entry list) the diagonal comes first, the order is arbitrary and the rows are sorted afterwards.
+template <int NW, bool FILL, bool W32, bool SORTED>
 __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, const TileDesc *tiles, int64_t ntiles, int64_t row_begin,
-                                                                 int32_t *counts, const int64_t *cand_ptr, int32_t *cand) {
+                                                                 int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen) {
   __shared__ uint64_t sEb[W32 ? 1 : kConnStage * NW];
   __shared__ uint32_t sEb32[W32 ? kConnStage : 1];
   __shared__ uint32_t sErep[FILL ? kConnStage : 1];
@@ -285,49 +310,44 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
     int64_t base = 0;
     if (FILL && active) base = cand_ptr[p - row_begin];
     int cnt = 0;
-    if (active) {
+    if (!SORTED && active) {
       if (FILL) cand[base] = (int32_t)p;  // diagonal
       cnt = 1;
     }
     const int g = T.g;
-    // candidate groups: index -1 = own group, then the runs of the nel (N-1)-electron keys of the group's string
-    for (int ek = -1; ek < V.nel; ek++) {
-      int32_t rlo = 0, rhi = 1;
-      if (ek >= 0) { rlo = V.run_lo[(int64_t)g * V.nel + ek]; rhi = V.run_hi[(int64_t)g * V.nel + ek]; }
-      for (int32_t r = rlo; r < rhi; r++) {
-        const int32_t g2 = (ek < 0) ? g : V.K_grp[r];
-        if (ek >= 0 && g2 == g) continue;
-        const bool own = ek < 0;
-        const int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
-        for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
-          const int ns = (int)min((int64_t)kConnStage, hi - s0);
-          __syncthreads();  // previous stage fully consumed
-          for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    // candidate groups: the group itself and the groups of the strings one excitation away, in ascending order
+    for (int64_t q = V.nbr_off[g]; q < V.nbr_off[g + 1]; q++) {
+      const int32_t g2 = V.nbr[q];
+      const bool own = g2 == g;
+      const int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
+      for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
+        const int ns = (int)min((int64_t)kConnStage, hi - s0);
+        __syncthreads();  // previous stage fully consumed
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+          if (W32) {
+            sEb32[i] = (uint32_t)V.Eb[s0 + i];
+          } else {
+#pragma unroll
+            for (int w = 0; w < NW; w++) sEb[i * NW + w] = V.Eb[(s0 + i) * NW + w];
+          }
+          if (FILL) sErep[i] = V.Erep[s0 + i];
+        }
+        __syncthreads();
+        if (active) {
+          const uint32_t b32 = (uint32_t)b.w[0];
+#pragma unroll 8
+          for (int i = 0; i < ns; i++) {
+            int pc = 0;
             if (W32) {
-              sEb32[i] = (uint32_t)V.Eb[s0 + i];
+              pc = __popc(b32 ^ sEb32[i]);
             } else {
 #pragma unroll
-              for (int w = 0; w < NW; w++) sEb[i * NW + w] = V.Eb[(s0 + i) * NW + w];
+              for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
             }
-            if (FILL) sErep[i] = V.Erep[s0 + i];
-          }
-          __syncthreads();
-          if (active) {
-            const uint32_t b32 = (uint32_t)b.w[0];
-#pragma unroll 8
-            for (int i = 0; i < ns; i++) {
-              int pc = 0;
-              if (W32) {
-                pc = __popc(b32 ^ sEb32[i]);
-              } else {
-#pragma unroll
-                for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
-              }
-              const bool hit = own ? (pc == 2 || pc == 4) : (pc == 0 || pc == 2);
-              if (hit) {
-                if (FILL) cand[base + cnt] = (int32_t)(sErep[i] & ~kSwapBit);
-                cnt++;
-              }
+            const bool hit = own ? (pc == 2 || pc == 4 || (SORTED && pc == 0)) : (pc == 0 || pc == 2);
+            if (hit) {
+              if (FILL) cand[base + cnt] = (int32_t)(sErep[i] & ~kSwapBit);
+              cnt++;
             }
           }
         }
@@ -346,6 +366,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
       const int64_t p2 = (int64_t)V.Erep[e2];
       const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] : 0;
       int c2 = s_cnt[rr];
+      if (FILL && SORTED && lane == 0) alen[p2 - row_begin] = c2;
       const int32_t gb = V.eB[e2];
       const int64_t lo = V.gB_off[gb], hi = V.gB_off[gb + 1];
       for (int64_t tb = lo; tb < hi; tb += 32) {
@@ -436,20 +457,51 @@ __global__ void __launch_bounds__(256) sort_rows_block_kernel(const int64_t *ptr
 }
 
 // ------------------------------------------------------------------ element evaluation + in-row compaction
-// One warp per row.  cand (sorted) is compacted in place, vals written at the same offsets.
-template <int NW>
-__global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t *up, const uint64_t *dn, const int32_t *perm,
-                                                   int64_t row_begin, int64_t row_end, const int64_t *cand_ptr, const int32_t *cand_len,
-                                                   int32_t *cand, double *vals, int32_t *row_nnz) {
+// chem: does the element of this pair take the long path (a single excitation: ~nelec integral look-ups per spin, or a
+// diagonal-like term of the symmetrised element) instead of the 1-2 look-ups of a double?
+template <int NW, bool TS>
+__device__ __forceinline__ bool chem_is_heavy(const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
+  const int l1 = excitation_level(iu, id, ju, jd);
+  if (!TS) return l1 == 1;
+  bool heavy = l1 == 1 || l1 == 0;
+  if (!b_eq(iu, id) && !b_eq(ju, jd)) {  // second term of hamiltonian_chem_time_sym (chemistry.f90:1355-1364)
+    const int l2 = excitation_level(id, iu, ju, jd);
+    heavy = heavy || l2 == 1 || l2 == 0;
+  }
+  return heavy;
+}
+
+// diagonal elements of the rows [row0, row0 + nloc) (internal order), one thread per row; kept in the handle (Davidson's
+// preconditioner, the projector) and read by eval_kernel, whose body then holds no diagonal code at all
+template <int NW, int MODEL, bool TS>
+__global__ void diag_rows_kernel(ModelTables T, const uint64_t *up, const uint64_t *dn, const int32_t *perm, int64_t row0, int64_t nloc, double *out) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= nloc) return;
+  const Bits<NW> u = b_load<NW>(up, row0 + q), d = b_load<NW>(dn, row0 + q);
+  double v = model_hamiltonian<NW, MODEL, TS>(T, T.combine_2, u, d, u, d);
+  if (MODEL == MODEL_HUBBARDK && T.hf_to_psit && perm[row0 + q] == 0) v = 0.0;  // first row = single zero diagonal entry (hubbard.f90:9636-9643)
+  out[q] = v;
+}
+
+// One warp per row, specialised per model.  Pass 1 evaluates the element of every (sorted) candidate into vals[]:
+// doubles at once; chem singles -- ten times the work -- are queued per warp and evaluated 32 at a time, so a warp never
+// idles 31 lanes behind one single.  Pass 2 applies abs(H) > 1e-12 (chemistry.f90:9901; the diagonal is always kept,
+// :9887-9890), drops duplicate candidates (time-reversed partners) and compacts cand / vals in place, in order.
+template <int NW, int MODEL, bool TS>
+__global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t *__restrict__ up, const uint64_t *__restrict__ dn, const int32_t *__restrict__ perm,
+                                                   const double *__restrict__ diag, int64_t diag_row0, int64_t row_begin, int64_t row_end,
+                                                   const int64_t *__restrict__ cand_ptr, const int32_t *__restrict__ cand_len, int32_t *cand, double *vals,
+                                                   int32_t *row_nnz, int32_t *alen /* in: candidates of the first sorted run, out: kept ones; may be null */) {
   extern __shared__ int32_t c2s[];
+  __shared__ int32_t s_q[8][64];
   const int32_t *c2 = T.combine_2;
-  if (T.model == MODEL_CHEM) {
-    int n1 = T.norb + 1;
+  if (MODEL == MODEL_CHEM) {
+    const int n1 = T.norb + 1;
     for (int i = threadIdx.x; i < n1 * n1; i += blockDim.x) c2s[i] = T.combine_2[i];
     __syncthreads();
     c2 = c2s;
   }
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t p = row_begin + warp;
   if (p >= row_end) return;
@@ -458,54 +510,125 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
   const int32_t cp = perm[p];
   const int64_t base = cand_ptr[warp];
   const int L = cand_len[warp];
-  int kept = 0;
+  // ---- pass 1: values.  Every trip of the loop gives each lane at most one job (a candidate position to evaluate): a
+  // scan trip classifies the next 32 candidates -- light ones become the lane's job, chem singles go to the warp's queue --
+  // and a drain trip hands out 32 queued singles.  The element code is instantiated once, at the single job site below.
+  int qn = 0;  // queued singles (warp-uniform)
+  int kb = 0;
+  while (true) {
+    int job = -1;
+    if (MODEL == MODEL_CHEM && (qn >= 32 || (kb >= L && qn > 0))) {
+      const int take = min(qn, 32);
+      if (lane < take) job = s_q[w][lane];
+      const int rest = (32 + lane < qn) ? s_q[w][32 + lane] : 0;
+      __syncwarp();
+      s_q[w][lane] = rest;
+      qn -= take;
+      __syncwarp();
+    } else if (kb < L) {
+      const int k = kb + lane;
+      const bool in = k < L;
+      const int32_t j = in ? cand[base + k] : -1;
+      const int32_t jprev = (TS && in && k > 0) ? cand[base + k - 1] : -2;
+      const bool todo = in && j != (int32_t)p && j != jprev;
+      bool heavy = false;
+      if (MODEL == MODEL_CHEM && todo) {
+        const Bits<NW> ju = b_load<NW>(up, j), jd = b_load<NW>(dn, j);
+        heavy = cp < perm[j] ? chem_is_heavy<NW, TS>(pu, pd, ju, jd) : chem_is_heavy<NW, TS>(ju, jd, pu, pd);
+      }
+      if (todo && !heavy) job = k;
+      if (MODEL == MODEL_CHEM) {
+        const unsigned hm = __ballot_sync(full, heavy);
+        if (heavy) s_q[w][qn + __popc(hm & lt_mask)] = k;
+        qn += __popc(hm);
+        __syncwarp();
+      }
+      kb += 32;
+    } else {
+      break;
+    }
+    if (job >= 0) {
+      const int32_t j = cand[base + job];
+      Bits<NW> bu = pu, bd = pd, ku = b_load<NW>(up, j), kd = b_load<NW>(dn, j);
+      if (!(cp < perm[j])) {  // the reference stores H(i,j) for caller index i<j with det_i as bra: evaluate in that orientation
+        Bits<NW> t = bu; bu = ku; ku = t;
+        t = bd; bd = kd; kd = t;
+      }
+      vals[base + job] = model_hamiltonian<NW, MODEL, TS>(T, c2, bu, bd, ku, kd);
+    }
+  }
+  __syncwarp();
+  // ---- pass 2: filter + ordered in-place compaction
+  const int asplit = alen ? alen[warp] : L;
+  int kept = 0, kept_a = 0;
   for (int kb = 0; kb < L; kb += 32) {
-    int k = kb + lane;
-    bool in = k < L;
-    int32_t j = in ? cand[base + k] : -1;
-    int32_t jprev = (in && k > 0) ? cand[base + k - 1] : -2;
+    const int k = kb + lane;
+    const bool in = k < L;
+    const int32_t j = in ? cand[base + k] : -1;
+    const int32_t jprev = (TS && in && k > 0) ? cand[base + k - 1] : -2;
     bool keep = false;
     double v = 0.0;
     if (in && j != jprev) {
       if (j == (int32_t)p) {
-        v = model_hamiltonian<NW>(T, c2, pu, pd, pu, pd);
-        keep = true;  // diagonal is always stored (chemistry.f90:9887-9890)
+        v = diag[p - diag_row0];
+        keep = true;
       } else {
-        Bits<NW> ju = b_load<NW>(up, j), jd = b_load<NW>(dn, j);
-        // the reference stores H(i,j) for caller index i<j with det_i as bra
-        const int32_t cj = perm[j];
-        if (cp < cj) v = model_hamiltonian<NW>(T, c2, pu, pd, ju, jd);
-        else v = model_hamiltonian<NW>(T, c2, ju, jd, pu, pd);
+        v = vals[base + k];
         keep = fabs(v) > 1.e-12;
-        if (T.hf_to_psit && (cp == 0 || cj == 0)) keep = false;  // no row links to the first state
+        if (MODEL == MODEL_HUBBARDK && T.hf_to_psit && (cp == 0 || perm[j] == 0)) keep = false;  // no row links to the first state
       }
-      if (T.hf_to_psit && cp == 0 && j == (int32_t)p) v = 0.0;   // first row = single zero diagonal entry
     }
     __syncwarp();
-    unsigned m = __ballot_sync(full, keep);
+    const unsigned m = __ballot_sync(full, keep);
     if (keep) {
-      int pos = kept + __popc(m & lt_mask);
+      const int pos = kept + __popc(m & lt_mask);
       cand[base + pos] = j;
       vals[base + pos] = v;
     }
     kept += __popc(m);
+    if (alen) kept_a += __popc(__ballot_sync(full, keep && k < asplit));
     __syncwarp();
   }
-  if (lane == 0) row_nnz[warp] = kept;
+  if (lane == 0) {
+    row_nnz[warp] = kept;
+    if (alen) alen[warp] = kept_a;
+  }
 }
 
-// copy compacted rows to their final place
-__global__ void __launch_bounds__(256) compact_copy_kernel(const int64_t *cand_ptr, const int32_t *row_nnz, const int64_t *rowptr_chunk,
+// copy compacted rows to their final place.  alen != null: a row is two ascending runs (alen[row] entries, then the rest);
+// they are merged on the way: an entry's final position = its index in its own run + the entries of the other run that
+// sort before it (binary search; the runs share no column).
+__global__ void __launch_bounds__(256) compact_copy_kernel(const int64_t *cand_ptr, const int32_t *row_nnz, const int32_t *alen, const int64_t *rowptr_chunk,
                                                            int64_t nrows, const int32_t *cand, const double *vals, int32_t *cols_out,
                                                            double *vals_out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (row >= nrows) return;
-  int64_t src = cand_ptr[row], dst = rowptr_chunk[row];
-  int L = row_nnz[row];
+  const int64_t src = cand_ptr[row], dst = rowptr_chunk[row];
+  const int L = row_nnz[row];
+  const int KA = alen ? alen[row] : L;
+  if (KA == L) {
+    for (int k = lane; k < L; k += 32) {
+      cols_out[dst + k] = cand[src + k];
+      vals_out[dst + k] = vals[src + k];
+    }
+    return;
+  }
+  const int32_t *A = cand + src, *B = cand + src + KA;
+  const int KB = L - KA;
   for (int k = lane; k < L; k += 32) {
-    cols_out[dst + k] = cand[src + k];
-    vals_out[dst + k] = vals[src + k];
+    const int32_t c = cand[src + k];
+    const bool inA = k < KA;
+    const int32_t *O = inA ? B : A;
+    int lo = 0, hi = inA ? KB : KA;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (O[mid] < c) lo = mid + 1;
+      else hi = mid;
+    }
+    const int pos = (inA ? k : k - KA) + lo;
+    cols_out[dst + pos] = c;
+    vals_out[dst + pos] = vals[src + k];
   }
 }
 
@@ -514,12 +637,12 @@ __global__ void add_offset_kernel(int64_t *a, int64_t n, int64_t off) {
   if (i < n) a[i] += off;
 }
 
-template <int NW>
+template <int NW, int MODEL, bool TS>
 __global__ void diag_kernel(ModelTables T, const uint64_t *up, const uint64_t *dn, int64_t n, double *out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   Bits<NW> u = b_load<NW>(up, i), d = b_load<NW>(dn, i);
-  out[i] = model_hamiltonian<NW>(T, T.combine_2, u, d, u, d);
+  out[i] = model_hamiltonian<NW, MODEL, TS>(T, T.combine_2, u, d, u, d);
 }
 
 // exclusive scan int32 -> int64 offsets (n+1 outputs)
@@ -827,7 +950,33 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   kidx.release();
   K_keys.release();
 
-  ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, run_lo.p, run_hi.p, K_grp.p, nel};
+  // sorted neighbour-group list of every alpha group
+  DevBuf<int64_t> nbr_off;
+  DevBuf<int32_t> nbr, nbr_cnt;
+  SQ_CHECK(nbr_cnt.alloc(nA + 1));
+  SQ_CHECK(nbr_off.alloc(nA + 1));
+  SQ_CUDA(cudaMemsetAsync(nbr_cnt.p, 0, (nA + 1) * sizeof(int32_t), s));
+  nbr_count_kernel<<<nblocks(nA), kThreads, 0, s>>>(run_lo.p, run_hi.p, nA, nel, nbr_cnt.p);
+  SQ_LAUNCH_CHECK();
+  SQ_CHECK(exclusive_scan_i32_to_i64(nbr_cnt.p, nbr_off.p, nA, s));
+  int64_t nbr_total = 0;
+  SQ_CUDA(cudaMemcpy(&nbr_total, nbr_off.p + nA, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SQ_CHECK(nbr.alloc(std::max<int64_t>(nbr_total, 1)));
+  nbr_fill_kernel<<<nblocks(nA), kThreads, 0, s>>>(run_lo.p, run_hi.p, K_grp.p, nA, nel, nbr_off.p, nbr.p);
+  SQ_LAUNCH_CHECK();
+  sort_rows_warp_kernel<<<nblocks(nA, 8), 256, 0, s>>>(nbr_off.p, nbr_cnt.p, nA, nbr.p);
+  SQ_LAUNCH_CHECK();
+  SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
+  if ((int64_t)nel * (T.norb - nel) + 1 > kWarpSortMax) {  // more neighbours than the warp sort handles (large basis sets)
+    sort_rows_block_kernel<<<(int)std::min<int64_t>(nA, 148 * 16), 256, kBlockSortMax * 4, s>>>(nbr_off.p, nbr_cnt.p, nA, nbr.p);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CUDA(cudaStreamSynchronize(s));
+  run_lo.release();
+  run_hi.release();
+  K_grp.release();
+  nbr_cnt.release();
+  ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, nbr_off.p, nbr.p};
   // host copies for the tile lists: alpha-group offsets and (time-reversal only) the row -> entry map
   std::vector<int64_t> gA_host(nA + 1);
   SQ_CUDA(cudaMemcpy(gA_host.data(), gA_off.p, (nA + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -857,10 +1006,15 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       SQ_CHECK(dt.alloc((int64_t)tiles.size()));
       SQ_CUDA(cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
       const unsigned cgrid = (unsigned)std::min<int64_t>((int64_t)tiles.size(), G.sm_count * 16);
-      if (NW == 1 && T.norb <= 32)
-        connect_tile_kernel<NW, false, true><<<cgrid, kConnTile, 0, s>>>(V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr);
-      else
-        connect_tile_kernel<NW, false, false><<<cgrid, kConnTile, 0, s>>>(V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr);
+      const bool w32 = NW == 1 && T.norb <= 32;
+#define SQ_CONN(FILL, ...)                                                                               \
+  do {                                                                                                   \
+    if (w32 && !ts) connect_tile_kernel<NW, FILL, true, true><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);       \
+    else if (w32) connect_tile_kernel<NW, FILL, true, false><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);        \
+    else if (!ts) connect_tile_kernel<NW, FILL, false, true><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);        \
+    else connect_tile_kernel<NW, FILL, false, false><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);                \
+  } while (0)
+      SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr);
       SQ_LAUNCH_CHECK();
       SQ_CUDA(cudaStreamSynchronize(s));
     }
@@ -902,13 +1056,19 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
   SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
 
+  // diagonal of the local rows: read by eval_kernel, kept for Davidson's preconditioner and the projector
+  SQ_CUDA(cudaMalloc(&h->d_diag, std::max<int64_t>(nloc, 1) * sizeof(double)));
+  if (nloc > 0) {
+    SQ_MODEL_DISPATCH(T, (diag_rows_kernel<NW, kModel, kTS><<<nblocks(nloc), kThreads, 0, s>>>(T, h->d_up, h->d_dn, h->d_perm, h->row0, nloc, h->d_diag)));
+    SQ_LAUNCH_CHECK();
+  }
   HM.mark("alloc cols/vals/rowptr");
   // ---- chunks of rows bounded by temp candidates
   const int64_t kChunkCand = 1ll << 27;
   int64_t maxlen = 0;
   double ms_fill = 0, ms_eval = 0;
   int64_t base_nnz = 0;
-  DevBuf<int32_t> cand_tmp, row_nnz;
+  DevBuf<int32_t> cand_tmp, row_nnz, alen;
   DevBuf<double> vals_tmp;
   DevBuf<int64_t> cptr, rptr;
   int64_t r = h->row0;
@@ -947,11 +1107,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     SQ_CHECK(cand_tmp.alloc(tmp_cap));
     SQ_CHECK(vals_tmp.alloc(tmp_cap));
     SQ_CHECK(row_nnz.alloc(rows_cap + 1));
+    SQ_CHECK(alen.alloc(rows_cap + 1));
     SQ_CHECK(cptr.alloc(rows_cap + 1));
     SQ_CHECK(rptr.alloc(rows_cap + 1));
     SQ_CHECK(fill_tiles_dev.alloc(std::max<int64_t>((int64_t)all_tiles.size(), 1)));
     SQ_CUDA(cudaMemcpyAsync(fill_tiles_dev.p, all_tiles.data(), all_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-    SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
   }
   std::vector<cudaEvent_t> evs;
   for (const ChunkPlan &cp : plan) {
@@ -967,29 +1127,29 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     {
       const TileDesc *td = fill_tiles_dev.p + cp.tile_off;
       const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cp.ntiles, G.sm_count * 16));
-      if (NW == 1 && T.norb <= 32)
-        connect_tile_kernel<NW, true, true><<<cgrid, kConnTile, 0, s>>>(V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p);
-      else
-        connect_tile_kernel<NW, true, false><<<cgrid, kConnTile, 0, s>>>(V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p);
+      const bool w32 = NW == 1 && T.norb <= 32;
+      SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p);
       SQ_LAUNCH_CHECK();
     }
-    sort_rows_warp_kernel<<<nblocks(nr, 8), 256, 0, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
-    SQ_LAUNCH_CHECK();
-    if (cp.ml > kWarpSortMax) {
-      int smem = (int)std::min<int64_t>(cp.ml, kBlockSortMax) * 4;
-      sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
+    if (ts) {  // time-reversed partners in the entry list: arbitrary candidate order, duplicates -> sort the rows
+      sort_rows_warp_kernel<<<nblocks(nr, 8), 256, 0, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
       SQ_LAUNCH_CHECK();
+      if (cp.ml > kWarpSortMax) {
+        int smem = (int)std::min<int64_t>(cp.ml, kBlockSortMax) * 4;
+        sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
+        SQ_LAUNCH_CHECK();
+      }
     }
     cudaEventRecord(e1, s);
     SQ_CUDA(cudaMemsetAsync(row_nnz.p, 0, (nr + 1) * sizeof(int32_t), s));
     int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
-    eval_kernel<NW><<<nblocks(nr * 32), 256, c2bytes, s>>>(T, h->d_up, h->d_dn, h->d_perm, r, r_end, cptr.p, cand_count.p + r,
-                                                           cand_tmp.p, vals_tmp.p, row_nnz.p);
+    SQ_MODEL_DISPATCH(T, (eval_kernel<NW, kModel, kTS><<<nblocks(nr * 32), 256, c2bytes, s>>>(T, h->d_up, h->d_dn, h->d_perm, h->d_diag, h->row0, r, r_end, cptr.p,
+                                                                                              cand_count.p + r, cand_tmp.p, vals_tmp.p, row_nnz.p, ts ? nullptr : alen.p)));
     SQ_LAUNCH_CHECK();
     SQ_CHECK(exclusive_scan_i32_to_i64_async(row_nnz.p, rptr.p, nr, scan_tmp.p, scan_bytes, s));
     add_offset_dev_kernel<<<nblocks(nr + 1), kThreads, 0, s>>>(rptr.p, nr + 1, base_dev.p);
     SQ_LAUNCH_CHECK();
-    compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
+    compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, ts ? nullptr : alen.p, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaMemcpyAsync(h->d_rowptr + (r - h->row0), rptr.p, (nr + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     set_scalar_kernel<<<1, 1, 0, s>>>(base_dev.p, rptr.p + nr);
@@ -1105,8 +1265,8 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
     else split_dets_kernel<2><<<nblocks(n), kThreads, 0, s>>>(raw.p, which == 0 ? up.p : dn.p, n, bad.p, 0, 0);
     SQ_LAUNCH_CHECK();
   }
-  if (NW == 1) diag_kernel<1><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p);
-  else diag_kernel<2><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p);
+  if (NW == 1) SQ_MODEL_DISPATCH(h->T, (diag_kernel<1, kModel, kTS><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p)));
+  else SQ_MODEL_DISPATCH(h->T, (diag_kernel<2, kModel, kTS><<<nblocks(n), kThreads, 0, s>>>(h->T, up.p, dn.p, n, out.p)));
   SQ_LAUNCH_CHECK();
   SQ_CUDA(cudaMemcpyAsync(diag, out.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   SQ_CUDA(cudaStreamSynchronize(s));

@@ -119,15 +119,28 @@ __device__ __forceinline__ int b_ctz(const Bits<NW> &a) {
 }
 template <int NW>
 __host__ __device__ __forceinline__ bool b_test(const Bits<NW> &a, int k) {
-  return (a.w[k >> 6] >> (k & 63)) & 1ull;
+  if constexpr (NW == 1) return (a.w[0] >> k) & 1ull;  // no dynamic word index: keeps the string in registers
+  else return ((k < 64 ? a.w[0] : a.w[1]) >> (k & 63)) & 1ull;
 }
 template <int NW>
 __host__ __device__ __forceinline__ void b_clear(Bits<NW> &a, int k) {
-  a.w[k >> 6] &= ~(1ull << (k & 63));
+  if constexpr (NW == 1) {
+    a.w[0] &= ~(1ull << k);
+  } else {
+    const uint64_t m = ~(1ull << (k & 63));
+    if (k < 64) a.w[0] &= m;
+    else a.w[1] &= m;
+  }
 }
 template <int NW>
 __host__ __device__ __forceinline__ void b_set(Bits<NW> &a, int k) {
-  a.w[k >> 6] |= (1ull << (k & 63));
+  if constexpr (NW == 1) {
+    a.w[0] |= (1ull << k);
+  } else {
+    const uint64_t m = 1ull << (k & 63);
+    if (k < 64) a.w[0] |= m;
+    else a.w[1] |= m;
+  }
 }
 // clear lowest set bit
 template <int NW>

@@ -94,7 +94,7 @@ struct ChemCtx {
 };
 
 template <int NW>
-__device__ double chem_one_body(const ChemCtx &C, const Bits<NW> &up, const Bits<NW> &dn) {
+__device__ __forceinline__ double chem_one_body(const ChemCtx &C, const Bits<NW> &up, const Bits<NW> &dn) {
   double energy = 0.0;
   Bits<NW> det = up;
   while (!b_is_zero(det)) {
@@ -116,7 +116,7 @@ __device__ double chem_one_body(const ChemCtx &C, const Bits<NW> &up, const Bits
 }
 
 template <int NW>
-__device__ double chem_two_body(const ChemCtx &C, const Bits<NW> &up, const Bits<NW> &dn) {
+__device__ __forceinline__ double chem_two_body(const ChemCtx &C, const Bits<NW> &up, const Bits<NW> &dn) {
   double exchange = 0.0, direct = 0.0;
   // exchange: up pairs i<j ascending
   Bits<NW> di = up;
@@ -180,12 +180,17 @@ __device__ double chem_two_body(const ChemCtx &C, const Bits<NW> &up, const Bits
 }
 
 template <int NW>
-__device__ double chem_single(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
+__device__ __forceinline__ double chem_single(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
   // one_body_single + two_body_single (chemistry.f90:1439-1480,1845-1930)
   bool up_moves = !b_eq(iu, ju);
-  const Bits<NW> &same_i = up_moves ? iu : id;
-  const Bits<NW> &same_j = up_moves ? ju : jd;
-  const Bits<NW> &other = up_moves ? id : iu;
+  // selected by value (word-wise selects): a reference picked at run time would force the strings into local memory
+  Bits<NW> same_i, same_j, other;
+#pragma unroll
+  for (int k = 0; k < NW; k++) {
+    same_i.w[k] = up_moves ? iu.w[k] : id.w[k];
+    same_j.w[k] = up_moves ? ju.w[k] : jd.w[k];
+    other.w[k] = up_moves ? id.w[k] : iu.w[k];
+  }
   int i_bit = b_ctz(b_andnot(same_i, same_j)) + 1, j_bit = b_ctz(b_andnot(same_j, same_i)) + 1;
   int pf = permutation_factor(same_i, same_j);
   double one_body = pf * C.I(i_bit, j_bit, C.n1, C.n1);
@@ -207,7 +212,7 @@ __device__ double chem_single(const ChemCtx &C, const Bits<NW> &iu, const Bits<N
 }
 
 template <int NW>
-__device__ double chem_double(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
+__device__ __forceinline__ double chem_double(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
   int gamma, fi, si, fj, sj;
   if (b_eq(iu, ju)) {
     permutation_factor2(id, jd, gamma, fi, si, fj, sj);
@@ -225,7 +230,7 @@ __device__ double chem_double(const ChemCtx &C, const Bits<NW> &iu, const Bits<N
 }
 
 template <int NW>
-__device__ double chem_hamiltonian_level(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju,
+__device__ __forceinline__ double chem_hamiltonian_level(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju,
                                          const Bits<NW> &jd, int level) {
   if (level == 0) {
     double e1 = chem_one_body(C, iu, id);
@@ -240,7 +245,7 @@ __device__ double chem_hamiltonian_level(const ChemCtx &C, const Bits<NW> &iu, c
 }
 
 template <int NW>
-__device__ double chem_hamiltonian_time_sym(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju,
+__device__ __forceinline__ double chem_hamiltonian_time_sym(const ChemCtx &C, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju,
                                             const Bits<NW> &jd) {
   double m1 = 0.0, m2 = 0.0, norm_ketinv = 1.0, norm_bra = 1.0;
   bool check = true;
@@ -270,17 +275,22 @@ struct HegCtx {
   int n_dim;
   double length_cell;
   __device__ __forceinline__ double k(int orb1, int d) const { return kv[(orb1 - 1) * n_dim + d]; }
+  // n_dim is 2 or 3: loops are written over 3 fixed components with the third one guarded, so nothing is indexed dynamically
   __device__ __forceinline__ double ksum2(int p) const {
     double s = 0.0;
-    for (int d = 0; d < n_dim; d++) s += k(p, d) * k(p, d);
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      if (d < n_dim) s += k(p, d) * k(p, d);
     return s;
   }
   __device__ __forceinline__ double kdiff2(int p, int q) const {
     double s = 0.0;
-    for (int d = 0; d < n_dim; d++) {
-      double t = k(p, d) - k(q, d);
-      s += t * t;
-    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      if (d < n_dim) {
+        double t = k(p, d) - k(q, d);
+        s += t * t;
+      }
     return s;
   }
 };
@@ -300,7 +310,7 @@ __device__ __forceinline__ int heg_gamma_exp(const Bits<NW> &det, const Bits<NW>
 }
 
 template <int NW>
-__device__ double heg_hamiltonian(const HegCtx &H, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
+__device__ __forceinline__ double heg_hamiltonian(const HegCtx &H, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
   const double FOUR_PI = 4.0 * 3.14159265358979323846264338327950288;
   const double EPSILON = 1.0e-15;
   double L3 = H.length_cell * H.length_cell * H.length_cell;
@@ -341,24 +351,34 @@ __device__ double heg_hamiltonian(const HegCtx &H, const Bits<NW> &iu, const Bit
   bool pset = false, qset = false, sset = false;
   int orb_p = 0, orb_q = 0, orb_s = 0;
   for (int spin = 0; spin < 2; spin++) {
-    Bits<NW> e = spin == 0 ? eu : ed;
-    const Bits<NW> &di = spin == 0 ? iu : id;
+    Bits<NW> e, di;
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+      e.w[k] = spin == 0 ? eu.w[k] : ed.w[k];
+      di.w[k] = spin == 0 ? iu.w[k] : id.w[k];
+    }
     while (!b_is_zero(e)) {
       int o = b_ctz(e);
       b_clear_lowest(e);
       int orb = o + 1;
       if (b_test(di, o)) {
-        for (int d = 0; d < H.n_dim; d++) mom[d] = mom[d] - H.k(orb, d);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+          if (d < H.n_dim) mom[d] = mom[d] - H.k(orb, d);
         if (!pset) { orb_p = orb; pset = true; }
       } else {
-        for (int d = 0; d < H.n_dim; d++) mom[d] = mom[d] + H.k(orb, d);
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+          if (d < H.n_dim) mom[d] = mom[d] + H.k(orb, d);
         if (!qset) { orb_q = orb; qset = true; }
         else if (!sset) { orb_s = orb; sset = true; }
       }
     }
   }
   double m2 = 0.0;
-  for (int d = 0; d < H.n_dim; d++) m2 += mom[d] * mom[d];
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    if (d < H.n_dim) m2 += mom[d] * mom[d];
   if (m2 * (H.length_cell * H.length_cell) > EPSILON) return 0.0;
   double pot = FOUR_PI / H.kdiff2(orb_p, orb_q);
   if (n_eu != 2) pot = pot - FOUR_PI / H.kdiff2(orb_p, orb_s);
@@ -377,7 +397,7 @@ struct HubCtx {
   int l_x, l_y, nup, ndn;
 };
 template <int NW>
-__device__ double hub_hamiltonian(const HubCtx &H, const Bits<NW> &ub, const Bits<NW> &db, const Bits<NW> &uk, const Bits<NW> &dk) {
+__device__ __forceinline__ double hub_hamiltonian(const HubCtx &H, const Bits<NW> &ub, const Bits<NW> &db, const Bits<NW> &uk, const Bits<NW> &dk) {
   if (b_eq(ub, uk) && b_eq(db, dk)) {
     double me = H.ubyn * H.nup * H.ndn;
     Bits<NW> d = ub;
@@ -404,18 +424,23 @@ __device__ double hub_hamiltonian(const HubCtx &H, const Bits<NW> &ub, const Bit
 }
 
 // ---------------------------------------------------------------------------
-// model dispatch: hamiltonian(up1,dn1,up2,dn2) of chemistry.f90:10273,
-// heg.f90:3968, semistoch.f90:2234.  c2_smem: optional shared-memory copy of combine_2.
+// hamiltonian(up1,dn1,up2,dn2) of chemistry.f90:10273, heg.f90:3968, semistoch.f90:2234, specialised at COMPILE time on
+// the model and on time-reversal symmetry: every kernel that evaluates elements is instantiated per <NW, MODEL, TS> and
+// carries only its own model's code (no runtime switch inside a kernel; the host picks the instantiation once per call
+// with SQ_MODEL_DISPATCH).  c2: combine_2, normally the shared-memory copy.
 // ---------------------------------------------------------------------------
-template <int NW>
-__device__ __forceinline__ double model_hamiltonian(const ModelTables &T, const int32_t *c2, const Bits<NW> &iu,
-                                                    const Bits<NW> &id, const Bits<NW> &ju, const Bits<NW> &jd) {
-  if (T.model == MODEL_CHEM) {
+template <int NW, int MODEL, bool TS>
+__device__ __forceinline__ double model_hamiltonian(const ModelTables &T, const int32_t *c2, const Bits<NW> &iu, const Bits<NW> &id, const Bits<NW> &ju,
+                                                    const Bits<NW> &jd) {
+  if constexpr (MODEL == MODEL_CHEM) {
     ChemCtx C{T.integrals, c2, T.norb + 1, T.enuc, T.sqrt2, T.sqrt2inv, T.z};
-    if (T.time_sym) return chem_hamiltonian_time_sym(C, iu, id, ju, jd);
-    int lvl = excitation_level(iu, id, ju, jd);
-    return lvl >= 0 ? chem_hamiltonian_level(C, iu, id, ju, jd, lvl) : 0.0;
-  } else if (T.model == MODEL_HEG) {
+    if constexpr (TS) {
+      return chem_hamiltonian_time_sym(C, iu, id, ju, jd);
+    } else {
+      int lvl = excitation_level(iu, id, ju, jd);
+      return lvl >= 0 ? chem_hamiltonian_level(C, iu, id, ju, jd, lvl) : 0.0;
+    }
+  } else if constexpr (MODEL == MODEL_HEG) {
     HegCtx H{T.k_vectors, T.n_dim, T.length_cell};
     int lvl = excitation_level(iu, id, ju, jd);
     return lvl >= 0 ? heg_hamiltonian(H, iu, id, ju, jd) : 0.0;
@@ -424,5 +449,19 @@ __device__ __forceinline__ double model_hamiltonian(const ModelTables &T, const 
     return hub_hamiltonian(H, iu, id, ju, jd);
   }
 }
+
+// host: run `call` with the compile-time constants kModel / kTS of the system described by T
+#define SQ_MODEL_DISPATCH(T, call)                                                          \
+  do {                                                                                      \
+    if ((T).model == sqmc::MODEL_CHEM && (T).time_sym) {                                    \
+      constexpr int kModel = sqmc::MODEL_CHEM; constexpr bool kTS = true; call;             \
+    } else if ((T).model == sqmc::MODEL_CHEM) {                                             \
+      constexpr int kModel = sqmc::MODEL_CHEM; constexpr bool kTS = false; call;            \
+    } else if ((T).model == sqmc::MODEL_HEG) {                                              \
+      constexpr int kModel = sqmc::MODEL_HEG; constexpr bool kTS = false; call;             \
+    } else {                                                                                \
+      constexpr int kModel = sqmc::MODEL_HUBBARDK; constexpr bool kTS = false; call;        \
+    }                                                                                       \
+  } while (0)
 
 }  // namespace sqmc

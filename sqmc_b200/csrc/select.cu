@@ -121,14 +121,14 @@ __device__ __forceinline__ int nth_set(const uint8_t *list, int k) { return list
 
 // one warp per determinant; FILL=false counts, FILL=true writes (up,dn) of the selected determinants at out_ptr[i];
 // VALS additionally writes H(selected, i) * c_i, the numerator contributions of the second-order correction (pt2 below)
-template <int NW, bool FILL, bool VALS>
+template <int NW, bool FILL, bool VALS, int MODEL, bool TS>
 __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_begin, int64_t i_end, int32_t *counts, const int64_t *out_ptr,
                                                      uint64_t *out_up, uint64_t *out_dn, double *out_val) {
   __shared__ uint8_t s_occ[4][2][kSelMaxOrb], s_virt[4][2][kSelMaxOrb];
   extern __shared__ int32_t c2s[];
   const ModelTables &T = S.T;
   const int32_t *c2 = T.combine_2;
-  if (T.model == MODEL_CHEM) {
+  if (MODEL == MODEL_CHEM) {
     const int n1 = T.norb + 1;
     for (int k = threadIdx.x; k < n1 * n1; k += blockDim.x) c2s[k] = T.combine_2[k];
     __syncthreads();
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
   const Bits<NW> u = b_load<NW>(S.up, i), d = b_load<NW>(S.dn, i);
   const double cs = S.coeffs[i], c = fabs(cs), minH = S.min_H[i];
   const int norb = T.norb;
-  const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
+  constexpr bool ts = TS;  // time-reversal symmetrised determinants (chem only)
   int64_t base = FILL ? out_ptr[i - i_begin] : 0;
   int cnt = 0;
   // val = determinant-level element (VALS only): under time-reversal symmetry only this contribution to the symmetrised
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
       return b_eq(u, nd) && b_eq(d, nu);
     };
     // ---- singles (chem only)
-    if (T.model == MODEL_CHEM) {
+    if constexpr (MODEL == MODEL_CHEM) {
       for (int spin = 0; spin < 2; spin++) {
         const uint8_t *occ = spin == 0 ? occ_u : occ_d, *vir = spin == 0 ? vir_u : vir_d;
         const int no = spin == 0 ? nu_ : nd_, nv = spin == 0 ? nvu : nvd;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
         }
       }
     }
-    const bool use_hb = (T.model == MODEL_CHEM) && S.hb_val[0] != nullptr;
+    const bool use_hb = (MODEL == MODEL_CHEM) && S.hb_val[0] != nullptr;
     if (use_hb) {
       // ---- doubles from the heat-bath tables: one lane per hole pair finds its table range, then the warp walks it
       const int nss_u = nu_ * (nu_ - 1) / 2, nss_d = nd_ * (nd_ - 1) / 2, nos = nu_ * nd_;
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
           Bits<NW> &tgt = spin == 0 ? nu : nd;
           b_clear(tgt, occ[a]); b_clear(tgt, occ[bq]); b_set(tgt, vir[r]); b_set(tgt, vir[sq]);
           if (!ts_excluded(nu, nd)) {
-            if (T.model == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
+            if constexpr (MODEL == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
             else val = heg_hamiltonian(Hg, u, d, nu, nd);
             const double me = fabs(val);
-            keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
+            keep = (me > eps) && (MODEL != MODEL_CHEM || !(me > minH));
           }
         }
         emit(keep, nu, nd, val);
@@ -318,10 +318,10 @@ __global__ void __launch_bounds__(128) select_kernel(SelCtx<NW> S, int64_t i_beg
           b_clear(nu, occ_u[fu / nvu]); b_set(nu, vir_u[fu % nvu]);
           b_clear(nd, occ_d[fd / nvd]); b_set(nd, vir_d[fd % nvd]);
           if (!ts_excluded(nu, nd)) {
-            if (T.model == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
+            if constexpr (MODEL == MODEL_CHEM) val = chem_hamiltonian_level(C, u, d, nu, nd, 2);
             else val = heg_hamiltonian(Hg, u, d, nu, nd);
             const double me = fabs(val);
-            keep = (me > eps) && (T.model != MODEL_CHEM || !(me > minH));
+            keep = (me > eps) && (MODEL != MODEL_CHEM || !(me > minH));
           }
         }
         emit(keep, nu, nd, val);
@@ -522,7 +522,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
   SQ_CHECK(counts.alloc(nd + 1));
   SQ_CUDA(cudaMemsetAsync(counts.p, 0, (nd + 1) * sizeof(int32_t), s));
   if (nd > 0) {
-    select_kernel<NW, false, false><<<(unsigned)div_up(nd * 32, 128), 128, c2bytes, s>>>(S, 0, nd, counts.p, nullptr, nullptr, nullptr, nullptr);
+    SQ_MODEL_DISPATCH(T, (select_kernel<NW, false, false, kModel, kTS><<<(unsigned)div_up(nd * 32, 128), 128, c2bytes, s>>>(S, 0, nd, counts.p, nullptr, nullptr, nullptr, nullptr)));
     SQ_LAUNCH_CHECK();
   }
   std::vector<int32_t> hc(nd + 1);
@@ -550,7 +550,7 @@ static int select_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, cons
     std::vector<int64_t> hp(prefix.begin() + i0, prefix.begin() + i1 + 1);
     for (auto &v : hp) v -= prefix[i0];
     SQ_CUDA(cudaMemcpyAsync(optr.p, hp.data(), hp.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    select_kernel<NW, true, false><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, nullptr);
+    SQ_MODEL_DISPATCH(T, (select_kernel<NW, true, false, kModel, kTS><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, nullptr)));
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaStreamSynchronize(s));
     int64_t mu = 0;
@@ -618,7 +618,7 @@ __global__ void fill_double_kernel(double *a, int64_t n, double v) {
   if (i < n) a[i] = v;
 }
 __global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
-template <int NW>
+template <int NW, int MODEL, bool TS>
 __global__ void pt_term_kernel(ModelTables T, const uint64_t *a, const uint64_t *b, const double *num, const int32_t *external, double e_var,
                                double *term, int64_t m) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -626,7 +626,7 @@ __global__ void pt_term_kernel(ModelTables T, const uint64_t *a, const uint64_t 
   double r = 0.0;
   if (external[t]) {
     const Bits<NW> u = b_load<NW>(a, t), d = b_load<NW>(b, t);
-    const double haa = model_hamiltonian<NW>(T, T.combine_2, u, d, u, d);
+    const double haa = model_hamiltonian<NW, MODEL, TS>(T, T.combine_2, u, d, u, d);
     r = num[t] * num[t] / (e_var - haa);
   }
   term[t] = r;
@@ -723,7 +723,7 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   SQ_CHECK(counts.alloc(n + 1));
   SQ_CUDA(cudaMemsetAsync(counts.p, 0, (n + 1) * sizeof(int32_t), s));
   if (n > 0) {
-    select_kernel<NW, false, false><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr, nullptr);
+    SQ_MODEL_DISPATCH(T, (select_kernel<NW, false, false, kModel, kTS><<<(unsigned)div_up(n * 32, 128), 128, c2bytes, s>>>(S, 0, n, counts.p, nullptr, nullptr, nullptr, nullptr)));
     SQ_LAUNCH_CHECK();
   }
   std::vector<int32_t> hc(n + 1);
@@ -754,7 +754,7 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
     std::vector<int64_t> hp(prefix.begin() + i0, prefix.begin() + i1 + 1);
     for (auto &x : hp) x -= prefix[i0];
     SQ_CUDA(cudaMemcpyAsync(optr.p, hp.data(), hp.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    select_kernel<NW, true, true><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, cv.p);
+    SQ_MODEL_DISPATCH(T, (select_kernel<NW, true, true, kModel, kTS><<<(unsigned)div_up((i1 - i0) * 32, 128), 128, c2bytes, s>>>(S, i0, i1, nullptr, optr.p, ca.p, cb.p, cv.p)));
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaStreamSynchronize(s));
     int64_t mu = 0;
@@ -806,7 +806,7 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
     SQ_LAUNCH_CHECK();
     not_in_list_kernel<NW><<<g, 256, 0, s>>>(fa.p, fb.p, sup.p, sdn.p, n_all, ext.p, nf);  // 0 for variational determinants
     SQ_LAUNCH_CHECK();
-    pt_term_kernel<NW><<<g, 256, 0, s>>>(T, fa.p, fb.p, fv.p, ext.p, var_energy, term.p, nf);
+    SQ_MODEL_DISPATCH(T, (pt_term_kernel<NW, kModel, kTS><<<g, 256, 0, s>>>(T, fa.p, fb.p, fv.p, ext.p, var_energy, term.p, nf)));
     SQ_LAUNCH_CHECK();
     size_t tb = 0;
     cub::DeviceReduce::Sum(nullptr, tb, term.p, total.p, (int)nf, s);
