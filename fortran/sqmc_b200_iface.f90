@@ -102,6 +102,39 @@ module sqmc_b200_iface
       integer(c_int), value :: max_iter, ritz_cap
       integer(c_int) :: n_iter, n_ritz
     end function
+    integer(c_int) function sqmc_b200_set_ownership(h, owner_of_row, n_owned) bind(C, name="sqmc_b200_set_ownership")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int32_t) :: owner_of_row(*)          ! rank (0-based) owning each determinant of the list (get_det_owner)
+      integer(c_int64_t) :: n_owned
+    end function
+    integer(c_int) function sqmc_b200_matvec_local(h, x_local, y_local, nvec, ld_local) bind(C, name="sqmc_b200_matvec_local")
+      import :: c_int, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: h
+      real(c_double) :: x_local(*), y_local(*)
+      integer(c_int), value :: nvec
+      integer(c_int64_t), value :: ld_local
+    end function
+    integer(c_int) function sqmc_b200_projector_local(h, tau, e_trial, w_local, deltaw_local) bind(C, name="sqmc_b200_projector_local")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: h
+      real(c_double), value :: tau, e_trial
+      real(c_double) :: w_local(*), deltaw_local(*)
+    end function
+    integer(c_int) function sqmc_b200_davidson_local(h, n_states, v0, evecs, evals, tol, max_vec, n_matvec, ritz_log, ritz_cap, n_ritz) &
+        bind(C, name="sqmc_b200_davidson_local")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: h, v0, ritz_log          ! v0 / ritz_log may be c_null_ptr
+      integer(c_int), value :: n_states, max_vec, ritz_cap
+      real(c_double) :: evecs(*), evals(*)
+      real(c_double), value :: tol
+      integer(c_int) :: n_matvec, n_ritz
+    end function
+    integer(c_int) function sqmc_b200_register_host(ptr, bytes) bind(C, name="sqmc_b200_register_host")
+      import :: c_int, c_int64_t, c_ptr
+      type(c_ptr), value :: ptr
+      integer(c_int64_t), value :: bytes
+    end function
   end interface
 
 contains
@@ -227,6 +260,54 @@ contains
     lowest_eigenvalue = eig3(1)
     if (present(highest_eigenvalue)) highest_eigenvalue = eig3(2)
     if (present(second_lowest_eigenvalue)) second_lowest_eigenvalue = eig3(3)
+  end subroutine
+
+  ! ---- the MPI data distribution of the reference: slices in, slices out --------------------------------------------
+  ! owner(i) = get_det_owner(dets_up(i), dets_dn(i)) (mpi_routines.f90:419) for the list last passed to b200_build_h
+  subroutine b200_set_ownership(h, owner, my_n)
+    type(c_ptr), intent(in) :: h
+    integer, intent(in) :: owner(:)
+    integer(c_int64_t), intent(out) :: my_n
+    integer(c_int32_t), allocatable :: o(:)
+    allocate(o(size(owner)))
+    o = int(owner, c_int32_t)
+    call b200_check(sqmc_b200_set_ownership(h, o, my_n))
+  end subroutine
+
+  ! fast_sparse_matrix_multiply_local_band + mpi_redscatt_real_dparray (do_walk.f90:2259-2260): deltaw(1:my_nimp) on return
+  subroutine b200_matvec_local(h, vector_local, answer_local)
+    type(c_ptr), intent(in) :: h
+    real(c_double), intent(in) :: vector_local(:)
+    real(c_double), intent(out) :: answer_local(:)
+    call b200_check(sqmc_b200_matvec_local(h, vector_local, answer_local, 1_c_int, int(max(size(vector_local), 1), c_int64_t)))
+  end subroutine
+
+  ! the same + e_trial*tau*my_imp_wt (do_walk.f90:2290)
+  subroutine b200_projector_local(h, tau, e_trial, my_imp_wt, deltaw_local)
+    type(c_ptr), intent(in) :: h
+    real(c_double), intent(in) :: tau, e_trial, my_imp_wt(:)
+    real(c_double), intent(out) :: deltaw_local(:)
+    call b200_check(sqmc_b200_projector_local(h, tau, e_trial, my_imp_wt, deltaw_local))
+  end subroutine
+
+  ! davidson_sparse_mpi2 (more_tools.f90:2525): final_vector(local_det_map%ndets, n_states)
+  subroutine b200_davidson_local(h, n_states, final_vector, lowest_eigenvalues, initial_vector)
+    type(c_ptr), intent(in) :: h
+    integer, intent(in) :: n_states
+    real(c_double), intent(out) :: final_vector(:, :), lowest_eigenvalues(:)
+    real(c_double), intent(in), optional, target :: initial_vector(:, :)
+    integer(c_int) :: nmv, nlog
+    type(c_ptr) :: v0
+    v0 = c_null_ptr
+    if (present(initial_vector)) v0 = c_loc(initial_vector)
+    call b200_check(sqmc_b200_davidson_local(h, int(n_states, c_int), v0, final_vector, lowest_eigenvalues, 1.e-10_c_double, &
+                    50_c_int, nmv, c_null_ptr, 0_c_int, nlog))
+  end subroutine
+
+  ! page-lock walk_wt / deltaw once: the projector moves them across PCIe every Monte Carlo step
+  subroutine b200_register_host(array)
+    real(c_double), intent(in), target :: array(:)
+    call b200_check(sqmc_b200_register_host(c_loc(array), int(size(array), c_int64_t) * 8_c_int64_t))
   end subroutine
 
   subroutine b200_free(h)

@@ -11,6 +11,7 @@
 //   davidson_sparse                                more_tools.f90:2018
 //   deterministic projector step                   do_walk.f90:2255-2325
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -174,7 +175,37 @@ inline void second_order_pt(model_system &S, int64_t ndets, const void *dets_up,
                             rk eps_pt, rk &delta_e_2pt, int64_t &ndets_connected) {
   check(sqmc_b200_pt2(S.h, ndets, dets_up, dets_dn, wts.data(), var_energy, eps_pt, &delta_e_2pt, &ndets_connected));
 }
-// storage-order hint for H.v (0 = plain rows, 2/4/8 = column-merged bundles); no reference counterpart
+// ---- the reference's MPI data distribution: every rank passes / receives the slice of the determinants it owns ----
+// set once per determinant list: owner_of_row(i) = get_det_owner(dets_up(i), dets_dn(i)) (mpi_routines.f90:419); returns my_nimp
+inline int64_t set_ownership(model_system &S, const std::vector<int32_t> &owner_of_row) {
+  if ((i8b)owner_of_row.size() != S.n) throw std::runtime_error("sqmc_b200: owner_of_row must have n entries");
+  int64_t mine = 0;
+  check(sqmc_b200_set_ownership(S.h, owner_of_row.data(), &mine));
+  return mine;
+}
+// fast_sparse_matrix_multiply_local_band(n_imp, ..., vector = walk_wt(my_locations_of_imp_dets(1:my_nimp)), answer = deltaw)
+// followed by mpi_redscatt_real_dparray(deltaw(1:n_imp), imp_core_mask)   (do_walk.f90:2259-2260, more_tools.f90:3562, mpi_routines.f90:1592):
+// on return answer(1:my_nimp) holds this rank's rows of H . vector
+inline void fast_sparse_matrix_multiply_local_band(model_system &S, const std::vector<rk> &vector_local, std::vector<rk> &answer_local) {
+  answer_local.assign(vector_local.size(), 0.0);
+  check(sqmc_b200_matvec_local(S.h, vector_local.data(), answer_local.data(), 1, (i8b)std::max<size_t>(vector_local.size(), 1)));
+}
+// the same + e_trial*tau*my_imp_wt (do_walk.f90:2290): deltaw(1:my_nimp)
+inline void deterministic_projector_step_local(model_system &S, rk tau, rk e_trial, const std::vector<rk> &my_imp_wt, std::vector<rk> &deltaw_local) {
+  deltaw_local.assign(my_imp_wt.size(), 0.0);
+  check(sqmc_b200_projector_local(S.h, tau, e_trial, my_imp_wt.data(), deltaw_local.data()));
+}
+// davidson_sparse_mpi2(remote_det_map, local_det_map, n_states, final_vector, lowest_eigenvalues, ..., initial_vector)
+// (more_tools.f90:2525): vectors are local_det_map%ndets x n_states
+inline void davidson_sparse_mpi2(model_system &S, int64_t ndets_local, int n_states, std::vector<rk> &final_vector, std::vector<rk> &lowest_eigenvalues,
+                                 const std::vector<rk> *initial_vector = nullptr) {
+  final_vector.assign((size_t)std::max<int64_t>(ndets_local, 1) * n_states, 0.0);
+  lowest_eigenvalues.assign(n_states, 0.0);
+  int nmv = 0, nlog = 0;
+  check(sqmc_b200_davidson_local(S.h, n_states, initial_vector ? initial_vector->data() : nullptr, final_vector.data(), lowest_eigenvalues.data(), 1.e-10, 50,
+                                 &nmv, nullptr, 0, &nlog));
+}
+// storage-order hint for H.v (0 = plain rows, 2/4 = column-merged bundles); no reference counterpart
 inline void set_row_bundle(model_system &S, int rows_per_bundle) { check(sqmc_b200_set_row_bundle(S.h, rows_per_bundle)); }
 inline void deterministic_projector_step(model_system &S, rk tau, rk e_trial, const std::vector<rk> &imp_wt, std::vector<rk> &deltaw) {
   deltaw.assign(S.n, 0.0);

@@ -94,7 +94,10 @@ int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const voi
  * global list under MPI; the library shards rows itself).  ndet_old mirrors
  * sparse_ham%ndet (incremental reuse, chemistry.f90:7769-7843): rows
  * 1..ndet_old are promised unchanged since the previous call on this handle.
- * The resulting matrix is identical to a from-scratch build.
+ * When the previous matrix is still resident and unscaled (one rank, chem without time-reversal symmetry or heg) it is
+ * kept and only pairs involving a new determinant are generated and evaluated; otherwise the matrix is rebuilt.
+ * Either way the result is identical to a from-scratch build;
+ * sqmc_b200_last_build_incremental tells which path the last call took (1 = extended, 0 = rebuilt).
  * nnz_upper_out: stored entries of the reference's upper-triangular format
  * (what its log prints as "# of nonzero elem in H"), summed over ranks. */
 int sqmc_b200_build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t ndet_old,
@@ -109,6 +112,7 @@ int sqmc_b200_export_upper(sqmc_b200_handle *h, int64_t *H_nonzero_elements, int
  * read path, do_walk.f90:883-951): n rows, upper triangular, 1-based. */
 int sqmc_b200_import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *H_nonzero_elements, const int64_t *H_indices,
                            const double *H_values);
+int sqmc_b200_last_build_incremental(sqmc_b200_handle *h);
 int sqmc_b200_nnz(sqmc_b200_handle *h, int64_t *n, int64_t *nnz_upper, int64_t *nnz_full);
 int sqmc_b200_local_rows(sqmc_b200_handle *h, int64_t *n_local_rows, int64_t *nnz_full_local);
 /* One FULL row (both triangles) of the resident matrix in the caller's numbering: 1-based row in,

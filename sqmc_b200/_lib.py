@@ -21,7 +21,7 @@ SYMBOLS = [
     "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
     "sqmc_b200_hci_new_dets", "sqmc_b200_set_hf_to_psit",
     "sqmc_b200_set_ownership", "sqmc_b200_matvec_local", "sqmc_b200_projector_local", "sqmc_b200_davidson_local",
-    "sqmc_b200_register_host", "sqmc_b200_unregister_host", "sqmc_b200_exchange_mode",
+    "sqmc_b200_last_build_incremental", "sqmc_b200_register_host", "sqmc_b200_unregister_host", "sqmc_b200_exchange_mode",
 ]
 
 
@@ -83,6 +83,7 @@ def load():
     L.sqmc_b200_register_host.argtypes = [vp, i64]
     L.sqmc_b200_unregister_host.argtypes = [vp]
     L.sqmc_b200_exchange_mode.argtypes = [vp]
+    L.sqmc_b200_last_build_incremental.argtypes = [vp]
     _lib = L
     return L
 

@@ -109,6 +109,10 @@ class SparseHamiltonian:
         self.n = len(up)
         return nnz.value
 
+    def last_build_incremental(self):
+        """True when the last build extended the previous matrix (sparse_ham%ndet reuse, chemistry.f90:7769-7843)."""
+        return self._L.sqmc_b200_last_build_incremental(self._h) == 1
+
     def import_upper(self, H_nonzero_elements, H_indices, H_values):
         cnt = np.ascontiguousarray(H_nonzero_elements, dtype=np.int64)
         idx = np.ascontiguousarray(H_indices, dtype=np.int64)

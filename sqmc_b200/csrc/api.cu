@@ -231,6 +231,7 @@ int sqmc_b200_system_hubbardk(sqmc_b200_handle **out, int l_x, int l_y, const in
 int sqmc_b200_free(sqmc_b200_handle *h) {
   if (!h) return 0;
   free_matrix(h);
+  matrix_arrays_release(h);
   p2p_release(h);
   if (h->d_orbsym) cudaFree(h->d_orbsym);
   for (int k = 0; k < 2; k++) {
@@ -468,6 +469,7 @@ int sqmc_b200_unregister_host(void *ptr) {
   if (e != cudaSuccess) { cudaGetLastError(); set_error("unregister_host: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
+int sqmc_b200_last_build_incremental(sqmc_b200_handle *h) { return h ? h->last_build_incremental : -1; }
 int sqmc_b200_exchange_mode(sqmc_b200_handle *h) {  // 0 single rank, 1 NVLink peer stores, 2 NCCL
   if (!h || G.nranks == 1) return 0;
   return h->p2p.on ? 1 : 2;

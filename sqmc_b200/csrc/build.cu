@@ -291,10 +291,11 @@ static const int kConnStage = 1024;  // beta strings staged per step
 // entry list) the diagonal comes first, the order is arbitrary and the rows are sorted afterwards.
 template <int NW, bool FILL, bool W32, bool SORTED>
 __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, const TileDesc *tiles, int64_t ntiles, int64_t row_begin,
-                                                                 int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen) {
+                                                                 int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen,
+                                                                 const int32_t *old_of_new, const int32_t *olen) {
   __shared__ uint64_t sEb[W32 ? 1 : kConnStage * NW];
   __shared__ uint32_t sEb32[W32 ? kConnStage : 1];
-  __shared__ uint32_t sErep[FILL ? kConnStage : 1];
+  __shared__ uint32_t sErep[kConnStage];
   __shared__ int32_t s_cnt[kConnTile];
   __shared__ int32_t s_row[kConnTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -307,8 +308,12 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
     const int64_t p = active ? (int64_t)rep : -1;
     Bits<NW> b = b_zero<NW>();
     if (active) b = b_load<NW>(V.Eb, e);
+    // incremental build (old_of_new != null): a pair of two determinants of the previous list is already stored in the
+    // previous matrix -- only pairs with at least one new determinant are generated; the row's old entries sit in front
+    // of its candidates (olen of them)
+    const bool row_new = !old_of_new || (active && old_of_new[p] < 0);
     int64_t base = 0;
-    if (FILL && active) base = cand_ptr[p - row_begin];
+    if (FILL && active) base = cand_ptr[p - row_begin] + (olen ? olen[p] : 0);
     int cnt = 0;
     if (!SORTED && active) {
       if (FILL) cand[base] = (int32_t)p;  // diagonal
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
 #pragma unroll
             for (int w = 0; w < NW; w++) sEb[i * NW + w] = V.Eb[(s0 + i) * NW + w];
           }
-          if (FILL) sErep[i] = V.Erep[s0 + i];
+          sErep[i] = V.Erep[s0 + i];
         }
         __syncthreads();
         if (active) {
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
               for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
             }
             const bool hit = own ? (pc == 2 || pc == 4 || (SORTED && pc == 0)) : (pc == 0 || pc == 2);
-            if (hit) {
+            if (hit && (row_new || old_of_new[sErep[i] & ~kSwapBit] < 0)) {
               if (FILL) cand[base + cnt] = (int32_t)(sErep[i] & ~kSwapBit);
               cnt++;
             }
@@ -364,7 +369,8 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
       const int64_t e2 = T.e0 + rr;
       const Bits<NW> a2 = b_load<NW>(V.Ea, e2);
       const int64_t p2 = (int64_t)V.Erep[e2];
-      const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] : 0;
+      const bool new2 = !old_of_new || old_of_new[p2] < 0;
+      const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] + (olen ? olen[p2] : 0) : 0;
       int c2 = s_cnt[rr];
       if (FILL && SORTED && lane == 0) alen[p2 - row_begin] = c2;
       const int32_t gb = V.eB[e2];
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
         const int64_t k = tb + lane;
         const bool in = k < hi;
         const int pc = in ? b_popc_xor(a2, b_load<NW>(V.EBa, k)) : 0;
-        const bool hit = in && pc == 4;
+        const bool hit = in && pc == 4 && (new2 || old_of_new[V.EBrep[k] & ~kSwapBit] < 0);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (FILL && hit) cand[base2 + c2 + __popc(m & lt_mask)] = (int32_t)(V.EBrep[k] & ~kSwapBit);
         c2 += __popc(m);
@@ -491,7 +497,8 @@ template <int NW, int MODEL, bool TS>
 __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t *__restrict__ up, const uint64_t *__restrict__ dn, const int32_t *__restrict__ perm,
                                                    const double *__restrict__ diag, int64_t diag_row0, int64_t row_begin, int64_t row_end,
                                                    const int64_t *__restrict__ cand_ptr, const int32_t *__restrict__ cand_len, int32_t *cand, double *vals,
-                                                   int32_t *row_nnz, int32_t *alen /* in: candidates of the first sorted run, out: kept ones; may be null */) {
+                                                   int32_t *row_nnz, int32_t *alen /* in: candidates of the first sorted run, out: kept ones; may be null */,
+                                                   const int32_t *olen /* incremental build: entries of the previous matrix in front of the candidates */) {
   extern __shared__ int32_t c2s[];
   __shared__ int32_t s_q[8][64];
   const int32_t *c2 = T.combine_2;
@@ -508,7 +515,8 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
   const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
   const Bits<NW> pu = b_load<NW>(up, p), pd = b_load<NW>(dn, p);
   const int32_t cp = perm[p];
-  const int64_t base = cand_ptr[warp];
+  const int ol = olen ? olen[p] : 0;
+  const int64_t base = cand_ptr[warp] + ol;
   const int L = cand_len[warp];
   // ---- pass 1: values.  Every trip of the loop gives each lane at most one job (a candidate position to evaluate): a
   // scan trip classifies the next 32 candidates -- light ones become the lane's job, chem singles go to the warp's queue --
@@ -590,45 +598,90 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
     __syncwarp();
   }
   if (lane == 0) {
-    row_nnz[warp] = kept;
+    row_nnz[warp] = kept + ol;
     if (alen) alen[warp] = kept_a;
   }
 }
 
-// copy compacted rows to their final place.  alen != null: a row is two ascending runs (alen[row] entries, then the rest);
-// they are merged on the way: an entry's final position = its index in its own run + the entries of the other run that
-// sort before it (binary search; the runs share no column).
-__global__ void __launch_bounds__(256) compact_copy_kernel(const int64_t *cand_ptr, const int32_t *row_nnz, const int32_t *alen, const int64_t *rowptr_chunk,
-                                                           int64_t nrows, const int32_t *cand, const double *vals, int32_t *cols_out,
-                                                           double *vals_out) {
+// copy compacted rows to their final place.  A row is up to three ascending runs that share no column: the entries taken
+// over from the previous matrix (olen, incremental build), the candidates of the alpha part (alen) and the same-beta
+// up-doubles (the rest).  They are merged on the way: an entry's final position = its index in its own run + the entries
+// of the other runs that sort before it (binary searches).  alen == null: one run (rows were sorted), plain copy.
+__device__ __forceinline__ int lower_bound_i32(const int32_t *a, int n, int32_t c) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) compact_copy_kernel(const int64_t *cand_ptr, const int32_t *row_nnz, const int32_t *alen, const int32_t *olen,
+                                                           int64_t row_begin, const int64_t *rowptr_chunk, int64_t nrows, const int32_t *cand,
+                                                           const double *vals, int32_t *cols_out, double *vals_out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (row >= nrows) return;
   const int64_t src = cand_ptr[row], dst = rowptr_chunk[row];
   const int L = row_nnz[row];
-  const int KA = alen ? alen[row] : L;
-  if (KA == L) {
+  const int KO = olen ? olen[row_begin + row] : 0;
+  const int KA = alen ? alen[row] : L - KO;
+  const int KB = L - KO - KA;
+  if ((KO == L) || (KO == 0 && KB == 0) ) {
     for (int k = lane; k < L; k += 32) {
       cols_out[dst + k] = cand[src + k];
       vals_out[dst + k] = vals[src + k];
     }
     return;
   }
-  const int32_t *A = cand + src, *B = cand + src + KA;
-  const int KB = L - KA;
+  const int32_t *O = cand + src, *A = O + KO, *B = A + KA;
   for (int k = lane; k < L; k += 32) {
     const int32_t c = cand[src + k];
-    const bool inA = k < KA;
-    const int32_t *O = inA ? B : A;
-    int lo = 0, hi = inA ? KB : KA;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (O[mid] < c) lo = mid + 1;
-      else hi = mid;
-    }
-    const int pos = (inA ? k : k - KA) + lo;
+    int pos;
+    if (k < KO) pos = k + lower_bound_i32(A, KA, c) + lower_bound_i32(B, KB, c);
+    else if (k < KO + KA) pos = (k - KO) + lower_bound_i32(O, KO, c) + lower_bound_i32(B, KB, c);
+    else pos = (k - KO - KA) + lower_bound_i32(O, KO, c) + lower_bound_i32(A, KA, c);
     cols_out[dst + pos] = c;
     vals_out[dst + pos] = vals[src + k];
+  }
+}
+
+// ---- incremental build helpers (chemistry.f90:7769-7843: rows 1..ndet_old are kept and only extended)
+// old_of_new[p] = row of the previous matrix that holds determinant p of the new internal order, -1 for a new determinant
+__global__ void old_of_new_kernel(const int32_t *perm_new, const int32_t *iperm_old, int64_t n, int64_t n_old, int32_t *old_of_new) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int32_t cr = perm_new[p];
+  old_of_new[p] = cr < n_old ? iperm_old[cr] : -1;
+}
+__global__ void new_of_old_kernel(const int32_t *perm_old, const int32_t *iperm_new, int64_t n_old, int32_t *new_of_old) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q < n_old) new_of_old[q] = iperm_new[perm_old[q]];
+}
+__global__ void old_len_kernel(const int32_t *old_of_new, const int64_t *rowptr_old, int64_t n, int32_t *olen) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int32_t q = old_of_new[p];
+  olen[p] = q >= 0 ? (int32_t)(rowptr_old[q + 1] - rowptr_old[q]) : 0;
+}
+__global__ void add_i32_kernel(const int32_t *a, const int32_t *b, int32_t *out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+// rows [row_begin, row_begin + nrows): copy the row's old entries (columns renumbered; the map is monotone, so they stay
+// ascending) in front of its candidates in the chunk's temporaries.  One warp per row.
+__global__ void __launch_bounds__(256) copy_old_rows_kernel(const int32_t *old_of_new, const int64_t *rowptr_old, const int32_t *cols_old, const double *vals_old,
+                                                            const int32_t *new_of_old, int64_t row_begin, int64_t nrows, const int64_t *cand_ptr,
+                                                            int32_t *cand, double *vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const int32_t q = old_of_new[row_begin + row];
+  if (q < 0) return;
+  const int64_t b = rowptr_old[q], e = rowptr_old[q + 1], dst = cand_ptr[row];
+  for (int64_t k = b + lane; k < e; k += 32) {
+    cand[dst + (k - b)] = new_of_old[cols_old[k]];
+    vals[dst + (k - b)] = vals_old[k];
   }
 }
 
@@ -724,7 +777,8 @@ void free_matrix(sqmc_b200_handle *h) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr); F(h->d_cols); F(h->d_vals);
+  F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr);
+  // d_cols / d_vals live in the growable arrays: they keep their memory for the next build (released by matrix_arrays_release)
   F(h->d_bin_rows); F(h->d_x); F(h->d_y); F(h->d_tmp); F(h->d_x2); F(h->d_xi2); F(h->d_y2);
   F(h->d_shuf_of_internal); F(h->d_dest_rank); F(h->d_dest_pos); F(h->d_my_internal);
   h->own_set = false; h->my_n = 0; h->own_count.clear(); h->own_off.clear();
@@ -733,6 +787,45 @@ void free_matrix(sqmc_b200_handle *h) {
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
   h->row_starts.clear();
 }
+
+// reserve (once) and map the two entry arrays for `entries` stored entries
+int matrix_arrays_ensure(sqmc_b200_handle *h, int64_t entries) {
+  if (!h->g_cols.base) {
+    size_t fr = 0, tot = 0;
+    SQ_CUDA(cudaMemGetInfo(&fr, &tot));
+    const size_t max_entries = tot / 12 + (1 << 20);  // the device cannot hold more than this
+    SQ_CHECK(grow_reserve(h->g_cols, max_entries * sizeof(int32_t)));
+    SQ_CHECK(grow_reserve(h->g_vals, max_entries * sizeof(double)));
+  }
+  SQ_CHECK(grow_ensure(h->g_cols, (size_t)(entries + kSlack) * sizeof(int32_t)));
+  SQ_CHECK(grow_ensure(h->g_vals, (size_t)(entries + kSlack) * sizeof(double)));
+  h->d_cols = reinterpret_cast<int32_t *>(h->g_cols.base);
+  h->d_vals = reinterpret_cast<double *>(h->g_vals.base);
+  return 0;
+}
+void matrix_arrays_release(sqmc_b200_handle *h) {
+  grow_release(h->g_cols);
+  grow_release(h->g_vals);
+  h->d_cols = nullptr;
+  h->d_vals = nullptr;
+}
+
+// the previous matrix, detached from the handle while an incremental build extends it
+struct OldMatrix {
+  int64_t n = 0, nnz = 0;
+  int32_t *d_perm = nullptr, *d_iperm = nullptr;
+  int64_t *d_rowptr = nullptr;
+  ~OldMatrix() {
+    if (d_perm) cudaFree(d_perm);
+    if (d_iperm) cudaFree(d_iperm);
+    if (d_rowptr) cudaFree(d_rowptr);
+  }
+};
+struct EventSet {  // timing events of one build, destroyed on every exit path
+  cudaEvent_t e[5];
+  EventSet() { for (auto &x : e) cudaEventCreate(&x); }
+  ~EventSet() { for (auto &x : e) cudaEventDestroy(x); }
+};
 
 static int alloc_work_vectors(sqmc_b200_handle *h) {
   SQ_CHECK(p2p_setup(h, h->n));  // collective: (re)maps the peers' exchange buffers when the vectors outgrew them
@@ -759,11 +852,11 @@ void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *start
 
 // ------------------------------------------------------------------ the build
 template <int NW>
-static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn) {
+static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, OldMatrix *old) {
   cudaStream_t s = G.stream;
   const ModelTables &T = h->T;
-  cudaEvent_t ev[5];
-  for (auto &e : ev) cudaEventCreate(&e);
+  EventSet evset;
+  cudaEvent_t *ev = evset.e;
   HostMarks HM;
   cudaEventRecord(ev[0], s);
 
@@ -816,6 +909,22 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   up_c.release();
   dn_c.release();
   h->n = n;
+  // ---- incremental build: where the determinants of the previous list went
+  DevBuf<int32_t> old_of_new, new_of_old, olen;
+  if (old) {
+    SQ_CHECK(old_of_new.alloc(n));
+    SQ_CHECK(new_of_old.alloc(old->n));
+    SQ_CHECK(olen.alloc(n + 1));
+    old_of_new_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, old->d_iperm, n, old->n, old_of_new.p);
+    SQ_LAUNCH_CHECK();
+    new_of_old_kernel<<<nblocks(old->n), kThreads, 0, s>>>(old->d_perm, h->d_iperm, old->n, new_of_old.p);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaMemsetAsync(olen.p + n, 0, sizeof(int32_t), s));
+    old_len_kernel<<<nblocks(n), kThreads, 0, s>>>(old_of_new.p, old->d_rowptr, n, olen.p);
+    SQ_LAUNCH_CHECK();
+  }
+  const int32_t *d_oon = old ? old_of_new.p : nullptr;
+  const int32_t *d_olen = old ? olen.p : nullptr;
 
   // ---- expanded entry list E (alpha-major)
   const bool ts = (T.model == MODEL_CHEM) && T.time_sym;
@@ -1014,7 +1123,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     else if (!ts) connect_tile_kernel<NW, FILL, false, true><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);        \
     else connect_tile_kernel<NW, FILL, false, false><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);                \
   } while (0)
-      SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr);
+      SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
       SQ_LAUNCH_CHECK();
       SQ_CUDA(cudaStreamSynchronize(s));
     }
@@ -1031,9 +1140,18 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     }
   }
   HM.mark("count pass");
-  DevBuf<int64_t> cand_prefix;  // n+1 exclusive prefix of candidate counts over ALL rows
+  // per-row length of the chunk temporaries: the candidates, and in an incremental build the row's old entries in front
+  DevBuf<int32_t> seg_buf;
+  int32_t *seg_count = cand_count.p;
+  if (old) {
+    SQ_CHECK(seg_buf.alloc(n + 1));
+    add_i32_kernel<<<nblocks(n + 1), kThreads, 0, s>>>(cand_count.p, olen.p, seg_buf.p, n + 1);
+    SQ_LAUNCH_CHECK();
+    seg_count = seg_buf.p;
+  }
+  DevBuf<int64_t> cand_prefix;  // n+1 exclusive prefix of the segment lengths over ALL rows
   SQ_CHECK(cand_prefix.alloc(n + 1));
-  SQ_CHECK(exclusive_scan_i32_to_i64(cand_count.p, cand_prefix.p, n, s));
+  SQ_CHECK(exclusive_scan_i32_to_i64(seg_count, cand_prefix.p, n, s));
   std::vector<int64_t> hprefix(n + 1);
   SQ_CUDA(cudaMemcpy(hprefix.data(), cand_prefix.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
   cand_prefix.release();
@@ -1050,11 +1168,38 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   // ---- final arrays (capacity = candidate upper bound)
   h->capacity = std::max<int64_t>(Tloc, 1);
   // + kSlack entries: the 128-bit stream loads of the H.v kernels may touch a few entries past the last one
-  SQ_CHECK(big_malloc((void **)&h->d_cols, (h->capacity + kSlack) * sizeof(int32_t)));
-  SQ_CHECK(big_malloc((void **)&h->d_vals, (h->capacity + kSlack) * sizeof(double)));
+  SQ_CHECK(matrix_arrays_ensure(h, h->capacity));
   SQ_CUDA(cudaMemsetAsync(h->d_cols + h->capacity, 0, kSlack * sizeof(int32_t), s));
   SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
   SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
+  // incremental build: the previous entries move to the END of the arrays.  New rows are written from the front in
+  // ascending row order and old rows are consumed in the same order, so the write position never overtakes the unread
+  // old entries (at most capacity - nnz_old new entries are ever added).  The move goes through a bounded staging buffer,
+  // back to front, because source and destination overlap.
+  const int32_t *old_cols = nullptr;
+  const double *old_vals = nullptr;
+  if (old) {
+    const int64_t shift = h->capacity - old->nnz;
+    old_cols = h->d_cols + shift;
+    old_vals = h->d_vals + shift;
+    if (shift > 0 && old->nnz > 0) {
+      const int64_t step = std::min<int64_t>(old->nnz, 1ll << 26);
+      DevBuf<double> stage;
+      SQ_CHECK(stage.alloc(step));
+      for (int64_t e1 = old->nnz; e1 > 0; e1 -= step) {
+        const int64_t e0 = std::max<int64_t>(0, e1 - step), len = e1 - e0;
+        if (shift >= len) {  // disjoint: direct copy
+          SQ_CUDA(cudaMemcpyAsync(h->d_cols + e0 + shift, h->d_cols + e0, len * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(h->d_vals + e0 + shift, h->d_vals + e0, len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        } else {
+          SQ_CUDA(cudaMemcpyAsync(stage.p, h->d_cols + e0, len * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(h->d_cols + e0 + shift, stage.p, len * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(stage.p, h->d_vals + e0, len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(h->d_vals + e0 + shift, stage.p, len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        }
+      }
+    }
+  }
 
   // diagonal of the local rows: read by eval_kernel, kept for Davidson's preconditioner and the projector
   SQ_CUDA(cudaMalloc(&h->d_diag, std::max<int64_t>(nloc, 1) * sizeof(double)));
@@ -1122,13 +1267,17 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     const int64_t r_end = cp.r_end, nr = r_end - r;
     cudaEventRecord(e0, s);
     // chunk-local candidate offsets
-    SQ_CHECK(exclusive_scan_i32_to_i64_async(cand_count.p + r, cptr.p, nr, scan_tmp.p, scan_bytes, s));
-    // the scan above read cand_count[r+nr] as its spare slot; offsets beyond nr are unused
+    SQ_CHECK(exclusive_scan_i32_to_i64_async(seg_count + r, cptr.p, nr, scan_tmp.p, scan_bytes, s));
+    // the scan above read seg_count[r+nr] as its spare slot; offsets beyond nr are unused
+    if (old) {
+      copy_old_rows_kernel<<<nblocks(nr * 32), 256, 0, s>>>(old_of_new.p, old->d_rowptr, old_cols, old_vals, new_of_old.p, r, nr, cptr.p, cand_tmp.p, vals_tmp.p);
+      SQ_LAUNCH_CHECK();
+    }
     {
       const TileDesc *td = fill_tiles_dev.p + cp.tile_off;
       const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cp.ntiles, G.sm_count * 16));
       const bool w32 = NW == 1 && T.norb <= 32;
-      SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p);
+      SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p, d_oon, d_olen);
       SQ_LAUNCH_CHECK();
     }
     if (ts) {  // time-reversed partners in the entry list: arbitrary candidate order, duplicates -> sort the rows
@@ -1144,12 +1293,12 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     SQ_CUDA(cudaMemsetAsync(row_nnz.p, 0, (nr + 1) * sizeof(int32_t), s));
     int c2bytes = (T.model == MODEL_CHEM) ? (T.norb + 1) * (T.norb + 1) * 4 : 0;
     SQ_MODEL_DISPATCH(T, (eval_kernel<NW, kModel, kTS><<<nblocks(nr * 32), 256, c2bytes, s>>>(T, h->d_up, h->d_dn, h->d_perm, h->d_diag, h->row0, r, r_end, cptr.p,
-                                                                                              cand_count.p + r, cand_tmp.p, vals_tmp.p, row_nnz.p, ts ? nullptr : alen.p)));
+                                                                                              cand_count.p + r, cand_tmp.p, vals_tmp.p, row_nnz.p, ts ? nullptr : alen.p, d_olen)));
     SQ_LAUNCH_CHECK();
     SQ_CHECK(exclusive_scan_i32_to_i64_async(row_nnz.p, rptr.p, nr, scan_tmp.p, scan_bytes, s));
     add_offset_dev_kernel<<<nblocks(nr + 1), kThreads, 0, s>>>(rptr.p, nr + 1, base_dev.p);
     SQ_LAUNCH_CHECK();
-    compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, ts ? nullptr : alen.p, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
+    compact_copy_kernel<<<nblocks(nr * 32), 256, 0, s>>>(cptr.p, row_nnz.p, ts ? nullptr : alen.p, d_olen, r, rptr.p, nr, cand_tmp.p, vals_tmp.p, h->d_cols, h->d_vals);
     SQ_LAUNCH_CHECK();
     SQ_CUDA(cudaMemcpyAsync(h->d_rowptr + (r - h->row0), rptr.p, (nr + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     set_scalar_kernel<<<1, 1, 0, s>>>(base_dev.p, rptr.p + nr);
@@ -1186,30 +1335,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->nnz_upper = (tot + n) / 2;
   h->scale = 1.0;
 
-  // ---- shrink the final arrays when the candidate bound was loose
-  if (h->capacity - h->nnz_local > (1ll << 20) && (h->capacity - h->nnz_local) * 8 > h->capacity) {
-    int32_t *nc = nullptr;
-    double *nv = nullptr;
-    int64_t cap = std::max<int64_t>(h->nnz_local, 1);
-    if (cudaMalloc(&nc, (cap + kSlack) * sizeof(int32_t)) == cudaSuccess) {
-      if (cudaMalloc(&nv, (cap + kSlack) * sizeof(double)) == cudaSuccess) {
-        cudaMemsetAsync(nc + cap, 0, kSlack * sizeof(int32_t), s);
-        cudaMemsetAsync(nv + cap, 0, kSlack * sizeof(double), s);
-        cudaMemcpyAsync(nc, h->d_cols, h->nnz_local * sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
-        cudaMemcpyAsync(nv, h->d_vals, h->nnz_local * sizeof(double), cudaMemcpyDeviceToDevice, s);
-        cudaStreamSynchronize(s);
-        cudaFree(h->d_cols);
-        cudaFree(h->d_vals);
-        h->d_cols = nc;
-        h->d_vals = nv;
-        h->capacity = cap;
-      } else {
-        cudaFree(nc);
-        cudaGetLastError();
-      }
-    } else {
-      cudaGetLastError();
-    }
+  // ---- give back the memory above the stored entries when the candidate bound was loose (the arrays keep their address)
+  if (h->capacity - h->nnz_local > (1ll << 26)) {
+    h->capacity = std::max<int64_t>(h->nnz_local, 1);
+    grow_trim(h->g_cols, (size_t)(h->capacity + kSlack) * sizeof(int32_t));
+    grow_trim(h->g_vals, (size_t)(h->capacity + kSlack) * sizeof(double));
   }
   HM.mark("nnz reduce + shrink");
   SQ_CHECK(alloc_work_vectors(h));
@@ -1228,7 +1358,6 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->build_ms[5] = (double)Tloc;
   h->build_ms[6] = (double)nA;
   h->build_ms[7] = (double)nB;
-  for (auto &e : ev) cudaEventDestroy(e);
   (void)maxlen;
   return 0;
 }
@@ -1237,13 +1366,38 @@ int build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *det
   if (n <= 0) { set_error("build_h: n must be positive"); return 2; }
   if (n >= (1ll << 31) - 2) { set_error("build_h: n=%lld exceeds 32-bit row indices", (long long)n); return 2; }
   if (ndet_old < 0 || ndet_old > n) { set_error("build_h: ndet_old out of range"); return 2; }
-  // incremental semantics: the result equals a from-scratch build, so rebuild.
+  // Incremental build (sparse_ham%ndet, chemistry.f90:7769-7843): the caller promises that rows 1..ndet_old are the list of
+  // the previous call on this handle.  Then the previous matrix is kept and only pairs with a new determinant are generated
+  // and evaluated -- the result is identical to a from-scratch build (an entry depends only on its two determinants).
+  // Taken when the previous matrix is resident, unscaled, built (not imported) on one rank, without time-reversal
+  // expansion and by a partial-connection builder (chem / heg); otherwise the matrix is rebuilt.  SQMC_INCREMENTAL=0 disables.
+  const ModelTables &T = h->T;
+  const char *ie = getenv("SQMC_INCREMENTAL");
+  bool inc = !(ie && atoi(ie) == 0) && ndet_old > 0 && ndet_old < n && h->d_rowptr && h->d_up && h->n == ndet_old && G.nranks == 1 && h->scale == 1.0 &&
+             !(T.model == MODEL_CHEM && T.time_sym) && T.model != MODEL_HUBBARDK && h->row0 == 0 && h->row1 == h->n;
+  OldMatrix old;
+  if (inc) {
+    if (bundle_decode(h)) inc = false;  // the merge reads plain rows
+  }
+  if (inc) {
+    old.n = h->n;
+    old.nnz = h->nnz_local;
+    old.d_perm = h->d_perm; h->d_perm = nullptr;
+    old.d_iperm = h->d_iperm; h->d_iperm = nullptr;
+    old.d_rowptr = h->d_rowptr; h->d_rowptr = nullptr;
+  }
   {
     HostMarks FM;
     free_matrix(h);
     FM.mark("free previous matrix");
   }
-  return h->NW == 1 ? build_impl<1>(h, n, dets_up, dets_dn) : build_impl<2>(h, n, dets_up, dets_dn);
+  h->last_build_incremental = inc ? 1 : 0;
+  int rc = h->NW == 1 ? build_impl<1>(h, n, dets_up, dets_dn, inc ? &old : nullptr) : build_impl<2>(h, n, dets_up, dets_dn, inc ? &old : nullptr);
+  if (rc) {  // leave no half-built matrix behind
+    cudaStreamSynchronize(G.stream);
+    free_matrix(h);
+  }
+  return rc;
 }
 
 int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, double *diag) {

@@ -315,8 +315,7 @@ int import_upper_device(sqmc_b200_handle *h, int64_t n, const int64_t *counts, c
   int64_t maxlen = 0;
   for (int64_t i = 0; i < n; i++) maxlen = std::max<int64_t>(maxlen, hdeg[i]);
   h->capacity = std::max<int64_t>(nnzf, 1);
-  SQ_CHECK(big_malloc((void **)&h->d_cols, (h->capacity + 1024) * sizeof(int32_t)));
-  SQ_CHECK(big_malloc((void **)&h->d_vals, (h->capacity + 1024) * sizeof(double)));
+  SQ_CHECK(matrix_arrays_ensure(h, h->capacity));
   if (nnzu > 0) {
     import_fill_kernel<<<cblocks(nnzu), 256, 0, s>>>(uidx.p, uval.p, row_of.p, nnzu, h->d_rowptr, cursor.p, h->d_cols, h->d_vals);
     SQ_LAUNCH_CHECK();

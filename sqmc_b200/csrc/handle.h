@@ -90,6 +90,17 @@ struct P2P {
   cudaStream_t last_stream = nullptr;
 };
 
+// ---- device array that grows in place (csrc/growbuf.cu: CUDA virtual memory management) ----
+struct GrowBuf {
+  unsigned long long base = 0;  // device address of the reserved range
+  size_t reserved = 0, mapped = 0, chunk = 0;
+  std::vector<unsigned long long> handles;  // physical chunks mapped behind [base, base + mapped)
+};
+int grow_reserve(GrowBuf &b, size_t max_bytes);
+int grow_ensure(GrowBuf &b, size_t bytes);
+void grow_trim(GrowBuf &b, size_t bytes);
+void grow_release(GrowBuf &b);
+
 // number of degree bins for the SpMV (sub-warp vector sizes 2,4,8,16,32 + CTA-per-row)
 static const int kNumBins = 6;
 
@@ -117,8 +128,10 @@ struct sqmc_b200_handle {
 
   // ---- full symmetric CSR of the local rows, columns in internal numbering ----
   int64_t *d_rowptr = nullptr;  // (row1-row0+1) offsets into cols/vals
-  int32_t *d_cols = nullptr;
-  double *d_vals = nullptr;
+  int32_t *d_cols = nullptr;    // = g_cols.base: the two entry arrays keep their address and memory across builds
+  double *d_vals = nullptr;     // = g_vals.base
+  sqmc::GrowBuf g_cols, g_vals;
+  int last_build_incremental = 0;  // 1 when the last build_h extended the previous matrix instead of rebuilding it
   int64_t nnz_local = 0, capacity = 0;
   int64_t nnz_full = 0, nnz_upper = 0;  // global
   double scale = 1.0;                   // product of scale_values() ratios applied to d_vals
@@ -165,6 +178,8 @@ int diagonal(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *de
 int export_upper(sqmc_b200_handle *h, int64_t *counts, int64_t *indices, double *values);
 int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const int64_t *indices, const double *values);
 void free_matrix(sqmc_b200_handle *h);
+int matrix_arrays_ensure(sqmc_b200_handle *h, int64_t entries);  // (re)map the growable cols / vals arrays
+void matrix_arrays_release(sqmc_b200_handle *h);
 void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *starts);
 int upload_dets(int NW, int norb, const void *host16, uint64_t *out, int64_t n, cudaStream_t s);
 int sort_pairs_index(int NW, int norb, const uint64_t *a, const uint64_t *b, int32_t *idx, int64_t n, cudaStream_t s);

@@ -90,6 +90,7 @@ def hci_space(H, system, n_dets, eps_schedule=(1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 5e-
     This is the BASELINE.json configs[3] recipe ("eps_var lowered to give ~10^7 determinants").  Under torchrun every
     rank runs the same loop (selection is replicated, build / Davidson are sharded collectives) and obtains identical lists.
     Returns (up, dn, wts, energy); H keeps the matrix of the final space resident."""
+    import time
     from .api import dets_to_u64
     up = dets_to_u64([system.hf_up])
     dn = dets_to_u64([system.hf_dn])
@@ -98,20 +99,28 @@ def hci_space(H, system, n_dets, eps_schedule=(1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 5e-
     energy = None
     for it, eps in enumerate(eps_schedule, 1):
         n_old = len(up)
+        t0 = time.perf_counter()
         nu, nd, min_h = H.get_next_det_list(up, dn, np.abs(wts[:, 0]), min_h, eps)
+        t_sel = time.perf_counter() - t0
         if len(nu) == 0:
             continue
         if n_old + len(nu) > n_dets:
             nu, nd = nu[:n_dets - n_old], nd[:n_dets - n_old]
         up, dn = np.concatenate([up, nu]), np.concatenate([dn, nd])
         min_h = np.concatenate([min_h, np.full(len(nu), 9e99)])
+        t0 = time.perf_counter()
         nnz = H.generate_sparse_ham_upper_triangular(up, dn, ndet_old=n_old)
+        t_build = time.perf_counter() - t0
         v0 = np.zeros((len(up), 1))
         v0[:n_old, 0] = wts[:, 0]
+        t0 = time.perf_counter()
         d = H.davidson_sparse(n_states=1, initial_vector=v0)
+        t_dav = time.perf_counter() - t0
         wts, energy = d["evecs"], float(d["evals"][0])
         if log is not None:
-            log.append({"iter": it, "eps_var": eps, "n_dets": len(up), "nnz_upper": int(nnz), "energy": energy})
+            log.append({"iter": it, "eps_var": eps, "n_dets": len(up), "nnz_upper": int(nnz), "energy": energy, "select_s": t_sel, "build_s": t_build,
+                        "build_device_ms": H.build_times()["total_ms"], "build_incremental": bool(H.last_build_incremental()),
+                        "davidson_s": t_dav, "n_matvec": int(d["n_matvec"])})
         if len(up) >= n_dets:
             break
     return up, dn, wts, energy
