@@ -13,6 +13,7 @@ namespace sqmc {
 std::string g_last_error;
 int64_t g_launch_count = 0;
 Global G;
+std::vector<sqmc_b200_handle *> g_handles;
 void set_error(const char *fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -43,6 +44,11 @@ int devbuf_alloc(void **p, size_t bytes) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     e = cudaMallocAsync(p, bytes, G.stream);
+    if (e != cudaSuccess) {  // still short: the matrices give back the surplus of their growable arrays
+      cudaGetLastError();
+      matrix_arrays_release_surplus();
+      e = cudaMallocAsync(p, bytes, G.stream);
+    }
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -66,6 +72,11 @@ int big_malloc(void **p, size_t bytes) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      matrix_arrays_release_surplus();
+      e = cudaMalloc(p, bytes);
+    }
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -160,6 +171,7 @@ static sqmc_b200_handle *new_handle(int model, int norb, int nup, int ndn) {
   h->T.ndn = ndn;
   h->T.z = 1;
   h->NW = norb <= 64 ? 1 : 2;
+  g_handles.push_back(h);
   return h;
 }
 
@@ -234,6 +246,7 @@ int sqmc_b200_free(sqmc_b200_handle *h) {
   matrix_arrays_release(h);
   p2p_release(h);
   if (h->d_orbsym) cudaFree(h->d_orbsym);
+  if (h->d_scat_counter) cudaFree(h->d_scat_counter);
   for (int k = 0; k < 2; k++) {
     if (h->d_hb_val[k]) cudaFree(h->d_hb_val[k]);
     if (h->d_hb_rs[k]) cudaFree(h->d_hb_rs[k]);
@@ -243,6 +256,7 @@ int sqmc_b200_free(sqmc_b200_handle *h) {
   if (h->d_kvec) cudaFree(h->d_kvec);
   if (h->d_hkvec) cudaFree(h->d_hkvec);
   if (h->d_kenergies) cudaFree(h->d_kenergies);
+  g_handles.erase(std::remove(g_handles.begin(), g_handles.end(), h), g_handles.end());
   delete h;
   return 0;
 }

@@ -267,6 +267,11 @@ struct ConnView {
   // per alpha group: its own index and the groups of the strings one excitation away, ascending
   const int64_t *nbr_off;
   const int32_t *nbr;
+  // incremental build (null otherwise): inside every alpha group the determinants of the previous list first, then the new
+  // ones, each part in beta order.  Pidx = internal row at a view position, Pb = its beta string, gNew_off = first new position.
+  const int32_t *Pidx;
+  const uint64_t *Pb;
+  const int64_t *gNew_off;
 };
 
 // Tiled candidate generation: one CTA per tile of <= 256 consecutive entries of ONE alpha-group, one thread per entry
@@ -276,9 +281,10 @@ struct ConnView {
 // shared-memory reads, no divergence in the test).  The same-beta up-doubles are found afterwards, one warp per row.
 // FILL=false counts, FILL=true writes candidate rep indices (order inside a row is arbitrary; rows are sorted later).
 struct TileDesc {
-  int64_t e0;   // first entry
-  int32_t n;    // entries (<= kConnTile)
-  int32_t g;    // alpha group
+  int64_t e0;    // first entry (position in the row view)
+  int16_t n;     // entries (<= kConnTile)
+  int16_t kind;  // 0: candidates = every entry of a group; 1 (incremental build, rows of the previous list): only the new entries
+  int32_t g;     // alpha group
 };
 static const int kConnTile = 256;
 static const int kConnStage = 1024;  // beta strings staged per step
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
                                                                  const int32_t *old_of_new, const int32_t *olen) {
   __shared__ uint64_t sEb[W32 ? 1 : kConnStage * NW];
   __shared__ uint32_t sEb32[W32 ? kConnStage : 1];
-  __shared__ uint32_t sErep[kConnStage];
+  __shared__ uint32_t sErep[FILL ? kConnStage : 1];
   __shared__ int32_t s_cnt[kConnTile];
   __shared__ int32_t s_row[kConnTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -303,15 +309,16 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
     const TileDesc T = tiles[t];
     const int64_t e = T.e0 + threadIdx.x;
     const bool have = threadIdx.x < T.n;
-    const uint32_t rep = have ? V.Erep[e] : kSwapBit;
+    const bool part = SORTED && V.Pidx != nullptr;  // rows come from the partitioned view
+    const uint32_t rep = have ? (part ? (uint32_t)V.Pidx[e] : V.Erep[e]) : kSwapBit;
     const bool active = have && !(rep & kSwapBit);  // rows are the unswapped entries
     const int64_t p = active ? (int64_t)rep : -1;
     Bits<NW> b = b_zero<NW>();
-    if (active) b = b_load<NW>(V.Eb, e);
-    // incremental build (old_of_new != null): a pair of two determinants of the previous list is already stored in the
-    // previous matrix -- only pairs with at least one new determinant are generated; the row's old entries sit in front
-    // of its candidates (olen of them)
-    const bool row_new = !old_of_new || (active && old_of_new[p] < 0);
+    if (active) b = b_load<NW>(part ? V.Pb : V.Eb, e);
+    // incremental build: a pair of two determinants of the previous list is already stored in the previous matrix -- only
+    // pairs with at least one new determinant are generated (tiles of kind 1 stage just the new entries of every candidate
+    // group); the row's old entries sit in front of its candidates (olen of them)
+    const bool only_new = part && T.kind == 1;
     int64_t base = 0;
     if (FILL && active) base = cand_ptr[p - row_begin] + (olen ? olen[p] : 0);
     int cnt = 0;
@@ -324,18 +331,19 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
     for (int64_t q = V.nbr_off[g]; q < V.nbr_off[g + 1]; q++) {
       const int32_t g2 = V.nbr[q];
       const bool own = g2 == g;
-      const int64_t lo = V.gA_off[g2], hi = V.gA_off[g2 + 1];
+      const int64_t lo = only_new ? V.gNew_off[g2] : V.gA_off[g2], hi = V.gA_off[g2 + 1];
+      const uint64_t *cEb = only_new ? V.Pb : V.Eb;
       for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
         const int ns = (int)min((int64_t)kConnStage, hi - s0);
         __syncthreads();  // previous stage fully consumed
         for (int i = threadIdx.x; i < ns; i += blockDim.x) {
           if (W32) {
-            sEb32[i] = (uint32_t)V.Eb[s0 + i];
+            sEb32[i] = (uint32_t)cEb[s0 + i];
           } else {
 #pragma unroll
-            for (int w = 0; w < NW; w++) sEb[i * NW + w] = V.Eb[(s0 + i) * NW + w];
+            for (int w = 0; w < NW; w++) sEb[i * NW + w] = cEb[(s0 + i) * NW + w];
           }
-          sErep[i] = V.Erep[s0 + i];
+          if (FILL) sErep[i] = only_new ? (uint32_t)V.Pidx[s0 + i] : V.Erep[s0 + i];
         }
         __syncthreads();
         if (active) {
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
               for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
             }
             const bool hit = own ? (pc == 2 || pc == 4 || (SORTED && pc == 0)) : (pc == 0 || pc == 2);
-            if (hit && (row_new || old_of_new[sErep[i] & ~kSwapBit] < 0)) {
+            if (hit) {
               if (FILL) cand[base + cnt] = (int32_t)(sErep[i] & ~kSwapBit);
               cnt++;
             }
@@ -366,9 +374,9 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int rr = warp; rr < T.n; rr += kConnTile / 32) {
       if (s_row[rr] < 0) continue;
-      const int64_t e2 = T.e0 + rr;
+      const int64_t e2 = part ? (int64_t)V.Pidx[T.e0 + rr] : T.e0 + rr;  // entry == row when the view is partitioned (no time-reversal expansion)
       const Bits<NW> a2 = b_load<NW>(V.Ea, e2);
-      const int64_t p2 = (int64_t)V.Erep[e2];
+      const int64_t p2 = part ? e2 : (int64_t)V.Erep[e2];
       const bool new2 = !old_of_new || old_of_new[p2] < 0;
       const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] + (olen ? olen[p2] : 0) : 0;
       int c2 = s_cnt[rr];
@@ -397,7 +405,16 @@ static void make_conn_tiles(const std::vector<int64_t> &gA, int64_t e_lo, int64_
   int64_t g = std::upper_bound(gA.begin(), gA.end(), e_lo) - gA.begin() - 1;
   for (; g + 1 < (int64_t)gA.size() && gA[g] < e_hi; g++) {
     int64_t a = std::max(gA[g], e_lo), b = std::min(gA[g + 1], e_hi);
-    for (int64_t x = a; x < b; x += kConnTile) tiles.push_back({x, (int32_t)std::min<int64_t>(kConnTile, b - x), (int32_t)g});
+    for (int64_t x = a; x < b; x += kConnTile) tiles.push_back({x, (int16_t)std::min<int64_t>(kConnTile, b - x), (int16_t)0, (int32_t)g});
+  }
+}
+// incremental build: the rows of whole alpha groups [g_lo, g_hi) in the partitioned view (inside a group: the determinants of
+// the previous list, then the new ones; gNew = first new position of every group): old rows meet only new candidates
+static void make_conn_tiles_split(const std::vector<int64_t> &gA, const std::vector<int64_t> &gNew, int64_t g_lo, int64_t g_hi, std::vector<TileDesc> &tiles) {
+  tiles.clear();
+  for (int64_t g = g_lo; g < g_hi; g++) {
+    for (int64_t x = gA[g]; x < gNew[g]; x += kConnTile) tiles.push_back({x, (int16_t)std::min<int64_t>(kConnTile, gNew[g] - x), (int16_t)1, (int32_t)g});
+    for (int64_t x = gNew[g]; x < gA[g + 1]; x += kConnTile) tiles.push_back({x, (int16_t)std::min<int64_t>(kConnTile, gA[g + 1] - x), (int16_t)0, (int32_t)g});
   }
 }
 
@@ -664,6 +681,31 @@ __global__ void old_len_kernel(const int32_t *old_of_new, const int64_t *rowptr_
   const int32_t q = old_of_new[p];
   olen[p] = q >= 0 ? (int32_t)(rowptr_old[q + 1] - rowptr_old[q]) : 0;
 }
+__global__ void is_new_kernel(const int32_t *old_of_new, int64_t n, int32_t *flag) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e <= n) flag[e] = (e < n && old_of_new[e] < 0) ? 1 : 0;
+}
+// stable partition inside every alpha group: previous determinants first, new ones after (newrank = exclusive scan of is_new)
+template <int NW>
+__global__ void partition_view_kernel(const int32_t *old_of_new, const int32_t *newrank, const int32_t *eA, const int64_t *gA_off, const uint64_t *Eb, int64_t n,
+                                      int32_t *Pidx, uint64_t *Pb) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int32_t g = eA[e];
+  const int64_t s = gA_off[g], e1 = gA_off[g + 1];
+  const int64_t nn_before = newrank[e] - newrank[s];
+  const int64_t nold_g = (e1 - s) - (newrank[e1] - newrank[s]);
+  const int64_t pos = old_of_new[e] < 0 ? s + nold_g + nn_before : s + (e - s) - nn_before;
+  Pidx[pos] = (int32_t)e;
+  b_store<NW>(Pb, pos, b_load<NW>(Eb, e));
+}
+__global__ void group_new_off_kernel(const int32_t *newrank, const int64_t *gA_off, int64_t nA, int64_t *gNew_off) {
+  int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g > nA) return;
+  if (g == nA) { gNew_off[g] = gA_off[nA]; return; }
+  const int64_t s = gA_off[g], e1 = gA_off[g + 1];
+  gNew_off[g] = e1 - (newrank[e1] - newrank[s]);
+}
 __global__ void add_i32_kernel(const int32_t *a, const int32_t *b, int32_t *out, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
@@ -802,6 +844,15 @@ int matrix_arrays_ensure(sqmc_b200_handle *h, int64_t entries) {
   h->d_cols = reinterpret_cast<int32_t *>(h->g_cols.base);
   h->d_vals = reinterpret_cast<double *>(h->g_vals.base);
   return 0;
+}
+// called when a device allocation failed: unmap what the matrices do not use
+void matrix_arrays_release_surplus() {
+  for (sqmc_b200_handle *h : g_handles) {
+    if (!h->g_cols.base) continue;
+    const int64_t keep = h->d_rowptr ? h->capacity + kSlack : 0;
+    grow_trim(h->g_cols, (size_t)keep * sizeof(int32_t));
+    grow_trim(h->g_vals, (size_t)keep * sizeof(double));
+  }
 }
 void matrix_arrays_release(sqmc_b200_handle *h) {
   grow_release(h->g_cols);
@@ -1085,7 +1136,36 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   run_hi.release();
   K_grp.release();
   nbr_cnt.release();
-  ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, nbr_off.p, nbr.p};
+  // incremental build: the partitioned row / candidate view
+  DevBuf<int32_t> Pidx;
+  DevBuf<uint64_t> Pb;
+  DevBuf<int64_t> gNew_off;
+  std::vector<int64_t> gNew_host;
+  if (old) {
+    DevBuf<int32_t> isnew, newrank;
+    SQ_CHECK(isnew.alloc(n + 1));
+    SQ_CHECK(newrank.alloc(n + 1));
+    SQ_CHECK(Pidx.alloc(n));
+    SQ_CHECK(Pb.alloc(n * NW));
+    SQ_CHECK(gNew_off.alloc(nA + 1));
+    is_new_kernel<<<nblocks(n + 1), kThreads, 0, s>>>(old_of_new.p, n, isnew.p);
+    SQ_LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, isnew.p, newrank.p, (int)(n + 1), s);
+    DevBuf<char> tmp;
+    SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+    SQ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, isnew.p, newrank.p, (int)(n + 1), s));
+    g_launch_count += 2;
+    partition_view_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(old_of_new.p, newrank.p, eA.p, gA_off.p, Eb, n, Pidx.p, Pb.p);
+    SQ_LAUNCH_CHECK();
+    group_new_off_kernel<<<nblocks(nA + 1), kThreads, 0, s>>>(newrank.p, gA_off.p, nA, gNew_off.p);
+    SQ_LAUNCH_CHECK();
+    gNew_host.resize(nA + 1);
+    SQ_CUDA(cudaMemcpyAsync(gNew_host.data(), gNew_off.p, (nA + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+  }
+  ConnView V{Ea, Eb, Erep_buf.p, eA.p, gA_off.p, eB.p, gB_off.p, EBa.p, EBrep.p, rowE_buf.p, nbr_off.p, nbr.p,
+             old ? Pidx.p : nullptr, old ? Pb.p : nullptr, old ? gNew_off.p : nullptr};
   // host copies for the tile lists: alpha-group offsets and (time-reversal only) the row -> entry map
   std::vector<int64_t> gA_host(nA + 1);
   SQ_CUDA(cudaMemcpy(gA_host.data(), gA_off.p, (nA + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -1110,7 +1190,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     int64_t c0 = std::min<int64_t>(n, per * G.rank), c1 = std::min<int64_t>(n, c0 + per);
     if (c1 > c0) {
       std::vector<TileDesc> tiles;
-      make_conn_tiles(gA_host, row_entry(c0), row_entry(c1 - 1) + 1, tiles);
+      if (old) make_conn_tiles_split(gA_host, gNew_host, 0, nA, tiles);  // single rank: all rows
+      else make_conn_tiles(gA_host, row_entry(c0), row_entry(c1 - 1) + 1, tiles);
       DevBuf<TileDesc> dt;
       SQ_CHECK(dt.alloc((int64_t)tiles.size()));
       SQ_CUDA(cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
@@ -1237,13 +1318,24 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       r_end = std::upper_bound(hprefix.begin() + r + 1, hprefix.begin() + h->row1 + 1, limit) - hprefix.begin() - 1;
       if (r_end <= r) r_end = r + 1;
       if (r_end > h->row1) r_end = h->row1;
+      if (old && r_end < h->row1) {  // incremental build: chunks end on alpha-group boundaries (tiles come from the partitioned view)
+        int64_t gb = std::upper_bound(gA_host.begin(), gA_host.end(), r_end) - gA_host.begin() - 1;
+        if (gA_host[gb] <= r) gb++;
+        r_end = gA_host[gb];
+      }
     }
     int64_t ml = 0;
     for (int64_t q = r; q < r_end; q++) ml = std::max(ml, hprefix[q + 1] - hprefix[q]);
     maxlen = std::max(maxlen, ml);
     tmp_cap = std::max(tmp_cap, hprefix[r_end] - hprefix[r]);
     rows_cap = std::max(rows_cap, r_end - r);
-    make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
+    if (old) {
+      const int64_t ga = std::lower_bound(gA_host.begin(), gA_host.end(), r) - gA_host.begin();
+      const int64_t gb = std::lower_bound(gA_host.begin(), gA_host.end(), r_end) - gA_host.begin();
+      make_conn_tiles_split(gA_host, gNew_host, ga, gb, fill_tiles);
+    } else {
+      make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
+    }
     plan.push_back({r, r_end, (int64_t)all_tiles.size(), (int64_t)fill_tiles.size(), ml});
     all_tiles.insert(all_tiles.end(), fill_tiles.begin(), fill_tiles.end());
     r = r_end;
@@ -1335,12 +1427,9 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->nnz_upper = (tot + n) / 2;
   h->scale = 1.0;
 
-  // ---- give back the memory above the stored entries when the candidate bound was loose (the arrays keep their address)
-  if (h->capacity - h->nnz_local > (1ll << 26)) {
-    h->capacity = std::max<int64_t>(h->nnz_local, 1);
-    grow_trim(h->g_cols, (size_t)(h->capacity + kSlack) * sizeof(int32_t));
-    grow_trim(h->g_vals, (size_t)(h->capacity + kSlack) * sizeof(double));
-  }
+  // the surplus above the stored entries (candidate bound vs kept entries) stays mapped: unmapping costs ~10 ms per 256 MB and
+  // the next build needs the room again; it is given back only when some other allocation runs out of memory (release_surplus)
+  h->capacity = std::max<int64_t>(h->nnz_local, 1);
   HM.mark("nnz reduce + shrink");
   SQ_CHECK(alloc_work_vectors(h));
   SQ_CHECK(spmv_setup_bins(h));
@@ -1391,6 +1480,7 @@ int build_h(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *det
     free_matrix(h);
     FM.mark("free previous matrix");
   }
+  if (inc) h->capacity = old.nnz;  // the entries of the previous matrix stay in the arrays until the merge has consumed them
   h->last_build_incremental = inc ? 1 : 0;
   int rc = h->NW == 1 ? build_impl<1>(h, n, dets_up, dets_dn, inc ? &old : nullptr) : build_impl<2>(h, n, dets_up, dets_dn, inc ? &old : nullptr);
   if (rc) {  // leave no half-built matrix behind

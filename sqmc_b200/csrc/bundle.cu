@@ -232,16 +232,22 @@ __device__ __forceinline__ void blk_load(Blk &B, const int32_t *cols, const doub
   B.v23 = ld_val2(vals + o + 4 * lane + 2, P);
 }
 
+// SCAT (distributed-slice entry points): the kernel does not write y but sends every finished row sum -- plus c*w[row] for the
+// projector, do_walk.f90:2290 -- straight to the rank that owns the determinant (a store into that rank's exchange buffer
+// over NVLink, p2p.cu), and the last CTA publishes the epoch to every peer: H.v and the reduce-scatter of
+// mpi_redscatt_real_dparray (mpi_routines.f90:1592) are one kernel, the transfers overlap the arithmetic bundle by bundle.
+
 // NV = 1: y = H x.  NV = 2: two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x / y hold the
 // two vectors interleaved (x[2*col + k]), one 16-byte gather serves both and the matrix is streamed once
 // (algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)).
-template <int R, int MODE, int NV, int MINB>
+template <int R, int MODE, int NV, int MINB, bool SCAT>
 __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
-                                                              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
+                                                              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                                                              OwnerScatter O) {
   const Policies P;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (b >= nb) return;
+  if (b < nb) {
   const int64_t r0 = b * R;
   const int64_t e0 = rowptr[r0], e1 = rowptr[min(r0 + R, nloc)];
   const Sigma S(e0, e1 - e0);
@@ -323,11 +329,30 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
     if (lane == r) { m0 = a0; m1 = a1; }
   }
   if (lane < R && r0 + lane < nloc) {
-    if (NV == 1) {
-      y[r0 + lane] = m0;
+    const int64_t row = r0 + lane;
+    if (SCAT) {
+      double v = m0;
+      if (O.w) v = v + O.c * O.w[row];
+      O.dst[O.owner[row]][O.pos[row]] = v;
+    } else if (NV == 1) {
+      y[row] = m0;
     } else {
-      y[2 * (r0 + lane)] = m0;
-      y[2 * (r0 + lane) + 1] = m1;
+      y[2 * row] = m0;
+      y[2 * row + 1] = m1;
+    }
+  }
+  }  // b < nb
+  if (SCAT) {  // all rows of this CTA are on their way: the last CTA publishes the epoch to every peer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long prev = atomicAdd(O.counter, 1ull);
+      if (prev == gridDim.x - 1) {
+        *O.counter = 0ull;
+        __threadfence_system();
+        for (int p = 0; p < O.nranks; p++)
+          if (O.flag[p]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(O.flag[p]), "l"(O.epoch) : "memory");
+      }
     }
   }
 }
@@ -445,7 +470,8 @@ static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream
   if (nb == 0) return 0;
   const unsigned grid = (unsigned)div_up(nb * 32, (int64_t)256);
   const int var = bundle_variant();
-#define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y)
+  const OwnerScatter none = {};
+#define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none)
   if (R == 4) {
     if (var == 14) SQ_BL(4, 1, 4); else if (var == 15) SQ_BL(4, 1, 5); else if (var == 4) SQ_BL(4, 0, 4); else SQ_BL(4, 0, 5);
   } else {
@@ -456,6 +482,19 @@ static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream
   return 0;
 }
 int bundle_spmv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) { return launch_hv<1>(h, x, y, s); }
+
+// y = H x (+ c*w) with every row sum sent to its owner from inside the kernel (see OwnerScatter).  The grid always has at
+// least one CTA so that a rank without rows still publishes its epoch.
+int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x, const OwnerScatter &O, cudaStream_t s) {
+  const int64_t nloc = h->row1 - h->row0;
+  const int R = h->bundle_R;
+  const int64_t nb = div_up(nloc, (int64_t)R);
+  const unsigned grid = (unsigned)std::max<int64_t>(1, div_up(nb * 32, (int64_t)256));
+  if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O);
+  else bundle_hv_kernel<2, 1, 1, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O);
+  SQ_LAUNCH_CHECK();
+  return 0;
+}
 
 // y2 = H x2 for two interleaved vectors; only on bundled matrices (the caller falls back to two H.v otherwise)
 int bundle_spmm2(sqmc_b200_handle *h, const double *x2, double *y2, cudaStream_t s) {

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "elements.cuh"
 
+struct sqmc_b200_handle;
 namespace sqmc {
 
 struct Global {
@@ -21,6 +22,7 @@ struct Global {
   cudaStream_t stream = nullptr;  // all library work is issued on this stream unless a stream is passed in
 };
 extern Global G;
+extern std::vector<struct ::sqmc_b200_handle *> g_handles;  // live handles (their growable arrays can give memory back)
 
 // RAII device buffer for temporaries.  Stream-ordered allocation from the device's default memory pool on the library
 // stream (the pool keeps up to kPoolKeepBytes cached, sqmc_b200_init): the selection / build / conversion paths allocate
@@ -101,6 +103,18 @@ int grow_ensure(GrowBuf &b, size_t bytes);
 void grow_trim(GrowBuf &b, size_t bytes);
 void grow_release(GrowBuf &b);
 
+// arguments of the fused H.v + owner exchange kernel (csrc/bundle.cu)
+struct OwnerScatter {
+  double *dst[kMaxRanks];               // every rank's result buffer (this rank's own: device memory)
+  unsigned long long *flag[kMaxRanks];  // the calling rank's word in every rank's flag array (null entries: single rank)
+  unsigned long long *counter;          // local CTA counter
+  const int32_t *owner, *pos;           // per local row: owning rank, position inside the owner's slice
+  const double *w;                      // projector: deltaw = H.w + c*w (null: plain product)
+  double c;
+  unsigned long long epoch;
+  int nranks;
+};
+
 // number of degree bins for the SpMV (sub-warp vector sizes 2,4,8,16,32 + CTA-per-row)
 static const int kNumBins = 6;
 
@@ -153,6 +167,7 @@ struct sqmc_b200_handle {
   int32_t *d_dest_rank = nullptr;           // [nloc] owner rank of the local row's determinant
   int32_t *d_dest_pos = nullptr;            // [nloc] its position inside the owner's slice
   int32_t *d_my_internal = nullptr;         // [my_n] internal row of the k-th determinant this rank owns
+  unsigned long long *d_scat_counter = nullptr;  // CTA counter of the fused H.v + owner exchange kernel on a single rank
   // ---- work buffers ----
   double *d_x = nullptr;   // n (global length, internal order)
   double *d_y = nullptr;   // local rows
@@ -180,6 +195,7 @@ int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const in
 void free_matrix(sqmc_b200_handle *h);
 int matrix_arrays_ensure(sqmc_b200_handle *h, int64_t entries);  // (re)map the growable cols / vals arrays
 void matrix_arrays_release(sqmc_b200_handle *h);
+void matrix_arrays_release_surplus();  // all handles: unmap the part of the entry arrays no matrix uses (out-of-memory path)
 void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *starts);
 int upload_dets(int NW, int norb, const void *host16, uint64_t *out, int64_t n, cudaStream_t s);
 int sort_pairs_index(int NW, int norb, const uint64_t *a, const uint64_t *b, int32_t *idx, int64_t n, cudaStream_t s);
@@ -211,6 +227,10 @@ void p2p_release(sqmc_b200_handle *h);
 int p2p_gather(sqmc_b200_handle *h, const double *src, int64_t count, int64_t off, int which, cudaStream_t s, double **full_out);
 int p2p_to_owners(sqmc_b200_handle *h, const double *src, const int32_t *owner, const int32_t *pos, int64_t count, cudaStream_t s, double **y_out);
 int p2p_barrier(sqmc_b200_handle *h, cudaStream_t s);
+// owner exchange done by the producing kernel itself: fills the peer tables / epoch of O (after the barrier that makes the
+// peers' result buffers writable), then p2p_owner_wait queues the wait for everybody's rows
+int p2p_owner_begin(sqmc_b200_handle *h, OwnerScatter &O, cudaStream_t s);
+int p2p_owner_wait(sqmc_b200_handle *h, const OwnerScatter &O, cudaStream_t s, double **y_out);
 int p2p_check(sqmc_b200_handle *h, cudaStream_t s);
 double *p2p_x(sqmc_b200_handle *h, int r, int b);
 // local.cu: the caller's data distribution (owned slices in / out)
@@ -229,6 +249,7 @@ int bundle_encode_r(sqmc_b200_handle *h, int R);  // same with an explicit bundl
 int bundle_decode(sqmc_b200_handle *h);  // exact inverse
 int bundle_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
 int bundle_spmm2(sqmc_b200_handle *h, const double *x2_dev, double *y2_dev, cudaStream_t s);  // two interleaved vectors
+int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x_dev, const OwnerScatter &O, cudaStream_t s);  // H.v fused with the owner exchange
 int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 // davidson.cu
 // local_io: v0 / evecs are this rank's owned slices (my_n x n_states, leading dimension my_n) instead of full vectors

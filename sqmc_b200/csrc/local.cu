@@ -73,6 +73,10 @@ int set_ownership(sqmc_b200_handle *h, const int32_t *owner_host, int64_t *n_own
   SQ_CUDA(cudaMalloc(&h->d_dest_rank, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
   SQ_CUDA(cudaMalloc(&h->d_dest_pos, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
   SQ_CUDA(cudaMalloc(&h->d_my_internal, std::max<int64_t>(h->my_n, 1) * sizeof(int32_t)));
+  if (!h->d_scat_counter) {
+    SQ_CUDA(cudaMalloc(&h->d_scat_counter, sizeof(unsigned long long)));
+    SQ_CUDA(cudaMemset(h->d_scat_counter, 0, sizeof(unsigned long long)));
+  }
   DevBuf<int32_t> owner, owner_sorted, rows, sorted_row, shuf_pos;
   SQ_CHECK(owner.alloc(n));
   SQ_CHECK(owner_sorted.alloc(n));
@@ -174,19 +178,50 @@ int store_local_vector(sqmc_b200_handle *h, const double *block, double *host_sl
   return p2p_check(h, s);
 }
 
+// H.v (+ c*w) on the gathered vector in h->d_x, results delivered to their owners; host_slice receives this rank's slice.
+// Row-bundle layout: ONE kernel multiplies and sends every row sum to its owner's buffer (bundle_hv_kernel<SCAT>);
+// plain rows (SQMC_BUNDLE=0) or the NCCL fallback: multiply, then exchange.
+static int multiply_to_owners(sqmc_b200_handle *h, double c, bool add_w, double *host_slice, cudaStream_t s) {
+  const int64_t nloc = h->row1 - h->row0;
+  const bool peers = G.nranks > 1 && h->p2p.on;
+  if (h->bundle_R && (G.nranks == 1 || peers)) {
+    OwnerScatter O = {};
+    double *y = nullptr;
+    if (peers) {
+      SQ_CHECK(p2p_owner_begin(h, O, s));
+    } else {  // one rank: the "owner buffer" is the caller-order staging vector
+      O.nranks = 1;
+      O.dst[0] = h->d_tmp;
+      O.counter = &h->d_scat_counter[0];
+      O.epoch = 1;
+    }
+    O.owner = h->d_dest_rank;
+    O.pos = h->d_dest_pos;
+    O.w = add_w ? h->d_x + h->row0 : nullptr;
+    O.c = c;
+    SQ_CHECK(bundle_spmv_scatter(h, h->d_x, O, s));
+    if (peers) SQ_CHECK(p2p_owner_wait(h, O, s, &y));
+    else y = h->d_tmp;
+    if (h->my_n > 0) SQ_CUDA(cudaMemcpyAsync(host_slice, y, h->my_n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    return p2p_check(h, s);
+  }
+  SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, s));
+  if (add_w) SQ_CHECK(projector_epilogue(h->d_y, h->d_x + h->row0, c, nloc, s));
+  return store_local_vector(h, h->d_y, host_slice, s);
+}
+
 int matvec_local(sqmc_b200_handle *h, const double *x_local, double *y_local) {
   cudaStream_t s = G.stream;
   SQ_CHECK(load_local_vector(h, x_local, s));
-  SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, s));
-  return store_local_vector(h, h->d_y, y_local, s);
+  return multiply_to_owners(h, 0.0, false, y_local, s);
 }
 
+// deltaw = Hstored . w (do_walk.f90:2259) + e_trial*tau*w (:2290), reduce-scattered to the owners (:2260)
 int projector_local(sqmc_b200_handle *h, double tau, double e_trial, const double *w_local, double *deltaw_local) {
   cudaStream_t s = G.stream;
   SQ_CHECK(load_local_vector(h, w_local, s));
-  SQ_CHECK(spmv_launch(h, h->d_x, h->d_y, s));                                                    // deltaw = Hstored . w (do_walk.f90:2259)
-  SQ_CHECK(projector_epilogue(h->d_y, h->d_x + h->row0, e_trial * tau, h->row1 - h->row0, s));   // += e_trial*tau*w (:2290)
-  return store_local_vector(h, h->d_y, deltaw_local, s);
+  return multiply_to_owners(h, e_trial * tau, true, deltaw_local, s);
 }
 
 }  // namespace sqmc

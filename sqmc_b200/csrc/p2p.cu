@@ -317,4 +317,25 @@ int p2p_to_owners(sqmc_b200_handle *h, const double *src, const int32_t *owner, 
   return 0;
 }
 
+// ---- owner exchange fused into the producing kernel (bundle_hv_kernel<..., SCAT = true>)
+int p2p_owner_begin(sqmc_b200_handle *h, OwnerScatter &O, cudaStream_t s) {
+  P2P &P = h->p2p;
+  SQ_CHECK(p2p_barrier(h, s));  // every rank has finished reading its result buffer of the previous exchange
+  O.epoch = ++P.epoch_y;
+  O.nranks = G.nranks;
+  O.counter = flag_base(P.slab) + 48;
+  for (int r = 0; r < kMaxRanks; r++) {
+    O.dst[r] = r < G.nranks ? p2p_y(h, r) : nullptr;
+    O.flag[r] = r < G.nranks ? flag_base(P.peer[r]) + 16 + G.rank : nullptr;
+  }
+  return 0;
+}
+int p2p_owner_wait(sqmc_b200_handle *h, const OwnerScatter &O, cudaStream_t s, double **y_out) {
+  P2P &P = h->p2p;
+  wait_flags_kernel<<<1, 32, 0, s>>>(flag_base(P.slab) + 16, G.nranks, O.epoch, flag_base(P.slab) + 49);
+  SQ_LAUNCH_CHECK();
+  *y_out = p2p_y(h, G.rank);
+  return 0;
+}
+
 }  // namespace sqmc
