@@ -815,8 +815,9 @@ int gather_strings(int NW, const uint64_t *src, const int32_t *idx, uint64_t *ou
 }
 
 void free_matrix(sqmc_b200_handle *h) {
+  // per-build arrays come from the stream-ordered pool (devbuf_alloc): freeing and re-allocating them costs no unmapping
   auto F = [](auto *&p) {
-    if (p) cudaFree(p);
+    if (p) devbuf_free(p);
     p = nullptr;
   };
   F(h->d_up); F(h->d_dn); F(h->d_perm); F(h->d_iperm); F(h->d_rowptr);
@@ -867,9 +868,9 @@ struct OldMatrix {
   int32_t *d_perm = nullptr, *d_iperm = nullptr;
   int64_t *d_rowptr = nullptr;
   ~OldMatrix() {
-    if (d_perm) cudaFree(d_perm);
-    if (d_iperm) cudaFree(d_iperm);
-    if (d_rowptr) cudaFree(d_rowptr);
+    if (d_perm) devbuf_free(d_perm);
+    if (d_iperm) devbuf_free(d_iperm);
+    if (d_rowptr) devbuf_free(d_rowptr);
   }
 };
 struct EventSet {  // timing events of one build, destroyed on every exit path
@@ -880,9 +881,9 @@ struct EventSet {  // timing events of one build, destroyed on every exit path
 
 static int alloc_work_vectors(sqmc_b200_handle *h) {
   SQ_CHECK(p2p_setup(h, h->n));  // collective: (re)maps the peers' exchange buffers when the vectors outgrew them
-  SQ_CUDA(cudaMalloc(&h->d_x, std::max<int64_t>(h->n, 1) * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&h->d_y, std::max<int64_t>(h->row1 - h->row0, 1) * sizeof(double)));
-  SQ_CUDA(cudaMalloc(&h->d_tmp, std::max<int64_t>(h->n, 1) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_x, std::max<int64_t>(h->n, 1) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_y, std::max<int64_t>(h->row1 - h->row0, 1) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_tmp, std::max<int64_t>(h->n, 1) * sizeof(double)));
   return 0;
 }
 
@@ -938,8 +939,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   }
 
   // ---- internal (alpha-major) order
-  SQ_CUDA(cudaMalloc(&h->d_perm, n * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_iperm, n * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_perm, n * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_iperm, n * sizeof(int32_t)));
   iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, n);
   SQ_LAUNCH_CHECK();
   {
@@ -950,8 +951,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   }
   invert_perm_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, h->d_iperm, n);
   SQ_LAUNCH_CHECK();
-  SQ_CUDA(cudaMalloc(&h->d_up, n * NW * sizeof(uint64_t)));
-  SQ_CUDA(cudaMalloc(&h->d_dn, n * NW * sizeof(uint64_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_up, n * NW * sizeof(uint64_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_dn, n * NW * sizeof(uint64_t)));
   gather_bits_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(up_c.p, h->d_perm, h->d_up, n);
   SQ_LAUNCH_CHECK();
   gather_bits_kernel<NW><<<nblocks(n), kThreads, 0, s>>>(dn_c.p, h->d_perm, h->d_dn, n);
@@ -1252,13 +1253,14 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   SQ_CHECK(matrix_arrays_ensure(h, h->capacity));
   SQ_CUDA(cudaMemsetAsync(h->d_cols + h->capacity, 0, kSlack * sizeof(int32_t), s));
   SQ_CUDA(cudaMemsetAsync(h->d_vals + h->capacity, 0, kSlack * sizeof(double), s));
-  SQ_CUDA(cudaMalloc(&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_rowptr, (nloc + 1) * sizeof(int64_t)));
   // incremental build: the previous entries move to the END of the arrays.  New rows are written from the front in
   // ascending row order and old rows are consumed in the same order, so the write position never overtakes the unread
   // old entries (at most capacity - nnz_old new entries are ever added).  The move goes through a bounded staging buffer,
   // back to front, because source and destination overlap.
   const int32_t *old_cols = nullptr;
   const double *old_vals = nullptr;
+  HM.mark("map entry arrays");
   if (old) {
     const int64_t shift = h->capacity - old->nnz;
     old_cols = h->d_cols + shift;
@@ -1282,8 +1284,9 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     }
   }
 
+  HM.mark("move old entries to the end");
   // diagonal of the local rows: read by eval_kernel, kept for Davidson's preconditioner and the projector
-  SQ_CUDA(cudaMalloc(&h->d_diag, std::max<int64_t>(nloc, 1) * sizeof(double)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_diag, std::max<int64_t>(nloc, 1) * sizeof(double)));
   if (nloc > 0) {
     SQ_MODEL_DISPATCH(T, (diag_rows_kernel<NW, kModel, kTS><<<nblocks(nloc), kThreads, 0, s>>>(T, h->d_up, h->d_dn, h->d_perm, h->row0, nloc, h->d_diag)));
     SQ_LAUNCH_CHECK();
@@ -1540,8 +1543,8 @@ int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const in
   h->row_starts = {0, n};
   h->row0 = 0;
   h->row1 = n;
-  SQ_CUDA(cudaMalloc(&h->d_perm, n * 4));
-  SQ_CUDA(cudaMalloc(&h->d_iperm, n * 4));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_perm, n * 4));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_iperm, n * 4));
   iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_perm, n);
   SQ_LAUNCH_CHECK();
   iota_kernel<<<nblocks(n), kThreads, 0, s>>>(h->d_iperm, n);

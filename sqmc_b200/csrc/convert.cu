@@ -297,7 +297,7 @@ int import_upper_device(sqmc_b200_handle *h, int64_t n, const int64_t *counts, c
   SQ_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   SQ_CUDA(cudaStreamSynchronize(s));
   if (hbad) { set_error("import_upper: column out of range"); return 2; }
-  SQ_CUDA(cudaMalloc(&h->d_rowptr, (n + 1) * sizeof(int64_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_rowptr, (n + 1) * sizeof(int64_t)));
   {
     size_t tb = 0;
     auto it = cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *>(deg.p, cub::CastOp<int64_t>());

@@ -67,12 +67,12 @@ int set_ownership(sqmc_b200_handle *h, const int32_t *owner_host, int64_t *n_own
   }
   for (int r = 0; r < R; r++) h->own_off[r + 1] = h->own_off[r] + h->own_count[r];
   h->my_n = h->own_count[G.rank];
-  auto F = [](int32_t *&p) { if (p) cudaFree(p); p = nullptr; };
+  auto F = [](int32_t *&p) { if (p) devbuf_free(p); p = nullptr; };
   F(h->d_shuf_of_internal); F(h->d_dest_rank); F(h->d_dest_pos); F(h->d_my_internal);
-  SQ_CUDA(cudaMalloc(&h->d_shuf_of_internal, n * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_dest_rank, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_dest_pos, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
-  SQ_CUDA(cudaMalloc(&h->d_my_internal, std::max<int64_t>(h->my_n, 1) * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_shuf_of_internal, n * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_dest_rank, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_dest_pos, std::max<int64_t>(nloc, 1) * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_my_internal, std::max<int64_t>(h->my_n, 1) * sizeof(int32_t)));
   if (!h->d_scat_counter) {
     SQ_CUDA(cudaMalloc(&h->d_scat_counter, sizeof(unsigned long long)));
     SQ_CUDA(cudaMemset(h->d_scat_counter, 0, sizeof(unsigned long long)));

@@ -38,11 +38,11 @@ struct BinPred {
 int spmv_setup_bins(sqmc_b200_handle *h) {
   cudaStream_t s = G.stream;
   const int64_t nloc = h->row1 - h->row0;
-  if (h->d_bin_rows) cudaFree(h->d_bin_rows);
+  if (h->d_bin_rows) devbuf_free(h->d_bin_rows);
   h->d_bin_rows = nullptr;
   for (int b = 0; b <= kNumBins; b++) h->bin_off[b] = 0;
   if (nloc == 0) return 0;
-  SQ_CUDA(cudaMalloc(&h->d_bin_rows, nloc * sizeof(int32_t)));
+  SQ_CHECK(devbuf_alloc((void **)&h->d_bin_rows, nloc * sizeof(int32_t)));
   int32_t *d_num = nullptr;
   SQ_CUDA(cudaMalloc(&d_num, sizeof(int32_t)));
   cub::CountingInputIterator<int32_t> it(0);
@@ -173,7 +173,7 @@ int gather_vector(sqmc_b200_handle *h, const double *block, int k, cudaStream_t 
   }
   double *buf = h->d_x;
   if (k == 2) {
-    if (!h->d_x2) SQ_CUDA(cudaMalloc(&h->d_x2, std::max<int64_t>(h->n, 1) * 2 * sizeof(double)));
+    if (!h->d_x2) SQ_CHECK(devbuf_alloc((void **)&h->d_x2, std::max<int64_t>(h->n, 1) * 2 * sizeof(double)));
     buf = h->d_x2;
   }
   if (nloc > 0 && block != buf + h->row0 * k) SQ_CUDA(cudaMemcpyAsync(buf + h->row0 * k, block, nloc * k * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -305,8 +305,8 @@ int spmv_pair(sqmc_b200_handle *h, const double *Va, const double *Vb, double *H
     return spmv_block(h, Vb, HVb, s);
   }
   if (!h->d_y2) {
-    SQ_CUDA(cudaMalloc(&h->d_xi2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
-    SQ_CUDA(cudaMalloc(&h->d_y2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
+    SQ_CHECK(devbuf_alloc((void **)&h->d_xi2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
+    SQ_CHECK(devbuf_alloc((void **)&h->d_y2, std::max<int64_t>(nloc, 1) * 2 * sizeof(double)));
   }
   if (nloc > 0) {
     interleave2_kernel<<<(unsigned)div_up(nloc, 256), 256, 0, s>>>(Va, Vb, h->d_xi2, nloc);

@@ -121,3 +121,82 @@ def test_round_robin_selection_merge_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert res[0][2] == res[1][2] and res[0][3] == res[1][3]
+
+
+def _worker_local_slices(rank, world, port, q):
+    """the distributed-slice data flow of csrc/local.cu + csrc/p2p.cu restated with numpy index maps over gloo:
+    owned slices (hash ownership, ascending list order) -> slice-concatenated vector on every rank -> one permutation into
+    the internal (alpha-major) order -> row-sharded full-row H.v -> every result row sent to its owner.  Checked against the
+    oracle's emulation of fast_sparse_matrix_multiply_local_band + MPI_REDUCE_SCATTER (do_walk.f90:2259-2260)."""
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+    from oracle import oracle as O
+    from sqmc_b200 import _lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = O.System.heg(3, 0.5, 14, 7, 1.49)
+    r = S.hci(1e-3, n_states=1, max_iters=1)
+    up, dn = r["up"], r["dn"]
+    cnt, idx, val = S.build_upper(up, dn)
+    n = len(cnt)
+    A = O.upper_to_scipy(cnt, idx, val).tocsr()
+    # internal order = alpha-major sort of the list; perm[p] = caller row of internal row p (what build_h computes on the device)
+    perm = np.lexsort((dn[:, 0], up[:, 0]))
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+    Aint = A[perm][:, perm].tocsr()
+    prefix = np.zeros(n + 1, dtype=np.int64)
+    prefix[1:] = np.cumsum(np.diff(Aint.indptr))
+    starts = np.zeros(world + 1, dtype=np.int64)
+    L = _lib.load()
+    assert L.sqmc_b200_partition_rows(prefix.ctypes.data_as(C.c_void_p), n, world, starts.ctypes.data_as(C.c_void_p)) == 0
+    r0, r1 = int(starts[rank]), int(starts[rank + 1])
+    # ---- set_ownership maps (local.cu): stable sort by owner = slice-concatenated order
+    owner = O.det_owner(up, dn, world)
+    sorted_row = np.argsort(owner, kind="stable")
+    shuf_pos = np.empty(n, dtype=np.int64)
+    shuf_pos[sorted_row] = np.arange(n)
+    off = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=world))])
+    shuf_of_internal = shuf_pos[perm]
+    dest_rank = owner[perm[r0:r1]]
+    dest_pos = shuf_pos[perm[r0:r1]] - off[dest_rank]
+    # ---- slices in
+    x = np.random.default_rng(17).uniform(-1, 1, n)
+    mine = np.nonzero(owner == rank)[0]
+    mx = int(np.max(np.diff(off)))
+    pad = torch.zeros(mx, dtype=torch.float64)
+    pad[:len(mine)] = torch.from_numpy(x[mine])
+    bufs = [torch.zeros(mx, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    xs = np.concatenate([bufs[k][:off[k + 1] - off[k]].numpy() for k in range(world)])      # slice-concatenated order
+    x_int = xs[shuf_of_internal]
+    y_blk = Aint[r0:r1] @ x_int
+    # ---- results to their owners (every row goes to exactly one rank)
+    rows = torch.zeros((n, 3), dtype=torch.float64)
+    rows[r0:r1, 0] = torch.from_numpy(y_blk)
+    rows[r0:r1, 1] = torch.from_numpy(dest_rank.astype(np.float64))
+    rows[r0:r1, 2] = torch.from_numpy(dest_pos.astype(np.float64))
+    dist.all_reduce(rows)                      # stands for the peer stores: disjoint row blocks, zeros elsewhere
+    rows = rows.numpy()
+    sel = rows[:, 1].astype(np.int64) == rank
+    y_loc = np.zeros(len(mine))
+    y_loc[rows[sel, 2].astype(np.int64)] = rows[sel, 0]
+    ref = O.matvec_local_band_redscatt(cnt, idx, val, owner, [x[owner == c] for c in range(world)])[rank]
+    ok = np.allclose(x_int, x[perm]) and y_loc.shape == ref.shape and np.max(np.abs(y_loc - ref)) <= 1e-12 * np.max(np.abs(ref))
+    q.put((rank, bool(ok), len(mine)))
+    dist.destroy_process_group()
+
+
+def test_distributed_slice_data_flow_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_local_slices, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(m for _, _, m in res) == 277
