@@ -706,6 +706,10 @@ __global__ void group_new_off_kernel(const int32_t *newrank, const int64_t *gA_o
   const int64_t s = gA_off[g], e1 = gA_off[g + 1];
   gNew_off[g] = e1 - (newrank[e1] - newrank[s]);
 }
+__global__ void gather_i64_kernel(const int64_t *src, const int64_t *idx, int64_t *dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
 __global__ void add_i32_kernel(const int32_t *a, const int32_t *b, int32_t *out, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
@@ -826,6 +830,8 @@ void free_matrix(sqmc_b200_handle *h) {
   F(h->d_shuf_of_internal); F(h->d_dest_rank); F(h->d_dest_pos); F(h->d_my_internal);
   h->own_set = false; h->my_n = 0; h->own_count.clear(); h->own_off.clear();
   F(h->d_diag);
+  x_textures_release(h);
+  h->bins_ready = false;
   h->bundle_R = 0;
   h->n = 0; h->nnz_local = 0; h->nnz_full = 0; h->nnz_upper = 0; h->capacity = 0; h->scale = 1.0;
   h->row_starts.clear();
@@ -1234,16 +1240,53 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   DevBuf<int64_t> cand_prefix;  // n+1 exclusive prefix of the segment lengths over ALL rows
   SQ_CHECK(cand_prefix.alloc(n + 1));
   SQ_CHECK(exclusive_scan_i32_to_i64(seg_count, cand_prefix.p, n, s));
-  std::vector<int64_t> hprefix(n + 1);
-  SQ_CUDA(cudaMemcpy(hprefix.data(), cand_prefix.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  // The host plans with the prefix SAMPLED at a few thousand rows (row blocks of the ranks and chunk boundaries fall on sample
+  // rows): every 256th row for large lists, every row for small ones, and the alpha-group boundaries in an incremental
+  // build (whose tiles cover whole groups).  Downloading and walking the full n-long prefix cost tens of ms of host time.
+  std::vector<int64_t> srow;
+  if (old) {
+    srow = gA_host;
+  } else {
+    const int64_t S = n > (1ll << 20) ? 256 : 1;
+    srow.reserve(n / S + 2);
+    for (int64_t q = 0; q < n; q += S) srow.push_back(q);
+    srow.push_back(n);
+  }
+  const int64_t ns = (int64_t)srow.size() - 1;  // sample intervals
+  std::vector<int64_t> spre(ns + 1);
+  int64_t max_seg = 0;
+  {
+    DevBuf<int64_t> d_srow, d_spre;
+    SQ_CHECK(d_srow.alloc(ns + 1));
+    SQ_CHECK(d_spre.alloc(ns + 1));
+    SQ_CUDA(cudaMemcpyAsync(d_srow.p, srow.data(), (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    gather_i64_kernel<<<nblocks(ns + 1), kThreads, 0, s>>>(cand_prefix.p, d_srow.p, d_spre.p, ns + 1);
+    SQ_LAUNCH_CHECK();
+    SQ_CUDA(cudaMemcpyAsync(spre.data(), d_spre.p, (ns + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    // longest row segment (selects the sort kernel of the time-reversal path)
+    DevBuf<int32_t> mx;
+    SQ_CHECK(mx.alloc(1));
+    size_t tb = 0;
+    cub::DeviceReduce::Max(nullptr, tb, seg_count, mx.p, (int)n, s);
+    DevBuf<char> tmp;
+    SQ_CHECK(tmp.alloc((int64_t)tb + 16));
+    SQ_CUDA(cub::DeviceReduce::Max(tmp.p, tb, seg_count, mx.p, (int)n, s));
+    g_launch_count += 1;
+    int32_t m32 = 0;
+    SQ_CUDA(cudaMemcpyAsync(&m32, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    max_seg = m32;
+  }
   cand_prefix.release();
-  const int64_t Ttot = hprefix[n];
+  const int64_t Ttot = spre[ns];
+  std::vector<int64_t> sstart(G.nranks + 1, 0);
+  partition_rows(spre.data(), ns, G.nranks, sstart.data());  // balance the candidates over the ranks, boundaries on sample rows
   h->row_starts.assign(G.nranks + 1, 0);
-  partition_rows(hprefix.data(), n, G.nranks, h->row_starts.data());
+  for (int rk = 0; rk <= G.nranks; rk++) h->row_starts[rk] = srow[sstart[rk]];
   h->row0 = h->row_starts[G.rank];
   h->row1 = h->row_starts[G.rank + 1];
   const int64_t nloc = h->row1 - h->row0;
-  const int64_t Tloc = hprefix[h->row1] - hprefix[h->row0];
+  const int64_t Tloc = spre[sstart[G.rank + 1]] - spre[sstart[G.rank]];
   HM.mark("prefix + partition");
   cudaEventRecord(ev[2], s);
 
@@ -1302,6 +1345,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   DevBuf<int64_t> cptr, rptr;
   int64_t r = h->row0;
   int64_t tmp_cap = 0, rows_cap = 0;
+  (void)Ttot;
   // the chunk loop is asynchronous: the running entry count lives on the device, the scans use one preallocated
   // workspace, and the per-chunk timing events are read after the loop; the host prepares the next chunk's tiles meanwhile
   DevBuf<int64_t> base_dev;
@@ -1314,34 +1358,20 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   struct ChunkPlan { int64_t r, r_end, tile_off, ntiles, ml; };
   std::vector<ChunkPlan> plan;
   std::vector<TileDesc> all_tiles;
-  while (r < h->row1) {
-    int64_t r_end = r + 1;
-    {  // largest r_end with prefix[r_end]-prefix[r] <= kChunkCand
-      int64_t limit = hprefix[r] + kChunkCand;
-      r_end = std::upper_bound(hprefix.begin() + r + 1, hprefix.begin() + h->row1 + 1, limit) - hprefix.begin() - 1;
-      if (r_end <= r) r_end = r + 1;
-      if (r_end > h->row1) r_end = h->row1;
-      if (old && r_end < h->row1) {  // incremental build: chunks end on alpha-group boundaries (tiles come from the partitioned view)
-        int64_t gb = std::upper_bound(gA_host.begin(), gA_host.end(), r_end) - gA_host.begin() - 1;
-        if (gA_host[gb] <= r) gb++;
-        r_end = gA_host[gb];
-      }
-    }
-    int64_t ml = 0;
-    for (int64_t q = r; q < r_end; q++) ml = std::max(ml, hprefix[q + 1] - hprefix[q]);
-    maxlen = std::max(maxlen, ml);
-    tmp_cap = std::max(tmp_cap, hprefix[r_end] - hprefix[r]);
+  maxlen = max_seg;
+  for (int64_t i = sstart[G.rank], i_end = sstart[G.rank + 1]; i < i_end;) {
+    // largest sample j with prefix[j] - prefix[i] <= kChunkCand
+    int64_t j = std::upper_bound(spre.begin() + i + 1, spre.begin() + i_end + 1, spre[i] + kChunkCand) - spre.begin() - 1;
+    if (j <= i) j = i + 1;
+    r = srow[i];
+    const int64_t r_end = srow[j];
+    tmp_cap = std::max(tmp_cap, spre[j] - spre[i]);
     rows_cap = std::max(rows_cap, r_end - r);
-    if (old) {
-      const int64_t ga = std::lower_bound(gA_host.begin(), gA_host.end(), r) - gA_host.begin();
-      const int64_t gb = std::lower_bound(gA_host.begin(), gA_host.end(), r_end) - gA_host.begin();
-      make_conn_tiles_split(gA_host, gNew_host, ga, gb, fill_tiles);
-    } else {
-      make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
-    }
-    plan.push_back({r, r_end, (int64_t)all_tiles.size(), (int64_t)fill_tiles.size(), ml});
+    if (old) make_conn_tiles_split(gA_host, gNew_host, i, j, fill_tiles);  // samples = alpha-group boundaries
+    else make_conn_tiles(gA_host, row_entry(r), row_entry(r_end - 1) + 1, fill_tiles);
+    plan.push_back({r, r_end, (int64_t)all_tiles.size(), (int64_t)fill_tiles.size(), max_seg});
     all_tiles.insert(all_tiles.end(), fill_tiles.begin(), fill_tiles.end());
-    r = r_end;
+    i = j;
   }
   if (!plan.empty()) {
     SQ_CHECK(cand_tmp.alloc(tmp_cap));
@@ -1435,8 +1465,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   h->capacity = std::max<int64_t>(h->nnz_local, 1);
   HM.mark("nnz reduce + shrink");
   SQ_CHECK(alloc_work_vectors(h));
-  SQ_CHECK(spmv_setup_bins(h));
-  HM.mark("work vectors + bins");
+  HM.mark("work vectors");
   SQ_CHECK(bundle_encode(h));
   HM.mark("bundle encode");
   cudaEventRecord(ev[4], s);
@@ -1551,7 +1580,6 @@ int import_upper(sqmc_b200_handle *h, int64_t n, const int64_t *counts, const in
   SQ_LAUNCH_CHECK();
   SQ_CHECK(import_upper_device(h, n, counts, indices, values));
   SQ_CHECK(alloc_work_vectors(h));
-  SQ_CHECK(spmv_setup_bins(h));
   return bundle_encode(h);
 }
 

@@ -240,11 +240,30 @@ __device__ __forceinline__ void blk_load(Blk &B, const int32_t *cols, const doub
 // NV = 1: y = H x.  NV = 2: two right-hand sides at once (Davidson with n_states >= 2, SURVEY.md 8(d) "SpMM"): x / y hold the
 // two vectors interleaved (x[2*col + k]), one 16-byte gather serves both and the matrix is streamed once
 // (algorithmic bytes 12*nnz_full + 36*n for two vectors instead of 2*(12*nnz_full + 20*n)).
-template <int R, int MODE, int NV, int MINB, bool SCAT>
+// XT: the gathers of x go through the texture path (tex1Dfetch on a linear texture over x) instead of LSU loads: the LSU data
+// pipe of L1TEX is the busiest unit of this kernel (90 % under ncu, half of its wavefronts are the gathers) and the texture
+// pipe is idle otherwise.
+template <int R, int MODE, int NV, int MINB, bool SCAT, bool XT>
 __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
                                                               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                                                              OwnerScatter O) {
+                                                              OwnerScatter O, cudaTextureObject_t xtex) {
   const Policies P;
+  auto gx = [&](int32_t col) -> double {
+    if constexpr (XT) {
+      const int2 t = tex1Dfetch<int2>(xtex, col);
+      return __hiloint2double(t.y, t.x);
+    } else {
+      return ld_x(x + col, P);
+    }
+  };
+  auto gx2 = [&](int32_t col) -> double2 {
+    if constexpr (XT) {
+      const int4 t = tex1Dfetch<int4>(xtex, col);
+      return make_double2(__hiloint2double(t.y, t.x), __hiloint2double(t.w, t.z));
+    } else {
+      return bld_x2(x + 2 * (int64_t)col, P);
+    }
+  };
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b < nb) {
@@ -259,9 +278,9 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
 
   auto one = [&](int32_t cw, double v) {
     if (NV == 1) {
-      badd<R, MODE>(acc, cw, v * ld_x(x + (cw >> kBShift), P));
+      badd<R, MODE>(acc, cw, v * gx(cw >> kBShift));
     } else {
-      const double2 xv = bld_x2(x + 2 * (int64_t)(cw >> kBShift), P);
+      const double2 xv = gx2(cw >> kBShift);
       badd<R, MODE>(acc, cw, v * xv.x);
       badd<(NV == 2 ? R : 1), MODE>(acc2, cw, v * xv.y);
     }
@@ -285,16 +304,16 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
   };
   auto gather = [&](const Blk &B, double (&xa)[4], double (&xb)[4]) {
     if (NV == 1) {
-      xa[0] = ld_x(x + (B.c.x >> kBShift), P);
-      xa[1] = ld_x(x + (B.c.y >> kBShift), P);
-      xa[2] = ld_x(x + (B.c.z >> kBShift), P);
-      xa[3] = ld_x(x + (B.c.w >> kBShift), P);
+      xa[0] = gx(B.c.x >> kBShift);
+      xa[1] = gx(B.c.y >> kBShift);
+      xa[2] = gx(B.c.z >> kBShift);
+      xa[3] = gx(B.c.w >> kBShift);
     } else {
       double2 t;
-      t = bld_x2(x + 2 * (int64_t)(B.c.x >> kBShift), P); xa[0] = t.x; xb[0] = t.y;
-      t = bld_x2(x + 2 * (int64_t)(B.c.y >> kBShift), P); xa[1] = t.x; xb[1] = t.y;
-      t = bld_x2(x + 2 * (int64_t)(B.c.z >> kBShift), P); xa[2] = t.x; xb[2] = t.y;
-      t = bld_x2(x + 2 * (int64_t)(B.c.w >> kBShift), P); xa[3] = t.x; xb[3] = t.y;
+      t = gx2(B.c.x >> kBShift); xa[0] = t.x; xb[0] = t.y;
+      t = gx2(B.c.y >> kBShift); xa[1] = t.x; xb[1] = t.y;
+      t = gx2(B.c.z >> kBShift); xa[2] = t.x; xb[2] = t.y;
+      t = gx2(B.c.w >> kBShift); xa[3] = t.x; xb[3] = t.y;
     }
   };
   // software pipeline over the full blocks with two named register sets: gathers of the current block, then the next
@@ -357,110 +376,6 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
   }
 }
 
-// ------------------------------------------------------------------ variant: stream loads staged through a per-lane shared-memory ring
-// The register-pipelined kernel above keeps ONE block (128 entries, 1.5 KB per warp) of the 12 B/entry streams in flight per
-// warp besides the one it works on.  Here every lane copies its own share of the next K-1 blocks into shared memory with
-// cp.async (16-byte LDGSTS, L2 evict-first, no L1 allocation) and later reads back exactly what it copied -- a lane-private
-// ring, so no barrier or mbarrier is needed, only cp.async.wait_group.  The x gathers of block j+1 are issued before the
-// arithmetic of block j.  K = ring depth (blocks); shared memory per CTA = 8 warps * K * 1.5 KB.
-__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int R, int K, int MINB>
-__global__ void __launch_bounds__(256, MINB) bundle_hv_ring_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
-                                                                   const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y) {
-  extern __shared__ __align__(16) unsigned char ring[];
-  const Policies P;
-  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (b >= nb) return;
-  // this lane's slots: slot k holds 16 B of column words, then two 16 B halves of the four values
-  int4 *s_c = reinterpret_cast<int4 *>(ring) + (w * K) * 32 + lane;                               // [K][32]
-  double2 *s_v0 = reinterpret_cast<double2 *>(ring + 8 * K * 512) + (w * K) * 32 + lane;        // [K][32]
-  double2 *s_v1 = reinterpret_cast<double2 *>(ring + 2 * 8 * K * 512) + (w * K) * 32 + lane;    // [K][32]
-  const int64_t r0 = b * R;
-  const int64_t e0 = rowptr[r0], e1 = rowptr[min(r0 + R, nloc)];
-  const Sigma S(e0, e1 - e0);
-  double acc[R];
-#pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
-  const int64_t nblk = S.nblk;
-  const int64_t o0 = e0 + S.h + 4 * lane;
-  auto issue = [&](int64_t j) {
-    if (j < nblk) {
-      const int k = (int)(j % K);
-      const int64_t o = o0 + (j << 7);
-      cp_async16((unsigned)__cvta_generic_to_shared(s_c + k * 32), cols + o, P.stream);
-      cp_async16((unsigned)__cvta_generic_to_shared(s_v0 + k * 32), vals + o, P.stream);
-      cp_async16((unsigned)__cvta_generic_to_shared(s_v1 + k * 32), vals + o + 2, P.stream);
-    }
-    cp_async_commit();  // one group per block index, empty past the end: the wait count stays uniform
-  };
-#pragma unroll
-  for (int j = 0; j < K - 1; j++) issue(j);
-  // entries in front of the first aligned block and behind the last full block: merged order, scalar loads (overlaps the prefetch)
-  if (lane < S.h) {
-    const int32_t cw = ld_col(cols + e0 + lane, P);
-    badd<R, 1>(acc, cw, ld_val(vals + e0 + lane, P) * ld_x(x + (cw >> kBShift), P));
-  }
-  for (int64_t k = e0 + S.h + (nblk << 7) + lane; k < e1; k += 32) {
-    const int32_t cw = ld_col(cols + k, P);
-    badd<R, 1>(acc, cw, ld_val(vals + k, P) * ld_x(x + (cw >> kBShift), P));
-  }
-  if (nblk > 0) {
-    int4 c0, c1;
-    double2 va0, vb0, va1, vb1;
-    double x0[4], x1[4];
-    cp_async_wait<K - 2>();
-    c0 = s_c[0]; va0 = s_v0[0]; vb0 = s_v1[0];
-    x0[0] = ld_x(x + (c0.x >> kBShift), P); x0[1] = ld_x(x + (c0.y >> kBShift), P);
-    x0[2] = ld_x(x + (c0.z >> kBShift), P); x0[3] = ld_x(x + (c0.w >> kBShift), P);
-    for (int64_t j = 0; j < nblk; j += 2) {
-      // ---- block j in set 0; fetch block j+1 into set 1
-      issue(j + K - 1);
-      if (j + 1 < nblk) {
-        cp_async_wait<K - 2>();
-        const int k = (int)((j + 1) % K);
-        c1 = s_c[k * 32]; va1 = s_v0[k * 32]; vb1 = s_v1[k * 32];
-        x1[0] = ld_x(x + (c1.x >> kBShift), P); x1[1] = ld_x(x + (c1.y >> kBShift), P);
-        x1[2] = ld_x(x + (c1.z >> kBShift), P); x1[3] = ld_x(x + (c1.w >> kBShift), P);
-      }
-      badd<R, 1>(acc, c0.x, va0.x * x0[0]);
-      badd<R, 1>(acc, c0.y, va0.y * x0[1]);
-      badd<R, 1>(acc, c0.z, vb0.x * x0[2]);
-      badd<R, 1>(acc, c0.w, vb0.y * x0[3]);
-      if (j + 1 >= nblk) break;
-      // ---- block j+1 in set 1; fetch block j+2 into set 0
-      issue(j + K);
-      if (j + 2 < nblk) {
-        cp_async_wait<K - 2>();
-        const int k = (int)((j + 2) % K);
-        c0 = s_c[k * 32]; va0 = s_v0[k * 32]; vb0 = s_v1[k * 32];
-        x0[0] = ld_x(x + (c0.x >> kBShift), P); x0[1] = ld_x(x + (c0.y >> kBShift), P);
-        x0[2] = ld_x(x + (c0.z >> kBShift), P); x0[3] = ld_x(x + (c0.w >> kBShift), P);
-      }
-      badd<R, 1>(acc, c1.x, va1.x * x1[0]);
-      badd<R, 1>(acc, c1.y, va1.y * x1[1]);
-      badd<R, 1>(acc, c1.z, vb1.x * x1[2]);
-      badd<R, 1>(acc, c1.w, vb1.y * x1[3]);
-    }
-  }
-  cp_async_wait<0>();
-  double m0 = 0.0;
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    double a0 = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    if (lane == r) m0 = a0;
-  }
-  if (lane < R && r0 + lane < nloc) y[r0 + lane] = m0;
-}
-
 // ------------------------------------------------------------------ host side
 // default: bundles of 4 rows (measured best on B200, profiles/r01_bundle_experiment.txt); SQMC_BUNDLE=0|2|4 overrides.
 // Read per call (a getenv is ~100 ns) so that one process can A/B layouts on one resident matrix.
@@ -474,7 +389,7 @@ static int bundle_want() {
 static int bundle_variant() {
   const char *e = getenv("SQMC_BUNDLE_KERNEL");
   const int v = e ? atoi(e) : 14;
-  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 24 || v == 26 || v == 28) ? v : 14;
+  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 34 || v == 35) ? v : 14;
 }
 
 template <int R>
@@ -566,6 +481,32 @@ int bundle_decode(sqmc_b200_handle *h) {
   return 0;
 }
 
+// linear texture over x (nv interleaved vectors per element), cached per (pointer, length, nv) on the handle
+static int x_texture(sqmc_b200_handle *h, const double *x, int nv, cudaTextureObject_t *out) {
+  for (auto &t : h->xtex)
+    if (t.ptr == x && t.n == h->n && t.nv == nv) { *out = t.tex; return 0; }
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypeLinear;
+  rd.res.linear.devPtr = const_cast<double *>(x);
+  rd.res.linear.desc = nv == 1 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<int4>();
+  rd.res.linear.sizeInBytes = (size_t)h->n * nv * sizeof(double);
+  cudaTextureDesc td = {};
+  td.readMode = cudaReadModeElementType;
+  cudaTextureObject_t tex = 0;
+  SQ_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  if (h->xtex.size() >= 16) {  // bounded cache
+    cudaDestroyTextureObject(h->xtex.front().tex);
+    h->xtex.erase(h->xtex.begin());
+  }
+  h->xtex.push_back({x, h->n, nv, tex});
+  *out = tex;
+  return 0;
+}
+void x_textures_release(sqmc_b200_handle *h) {
+  for (auto &t : h->xtex) cudaDestroyTextureObject(t.tex);
+  h->xtex.clear();
+}
+
 template <int NV>
 static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   const int64_t nloc = h->row1 - h->row0;
@@ -574,24 +515,18 @@ static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream
   if (nb == 0) return 0;
   const unsigned grid = (unsigned)div_up(nb * 32, (int64_t)256);
   const int var = bundle_variant();
-  if (NV == 1 && var >= 20) {  // shared-memory ring variants (single vector): 24 = 4 blocks deep, 26 = 6, 28 = 8
-#define SQ_RING(RR, KK, MB)                                                                                                          \
-  do {                                                                                                                               \
-    const int smem = 8 * KK * 1536;                                                                                                  \
-    SQ_CUDA(cudaFuncSetAttribute(bundle_hv_ring_kernel<RR, KK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));             \
-    bundle_hv_ring_kernel<RR, KK, MB><<<grid, 256, smem, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y);                   \
-  } while (0)
-    if (R == 4) {
-      if (var == 24) SQ_RING(4, 4, 4); else if (var == 26) SQ_RING(4, 6, 3); else SQ_RING(4, 8, 2);
-    } else {
-      if (var == 24) SQ_RING(2, 4, 4); else if (var == 26) SQ_RING(2, 6, 3); else SQ_RING(2, 8, 2);
-    }
-#undef SQ_RING
+  const OwnerScatter none = {};
+  if (var >= 30 && ((uintptr_t)x & 511) == 0) {  // gathers through the texture path (a linear texture needs a 512-byte aligned base)
+    cudaTextureObject_t tex = 0;
+    SQ_CHECK(x_texture(h, x, NV, &tex));
+#define SQ_BT(RR, MINB) bundle_hv_kernel<RR, 1, NV, MINB, false, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none, tex)
+    if (R == 4) { if (var == 34) SQ_BT(4, 4); else SQ_BT(4, 5); }
+    else { if (var == 34) SQ_BT(2, 4); else SQ_BT(2, 5); }
+#undef SQ_BT
     SQ_LAUNCH_CHECK();
     return 0;
   }
-  const OwnerScatter none = {};
-#define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none)
+#define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB, false, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none, 0)
   if (R == 4) {
     if (var == 14) SQ_BL(4, 1, 4); else if (var == 15) SQ_BL(4, 1, 5); else if (var == 4) SQ_BL(4, 0, 4); else SQ_BL(4, 0, 5);
   } else {
@@ -610,8 +545,8 @@ int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x, const OwnerScatter
   const int R = h->bundle_R;
   const int64_t nb = div_up(nloc, (int64_t)R);
   const unsigned grid = (unsigned)std::max<int64_t>(1, div_up(nb * 32, (int64_t)256));
-  if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O);
-  else bundle_hv_kernel<2, 1, 1, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O);
+  if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
+  else bundle_hv_kernel<2, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
   SQ_LAUNCH_CHECK();
   return 0;
 }

@@ -153,6 +153,7 @@ struct sqmc_b200_handle {
   // ---- SpMV degree bins: row lists (local row ids) ----
   int32_t *d_bin_rows = nullptr;  // concatenated lists
   int64_t bin_off[sqmc::kNumBins + 1] = {0};
+  bool bins_ready = false;  // built lazily by the first plain-row H.v
 
   // ---- row-bundle ordering (csrc/bundle.cu; active when bundle_R > 0: d_cols holds column << 3 | row-in-bundle) ----
   int bundle_R = 0, bundle_cap = 0;
@@ -167,6 +168,8 @@ struct sqmc_b200_handle {
   int32_t *d_dest_rank = nullptr;           // [nloc] owner rank of the local row's determinant
   int32_t *d_dest_pos = nullptr;            // [nloc] its position inside the owner's slice
   int32_t *d_my_internal = nullptr;         // [my_n] internal row of the k-th determinant this rank owns
+  struct XTex { const double *ptr; int64_t n; int nv; cudaTextureObject_t tex; };
+  std::vector<XTex> xtex;  // linear textures over gathered vectors (texture-path variant of the H.v kernel)
   unsigned long long *d_scat_counter = nullptr;  // CTA counter of the fused H.v + owner exchange kernel on a single rank
   // ---- work buffers ----
   double *d_x = nullptr;   // n (global length, internal order)
@@ -249,6 +252,7 @@ int bundle_encode_r(sqmc_b200_handle *h, int R);  // same with an explicit bundl
 int bundle_decode(sqmc_b200_handle *h);  // exact inverse
 int bundle_spmv(sqmc_b200_handle *h, const double *x_dev, double *y_dev, cudaStream_t s);
 int bundle_spmm2(sqmc_b200_handle *h, const double *x2_dev, double *y2_dev, cudaStream_t s);  // two interleaved vectors
+void x_textures_release(sqmc_b200_handle *h);
 int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x_dev, const OwnerScatter &O, cudaStream_t s);  // H.v fused with the owner exchange
 int bundle_get_row(sqmc_b200_handle *h, int64_t internal_row, std::vector<int32_t> &cols, std::vector<double> &vals);
 // davidson.cu

@@ -647,6 +647,7 @@ static int reduce_by_det(int norb, DevBuf<uint64_t> &a, DevBuf<uint64_t> &b, Dev
                          DevBuf<double> &rv, int64_t &mout, cudaStream_t s) {
   mout = 0;
   if (m == 0) return 0;
+  if (m >= (1ll << 31) - 1) { set_error("pt2: %lld (determinant, contribution) pairs exceed the 32-bit segment offsets; lower the work per call (larger eps_pt)", (long long)m); return 2; }
   DevBuf<int32_t> idx, flag, sel, num;
   DevBuf<uint64_t> sa, sb;
   DevBuf<double> sv;
@@ -736,7 +737,7 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
   const int64_t kChunk = 1ll << 27;
   DevBuf<uint64_t> acc_a, acc_b;
   DevBuf<double> acc_v;
-  int64_t acc_n = 0;
+  int64_t acc_n = 0, acc_cap = 0;
   int64_t i0 = 0;
   while (i0 < n) {
     int64_t i1 = std::upper_bound(prefix.begin() + i0 + 1, prefix.end(), prefix[i0] + kChunk) - prefix.begin() - 1;
@@ -760,22 +761,41 @@ static int pt2_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const v
     int64_t mu = 0;
     SQ_CHECK(reduce_by_det<NW>(T.norb, ca, cb, cv, m, ra, rb, rv, mu, s));
     if (mu > 0) {
-      DevBuf<uint64_t> na, nb;
-      DevBuf<double> nv;
-      SQ_CHECK(na.alloc((acc_n + mu) * NW));
-      SQ_CHECK(nb.alloc((acc_n + mu) * NW));
-      SQ_CHECK(nv.alloc(acc_n + mu));
-      if (acc_n) {
-        SQ_CUDA(cudaMemcpyAsync(na.p, acc_a.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(nb.p, acc_b.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
-        SQ_CUDA(cudaMemcpyAsync(nv.p, acc_v.p, acc_n * 8, cudaMemcpyDeviceToDevice, s));
+      // the accumulated partial sums are reduced again whenever they pass kAccReduce entries (the reference batches its PT
+      // for the same reason), and the buffers grow geometrically instead of being re-allocated for every chunk
+      const int64_t kAccReduce = 1ll << 28;
+      if (acc_n > 0 && acc_n + mu > kAccReduce) {
+        DevBuf<uint64_t> qa, qb;
+        DevBuf<double> qv;
+        int64_t qn = 0;
+        SQ_CHECK(reduce_by_det<NW>(T.norb, acc_a, acc_b, acc_v, acc_n, qa, qb, qv, qn, s));
+        acc_a.release(); acc_b.release(); acc_v.release();
+        acc_a.p = qa.take(); acc_b.p = qb.take(); acc_v.p = qv.take();
+        acc_n = qn;
+        acc_cap = qn;
       }
-      SQ_CUDA(cudaMemcpyAsync(na.p + acc_n * NW, ra.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
-      SQ_CUDA(cudaMemcpyAsync(nb.p + acc_n * NW, rb.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
-      SQ_CUDA(cudaMemcpyAsync(nv.p + acc_n, rv.p, mu * 8, cudaMemcpyDeviceToDevice, s));
+      if (acc_n + mu >= (1ll << 31) - 1) { set_error("pt2: more than 2^31 distinct connected determinants"); return 2; }
+      if (acc_n + mu > acc_cap) {
+        const int64_t cap = std::max<int64_t>(acc_n + mu, 2 * acc_cap);
+        DevBuf<uint64_t> na, nb;
+        DevBuf<double> nv;
+        SQ_CHECK(na.alloc(cap * NW));
+        SQ_CHECK(nb.alloc(cap * NW));
+        SQ_CHECK(nv.alloc(cap));
+        if (acc_n) {
+          SQ_CUDA(cudaMemcpyAsync(na.p, acc_a.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(nb.p, acc_b.p, acc_n * NW * 8, cudaMemcpyDeviceToDevice, s));
+          SQ_CUDA(cudaMemcpyAsync(nv.p, acc_v.p, acc_n * 8, cudaMemcpyDeviceToDevice, s));
+        }
+        SQ_CUDA(cudaStreamSynchronize(s));
+        acc_a.release(); acc_b.release(); acc_v.release();
+        acc_a.p = na.take(); acc_b.p = nb.take(); acc_v.p = nv.take();
+        acc_cap = cap;
+      }
+      SQ_CUDA(cudaMemcpyAsync(acc_a.p + acc_n * NW, ra.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaMemcpyAsync(acc_b.p + acc_n * NW, rb.p, mu * NW * 8, cudaMemcpyDeviceToDevice, s));
+      SQ_CUDA(cudaMemcpyAsync(acc_v.p + acc_n, rv.p, mu * 8, cudaMemcpyDeviceToDevice, s));
       SQ_CUDA(cudaStreamSynchronize(s));
-      acc_a.release(); acc_b.release(); acc_v.release();
-      acc_a.p = na.take(); acc_b.p = nb.take(); acc_v.p = nv.take();
       acc_n += mu;
     }
     i0 = i1;

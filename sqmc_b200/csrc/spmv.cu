@@ -41,6 +41,7 @@ int spmv_setup_bins(sqmc_b200_handle *h) {
   if (h->d_bin_rows) devbuf_free(h->d_bin_rows);
   h->d_bin_rows = nullptr;
   for (int b = 0; b <= kNumBins; b++) h->bin_off[b] = 0;
+  h->bins_ready = nloc == 0;
   if (nloc == 0) return 0;
   SQ_CHECK(devbuf_alloc((void **)&h->d_bin_rows, nloc * sizeof(int32_t)));
   int32_t *d_num = nullptr;
@@ -67,6 +68,7 @@ int spmv_setup_bins(sqmc_b200_handle *h) {
     set_error("spmv_setup_bins: bins cover %lld of %lld rows", (long long)off, (long long)nloc);
     return 4;
   }
+  h->bins_ready = true;
   return 0;
 }
 
@@ -155,6 +157,7 @@ static int launch_cta_bin(sqmc_b200_handle *h, const double *x, double *y, cudaS
 int spmv_launch(sqmc_b200_handle *h, const double *x, double *y, cudaStream_t s) {
   if (!h->d_rowptr) { set_error("matvec: no matrix on this handle"); return 2; }
   if (h->bundle_R) return bundle_spmv(h, x, y, s);
+  if (!h->bins_ready) SQ_CHECK(spmv_setup_bins(h));  // degree bins of the plain-row kernels: built on first use
   SQ_CHECK(launch_vec_bins(h, x, y, s));
   return launch_cta_bin(h, x, y, s);
 }
