@@ -384,12 +384,13 @@ static int bundle_want() {
   const int v = e ? atoi(e) : 4;
   return (v == 2 || v == 4) ? v : 0;
 }
-// kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 1 = 0/1-multiplier routing, 0 = predicated adds; MINB = CTAs/SM the
-// register allocation is bounded for).  A/B results in profiles/r02_bundle_kernel_ab.txt.
+// kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 3 = 0/1-multiplier routing + gathers through the texture path,
+// 1 = the same with LSU gathers, 0 = predicated adds; MINB = CTAs/SM the register allocation is bounded for).  Default 34
+// (falls back to 14 when the vector is not 512-byte aligned).  A/B results in profiles/r02_bundle_kernel_ab.txt.
 static int bundle_variant() {
   const char *e = getenv("SQMC_BUNDLE_KERNEL");
-  const int v = e ? atoi(e) : 14;
-  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 34 || v == 35) ? v : 14;
+  const int v = e ? atoi(e) : 34;
+  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 34 || v == 35) ? v : 34;
 }
 
 template <int R>
@@ -526,11 +527,12 @@ static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream
     SQ_LAUNCH_CHECK();
     return 0;
   }
+  const int var_lsu = var >= 30 ? var - 20 : var;  // unaligned vector: same routing, LSU gathers
 #define SQ_BL(RR, MODE, MINB) bundle_hv_kernel<RR, MODE, NV, MINB, false, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none, 0)
   if (R == 4) {
-    if (var == 14) SQ_BL(4, 1, 4); else if (var == 15) SQ_BL(4, 1, 5); else if (var == 4) SQ_BL(4, 0, 4); else SQ_BL(4, 0, 5);
+    if (var_lsu == 14) SQ_BL(4, 1, 4); else if (var_lsu == 15) SQ_BL(4, 1, 5); else if (var_lsu == 4) SQ_BL(4, 0, 4); else SQ_BL(4, 0, 5);
   } else {
-    if (var == 14) SQ_BL(2, 1, 4); else if (var == 15) SQ_BL(2, 1, 5); else if (var == 4) SQ_BL(2, 0, 4); else SQ_BL(2, 0, 5);
+    if (var_lsu == 14) SQ_BL(2, 1, 4); else if (var_lsu == 15) SQ_BL(2, 1, 5); else if (var_lsu == 4) SQ_BL(2, 0, 4); else SQ_BL(2, 0, 5);
   }
 #undef SQ_BL
   SQ_LAUNCH_CHECK();
@@ -545,8 +547,16 @@ int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x, const OwnerScatter
   const int R = h->bundle_R;
   const int64_t nb = div_up(nloc, (int64_t)R);
   const unsigned grid = (unsigned)std::max<int64_t>(1, div_up(nb * 32, (int64_t)256));
-  if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
-  else bundle_hv_kernel<2, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
+  if (bundle_variant() >= 30 && ((uintptr_t)x & 511) == 0) {
+    cudaTextureObject_t tex = 0;
+    SQ_CHECK(x_texture(h, x, 1, &tex));
+    if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, tex);
+    else bundle_hv_kernel<2, 1, 1, 4, true, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, tex);
+  } else if (R == 4) {
+    bundle_hv_kernel<4, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
+  } else {
+    bundle_hv_kernel<2, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
+  }
   SQ_LAUNCH_CHECK();
   return 0;
 }

@@ -303,7 +303,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   PT.start();
   D.n = n;
   D.nloc = h->row1 - h->row0;
-  D.ld = std::max<int64_t>(D.nloc, 1);
+  D.ld = (std::max<int64_t>(D.nloc, 1) + 63) / 64 * 64;  // columns start on 512-byte boundaries (texture-path gathers)
   const int64_t nloc = D.nloc, ld = D.ld;
   cudaStream_t s = D.s;
   int iterations = (int)std::min<int64_t>(n, max_vec);
@@ -502,7 +502,7 @@ int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double 
   D.s = G.stream;
   D.n = n;
   D.nloc = h->row1 - h->row0;
-  D.ld = std::max<int64_t>(D.nloc, 1);
+  D.ld = (std::max<int64_t>(D.nloc, 1) + 63) / 64 * 64;  // columns start on 512-byte boundaries (texture-path gathers)
   const int64_t nloc = D.nloc, ld = D.ld;
   cudaStream_t s = D.s;
   const int iterations = (int)std::min<int64_t>(n, max_iter);
@@ -642,7 +642,7 @@ int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, d
   D.s = G.stream;
   D.n = n;
   D.nloc = h->row1 - h->row0;
-  D.ld = std::max<int64_t>(D.nloc, 1);
+  D.ld = (std::max<int64_t>(D.nloc, 1) + 63) / 64 * 64;  // columns start on 512-byte boundaries (texture-path gathers)
   const int64_t nloc = D.nloc, ld = D.ld;
   cudaStream_t s = D.s;
   const int iterations = (int)std::min<int64_t>(n, max_iter);

@@ -167,7 +167,7 @@ int p2p_setup(sqmc_b200_handle *h, int64_t n) {
   if (P.slab && P.cap >= n) return 0;  // every rank sees the same n, so they all take the same branch
   p2p_release(h);
   int ok = p2p_wanted() ? 1 : 0;
-  const int64_t cap = (n + 15) / 16 * 16;
+  const int64_t cap = (n + 63) / 64 * 64;  // every buffer starts on a 512-byte boundary (linear textures over x)
   // layout (doubles): flags | x[0] (2 cap) | x[1] (2 cap) | xs[0] | xs[1] | y
   const size_t flag_bytes = 4096;
   const size_t bytes = flag_bytes + (size_t)cap * 7 * sizeof(double);
