@@ -516,7 +516,7 @@ def run_sweep(c, args):
     import sqmc_b200 as sq
     from sqmc_b200 import spaces
     from oracle import oracle as O
-    for rr in GEOMETRIES:
+    for rr in (args.geometries.split(",") if args.geometries else GEOMETRIES):
         fd = os.path.join(CURVE, "r" + rr, "FCIDUMP")
         chem = sq.ChemSystem(fd)
         t0 = time.perf_counter()
@@ -546,6 +546,7 @@ def main():
     ap.add_argument("--cpu-sample-dets", type=int, default=200_000)
     ap.add_argument("--sweep-dets", type=int, default=1_000_000)
     ap.add_argument("--heg-dets", type=int, default=1_000_000)
+    ap.add_argument("--geometries", default="", help="--config sweep: comma-separated subset of " + ",".join(GEOMETRIES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--davidson", action="store_true", help="also run a full device Davidson and print it on a second line")

@@ -34,9 +34,30 @@ static int require_init() {
 using namespace sqmc;
 
 namespace sqmc {
-static const uint64_t kPoolKeepBytes = 16ull << 30;  // cached by the device memory pool between calls
+// The stream-ordered pool never gives memory back on its own: with a finite release threshold every synchronisation trimmed
+// the pool and the next selection / build phase mapped the memory again (0.3-1.5 s stalls at random places of an HCI loop, unmapping
+// costs ~40 ms per GB).  Memory is returned explicitly when some allocation fails (devbuf_alloc, big_malloc, grow_ensure).
+static const uint64_t kPoolKeepBytes = ~0ull;
 static bool g_use_pool = true;
+// SQMC_ALLOC_TRACE=1: report every allocator call that blocks the host for more than 10 ms
+struct AllocTrace {
+  const char *what;
+  size_t bytes;
+  std::chrono::steady_clock::time_point t0;
+  static bool on() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SQMC_ALLOC_TRACE"); v = (e && atoi(e) > 0) ? 1 : 0; }
+    return v == 1;
+  }
+  AllocTrace(const char *w, size_t b) : what(w), bytes(b) { if (on()) t0 = std::chrono::steady_clock::now(); }
+  ~AllocTrace() {
+    if (!on()) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > 10.0) fprintf(stderr, "[sqmc alloc] %s of %.3f GB blocked the host for %.1f ms\n", what, bytes / 1e9, ms);
+  }
+};
 int devbuf_alloc(void **p, size_t bytes) {
+  AllocTrace tr("devbuf_alloc", bytes);
   cudaError_t e = g_use_pool ? cudaMallocAsync(p, bytes, G.stream) : cudaMalloc(p, bytes);
   if (e != cudaSuccess && g_use_pool) {  // pool exhausted next to a large matrix: give the cache back and retry
     cudaGetLastError();
@@ -60,6 +81,7 @@ int devbuf_alloc(void **p, size_t bytes) {
 }
 void devbuf_free(void *p) {
   if (!p) return;
+  AllocTrace tr("devbuf_free", 0);
   if (g_use_pool && G.stream) cudaFreeAsync(p, G.stream);
   else cudaFree(p);
 }
@@ -130,6 +152,21 @@ int sqmc_b200_init(int device, int rank, int nranks, const void *id128) {
     if (sqmc::g_use_pool && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       uint64_t keep = sqmc::kPoolKeepBytes;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      // grow the pool once, up front: on the measurement boxes a cudaMallocAsync that needs fresh physical memory blocks the
+      // host for 0.01-1.2 s at random (SQMC_ALLOC_TRACE=1 shows it, profiles/r02_alloc_trace.txt), whatever its size; with the
+      // memory already in the pool the per-call temporaries of selection / build / Davidson are served without the driver.
+      // SQMC_POOL_PREWARM_GB overrides the size (default: 1/12 of the device, at most 16 GB; 0 disables).
+      size_t fr = 0, tot = 0;
+      cudaMemGetInfo(&fr, &tot);
+      const char *pw = getenv("SQMC_POOL_PREWARM_GB");
+      size_t warm = pw ? (size_t)(atof(pw) * 1e9) : std::min<size_t>(tot / 12, (size_t)16 << 30);
+      if (warm > fr / 2) warm = fr / 2;
+      if (warm > 0) {
+        void *w = nullptr;
+        if (cudaMallocAsync(&w, warm, G.stream) == cudaSuccess) cudaFreeAsync(w, G.stream);
+        else cudaGetLastError();
+        cudaStreamSynchronize(G.stream);
+      }
     } else {
       sqmc::g_use_pool = false;
       cudaGetLastError();

@@ -207,6 +207,21 @@ struct PhaseTimer {
   }
 };
 
+// pinned host scratch for the few doubles fetched per iteration: allocated once per process (cudaMallocHost per solver call
+// costs up to milliseconds and synchronises the device)
+static int pinned_scratch(double **out, size_t bytes) {
+  static double *buf = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr;
+    cap = std::max<size_t>(bytes, 1 << 16);
+    SQ_CUDA(cudaMallocHost(&buf, cap));
+  }
+  *out = buf;
+  return 0;
+}
+
 struct Dav {
   sqmc_b200_handle *h;
   cudaStream_t s;
@@ -218,7 +233,7 @@ struct Dav {
   ~Dav() {
     for (double *p : {V, HV, W, HW, diag, partial, scal, coef, resid})
       if (p) devbuf_free(p);  // stream-ordered, back into the pool cache: the next HCI iteration reuses it
-    if (h_scal) cudaFreeHost(h_scal);
+    // h_scal is the process-wide pinned scratch (pinned_scratch): not freed here
   }
   unsigned blocks(int64_t cnt) const { return (unsigned)std::max<int64_t>(1, div_up(cnt, 256)); }
   // out_dev[0..k) = A(:,0..k)^T b  (summed over ranks)
@@ -317,7 +332,7 @@ int davidson(sqmc_b200_handle *h, int n_states, const double *v0, double *evecs,
   SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(m + 8) * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)m * n_states * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.resid, (size_t)n_states * sizeof(double)));
-  SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(m + 8) * sizeof(double)));
+  SQ_CHECK(pinned_scratch(&D.h_scal, (size_t)(m + 8) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * m * sizeof(double), s));
   auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
   auto HVc = [&](int c) { return D.HV + (int64_t)c * ld; };
@@ -514,7 +529,7 @@ int davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double 
   SQ_CHECK(devbuf_alloc((void **)&D.partial, (size_t)kDotBlocks * (iterations + 2) * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(iterations + 8) * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)(iterations + 8) * sizeof(double)));
-  SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CHECK(pinned_scratch(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * iterations * sizeof(double), s));
   auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
   auto HVc = [&](int c) { return D.HV + (int64_t)c * ld; };
@@ -651,7 +666,7 @@ int lanczos(sqmc_b200_handle *h, const double *v0, double *evec, double *eig3, d
   SQ_CHECK(devbuf_alloc((void **)&D.partial, (size_t)kDotBlocks * (iterations + 2) * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.scal, (size_t)(iterations + 8) * sizeof(double)));
   SQ_CHECK(devbuf_alloc((void **)&D.coef, (size_t)(iterations + 8) * sizeof(double)));
-  SQ_CUDA(cudaMallocHost(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
+  SQ_CHECK(pinned_scratch(&D.h_scal, (size_t)(iterations + 8) * sizeof(double)));
   SQ_CUDA(cudaMemsetAsync(D.V, 0, (size_t)ld * (iterations + 1) * sizeof(double), s));
   auto Vc = [&](int c) { return D.V + (int64_t)c * ld; };
   double *w = D.W;

@@ -10,6 +10,9 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "handle.h"
 
@@ -76,6 +79,19 @@ int grow_reserve(GrowBuf &b, size_t max_bytes) {
 // make at least `bytes` usable
 int grow_ensure(GrowBuf &b, size_t bytes) {
   if (bytes <= b.mapped) return 0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  const size_t mapped_before = b.mapped;
+  struct Report {
+    const std::chrono::steady_clock::time_point t0;
+    const size_t before;
+    GrowBuf &b;
+    ~Report() {
+      const char *e = getenv("SQMC_ALLOC_TRACE");
+      if (!(e && atoi(e) > 0)) return;
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > 10.0) fprintf(stderr, "[sqmc alloc] mapping %.3f GB of a growable array blocked the host for %.1f ms\n", (b.mapped - before) / 1e9, ms);
+    }
+  } report{t_begin, mapped_before, b};
   if (!b.base) { set_error("growbuf: not reserved"); return 1; }
   if (bytes > b.reserved) { set_error("growbuf: %zu bytes requested, %zu reserved", bytes, b.reserved); return 1; }
   CUmemAllocationProp prop = device_prop();

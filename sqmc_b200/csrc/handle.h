@@ -62,21 +62,30 @@ struct DevBuf {
 // host wall-clock marks of one build (SQMC_BUILD_PROFILE=1 prints them): finds time spent outside kernels
 // (allocation of the ~100 GB arrays, host loops, synchronisation) that the CUDA-event phases do not see
 struct HostMarks {
-  bool on;
+  int level;  // 0 off, 1: synchronise + print at every mark, 2: record the host clock without synchronising and print at the end
   const char *tag;
   std::chrono::steady_clock::time_point t0, last;
+  std::vector<std::pair<const char *, double>> log;
   explicit HostMarks(const char *env = "SQMC_BUILD_PROFILE", const char *tag_ = "build") : tag(tag_) {
     const char *e = getenv(env);
-    on = e && atoi(e) > 0;
+    level = e ? atoi(e) : 0;
     t0 = last = std::chrono::steady_clock::now();
   }
   void mark(const char *what) {
-    if (!on) return;
-    cudaDeviceSynchronize();
+    if (level <= 0) return;
+    if (level == 1) cudaDeviceSynchronize();
     auto t = std::chrono::steady_clock::now();
-    fprintf(stderr, "[sqmc %s] %-28s %9.1f ms  (t = %9.1f ms)\n", tag, what, std::chrono::duration<double, std::milli>(t - last).count(),
-            std::chrono::duration<double, std::milli>(t - t0).count());
+    if (level == 1) {
+      fprintf(stderr, "[sqmc %s] %-28s %9.1f ms  (t = %9.1f ms)\n", tag, what, std::chrono::duration<double, std::milli>(t - last).count(),
+              std::chrono::duration<double, std::milli>(t - t0).count());
+    } else {
+      log.push_back({what, std::chrono::duration<double, std::milli>(t - last).count()});
+    }
     last = t;
+  }
+  ~HostMarks() {
+    if (level != 2) return;
+    for (auto &e : log) fprintf(stderr, "[sqmc %s host, no sync] %-28s %9.1f ms\n", tag, e.first, e.second);
   }
 };
 

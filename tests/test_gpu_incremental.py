@@ -76,3 +76,17 @@ def test_many_small_extensions_and_fallbacks(oracle, c2_space, c2_space_ts):
     _check(Ht, St, rt["up"][:sizes[0]], rt["dn"][:sizes[0]], 0, want_incremental=False)
     _check(Ht, St, rt["up"][:sizes[1]], rt["dn"][:sizes[1]], sizes[0], want_incremental=False)
     Ht.close()
+
+
+def test_two_word_strings_incremental(oracle):
+    """81 plane waves (two 64-bit words per string): extension in three steps, each compared with the oracle from scratch"""
+    S = oracle.System.heg(3, 0.5, 14, 7, 2.5)
+    r = S.hci(2e-3, n_states=1, max_iters=1)
+    up, dn = r["up"], r["dn"]
+    n = len(up)
+    H = sq.SparseHamiltonian(sq.HegSystem(3, 0.5, 14, 7, 2.5))
+    prev = 0
+    for m in (n // 3, n // 2, n):
+        _check(H, S, up[:m], dn[:m], prev, want_incremental=prev > 0)
+        prev = m
+    H.close()
