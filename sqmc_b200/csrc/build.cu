@@ -398,6 +398,161 @@ __global__ void __launch_bounds__(kConnTile) connect_tile_kernel(ConnView V, con
   }
 }
 
+// ------------------------------------------------------------------ candidate generation by bitmap probes
+// The tiled XOR/popcount join above tests a row's beta string against EVERY entry of EVERY neighbour alpha group (~670 tests per
+// (row, group) at n = 10^7, ~1.5 % hits).  For a neighbour group (alpha' one excitation from alpha) the hits are exactly the
+// entries (alpha', beta') with beta' in {beta} U singles(beta).  So with
+//   * the unique beta strings numbered in sorted order (beta ids = beta groups), their single-excitation adjacency lists
+//     (ascending ids, the string itself included; same (N-1)-key construction as for the alpha groups), and
+//   * per alpha group a bitmap over beta ids ("is (alpha, beta) in the list?") with the popcount prefix of every word
+//     (entries of a group are beta-sorted, so rank in the bitmap = position inside the group),
+// a row probes ~89 bits per neighbour group instead of scanning it, and the hits still come out in ascending order.
+// The row's own group (beta doubles count too) is still scanned, as are the same-beta up-doubles.
+struct BmpView {
+  const uint32_t *bm, *rk;    // [nA][W] membership bits over beta ids / set bits in front of each word
+  const uint32_t *bmN, *rkN;  // incremental build: the same over the NEW entries only (rank inside the group's new part)
+  int W;
+  const int64_t *nbrB_off;    // [nB+1]
+  const int32_t *nbrB;        // beta ids one excitation away (+ itself), ascending
+};
+__global__ void bitmap_set_kernel(const int32_t *eA, const int32_t *eB, const int32_t *old_of_new /* null: all entries */, int64_t n, int W, uint32_t *bm) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (old_of_new && old_of_new[e] >= 0) return;
+  const int32_t b = eB[e];
+  atomicOr(bm + (int64_t)eA[e] * W + (b >> 5), 1u << (b & 31));
+}
+// one warp per alpha group: exclusive prefix of the popcounts of its bitmap words
+__global__ void __launch_bounds__(256) bitmap_rank_kernel(const uint32_t *bm, int64_t nA, int W, uint32_t *rk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (g >= nA) return;
+  uint32_t run = 0;
+  for (int w0 = 0; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t c = w < W ? __popc(bm[g * W + w]) : 0;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (w < W) rk[g * W + w] = run + incl - c;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+template <int NW, bool FILL>
+__global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, BmpView B, const TileDesc *tiles, int64_t ntiles, int64_t row_begin,
+                                                                   int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen,
+                                                                   const int32_t *old_of_new, const int32_t *olen) {
+  extern __shared__ uint32_t s_words[];  // bitmap row [W], rank row [W]
+  __shared__ uint64_t sEb[kConnStage * NW];
+  __shared__ uint32_t sErep[FILL ? kConnStage : 1];
+  __shared__ int32_t s_cnt[kConnTile];
+  __shared__ int32_t s_row[kConnTile];
+  uint32_t *s_bm = s_words, *s_rk = s_words + B.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const TileDesc T = tiles[t];
+    const int64_t e = T.e0 + threadIdx.x;
+    const bool active = threadIdx.x < T.n;
+    const bool part = V.Pidx != nullptr;  // rows come from the partitioned view (incremental build)
+    const int64_t p = active ? (part ? (int64_t)V.Pidx[e] : e) : -1;  // entry == row: no time-reversal expansion on this path
+    Bits<NW> b = b_zero<NW>();
+    if (active) b = b_load<NW>(part ? V.Pb : V.Eb, e);
+    const bool only_new = part && T.kind == 1;  // a row of the previous list: pairs with new determinants only
+    int64_t base = 0;
+    if (FILL && active) base = cand_ptr[p - row_begin] + (olen ? olen[p] : 0);
+    int cnt = 0;
+    int64_t nb0 = 0, nb1 = 0;
+    if (active) {
+      const int32_t bid = V.eB[p];
+      nb0 = B.nbrB_off[bid];
+      nb1 = B.nbrB_off[bid + 1];
+    }
+    const int g = T.g;
+    for (int64_t q = V.nbr_off[g]; q < V.nbr_off[g + 1]; q++) {
+      const int32_t g2 = V.nbr[q];
+      if (g2 == g) {
+        // own group: beta singles and doubles (and the row itself) -> scan the staged strings
+        const int64_t lo = only_new ? V.gNew_off[g2] : V.gA_off[g2], hi = V.gA_off[g2 + 1];
+        const uint64_t *cEb = only_new ? V.Pb : V.Eb;
+        for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
+          const int ns = (int)min((int64_t)kConnStage, hi - s0);
+          __syncthreads();
+          for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) sEb[i * NW + w] = cEb[(s0 + i) * NW + w];
+            if (FILL) sErep[i] = only_new ? (uint32_t)V.Pidx[s0 + i] : (uint32_t)(s0 + i);
+          }
+          __syncthreads();
+          if (active) {
+#pragma unroll 8
+            for (int i = 0; i < ns; i++) {
+              int pc = 0;
+#pragma unroll
+              for (int w = 0; w < NW; w++) pc += __popcll(b.w[w] ^ sEb[i * NW + w]);
+              if (pc == 0 || pc == 2 || pc == 4) {
+                if (FILL) cand[base + cnt] = (int32_t)sErep[i];
+                cnt++;
+              }
+            }
+          }
+        }
+      } else {
+        // neighbour group: probe the bits of {beta} U singles(beta)
+        const uint32_t *bmrow = (only_new ? B.bmN : B.bm) + (int64_t)g2 * B.W;
+        const uint32_t *rkrow = (only_new ? B.rkN : B.rk) + (int64_t)g2 * B.W;
+        __syncthreads();
+        for (int i = threadIdx.x; i < B.W; i += blockDim.x) { s_bm[i] = bmrow[i]; s_rk[i] = rkrow[i]; }
+        __syncthreads();
+        const int64_t pos0 = only_new ? V.gNew_off[g2] : V.gA_off[g2];
+        for (int64_t k = nb0; k < nb1; k++) {
+          const int32_t id = __ldg(B.nbrB + k);
+          const uint32_t w = s_bm[id >> 5];
+          const int bit = id & 31;
+          if ((w >> bit) & 1u) {
+            if (FILL) {
+              const int64_t pos = pos0 + s_rk[id >> 5] + __popc(w & ((1u << bit) - 1u));
+              cand[base + cnt] = only_new ? V.Pidx[pos] : (int32_t)pos;
+            }
+            cnt++;
+          }
+        }
+      }
+    }
+    // same beta-group, up doubles: one warp per row (coalesced scan of the beta-major view)
+    __syncthreads();
+    s_cnt[threadIdx.x] = cnt;
+    s_row[threadIdx.x] = active ? (int32_t)threadIdx.x : -1;
+    __syncthreads();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int rr = warp; rr < T.n; rr += kConnTile / 32) {
+      if (s_row[rr] < 0) continue;
+      const int64_t p2 = part ? (int64_t)V.Pidx[T.e0 + rr] : T.e0 + rr;
+      const Bits<NW> a2 = b_load<NW>(V.Ea, p2);
+      const bool new2 = !old_of_new || old_of_new[p2] < 0;
+      const int64_t base2 = FILL ? cand_ptr[p2 - row_begin] + (olen ? olen[p2] : 0) : 0;
+      int c2 = s_cnt[rr];
+      if (FILL && lane == 0) alen[p2 - row_begin] = c2;
+      const int32_t gb = V.eB[p2];
+      const int64_t lo = V.gB_off[gb], hi = V.gB_off[gb + 1];
+      for (int64_t tb = lo; tb < hi; tb += 32) {
+        const int64_t k = tb + lane;
+        const bool in = k < hi;
+        const int pc = in ? b_popc_xor(a2, b_load<NW>(V.EBa, k)) : 0;
+        const bool hit = in && pc == 4 && (new2 || old_of_new[V.EBrep[k] & ~kSwapBit] < 0);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) cand[base2 + c2 + __popc(m & lt_mask)] = (int32_t)(V.EBrep[k] & ~kSwapBit);
+        c2 += __popc(m);
+      }
+      if (!FILL && lane == 0) counts[p2 - row_begin] = c2;
+    }
+    __syncthreads();
+  }
+}
+
 // tiles covering the entries [e_lo, e_hi) (host; gA is the host copy of the alpha-group offsets)
 static void make_conn_tiles(const std::vector<int64_t> &gA, int64_t e_lo, int64_t e_hi, std::vector<TileDesc> &tiles) {
   tiles.clear();
@@ -908,6 +1063,60 @@ void partition_rows(const int64_t *prefix, int64_t n, int nranks, int64_t *start
   starts[nranks] = n;
 }
 
+// Sorted single-excitation neighbour lists of a set of unique strings: string g is str[g_off[g]] (first member of group g of a
+// sorted array).  Two strings are one excitation apart iff they share an (N-1)-electron key (the alpha_m1 idea of
+// chemistry.f90:9819 applied to unique strings): keys are sorted, the run of a key lists the strings that contain it.
+// nbr[nbr_off[g] .. nbr_off[g+1]) = g itself and its neighbours, ascending.
+template <int NW>
+static int neighbour_lists(const uint64_t *str, const int64_t *g_off, int64_t ng, int nel, int norb, DevBuf<int64_t> &nbr_off, DevBuf<int32_t> &nbr,
+                           cudaStream_t s) {
+  const int64_t m2 = ng * nel;
+  DevBuf<uint64_t> K_keys_u, K_keys;
+  DevBuf<int32_t> K_grp_u, K_grp, kidx, run_lo, run_hi, nbr_cnt;
+  SQ_CHECK(K_keys_u.alloc(std::max<int64_t>(m2, 1) * NW));
+  SQ_CHECK(K_grp_u.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(K_keys.alloc(std::max<int64_t>(m2, 1) * NW));
+  SQ_CHECK(K_grp.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(kidx.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(run_lo.alloc(std::max<int64_t>(m2, 1)));
+  SQ_CHECK(run_hi.alloc(std::max<int64_t>(m2, 1)));
+  if (m2 > 0) {
+    nm1_keys_kernel<NW><<<nblocks(ng), kThreads, 0, s>>>(str, g_off, ng, nel, K_keys_u.p, K_grp_u.p);
+    SQ_LAUNCH_CHECK();
+    iota_kernel<<<nblocks(m2), kThreads, 0, s>>>(kidx.p, m2);
+    SQ_LAUNCH_CHECK();
+    std::vector<KeyWord> words;
+    for (int w = 0; w < NW; w++) words.push_back({K_keys_u.p, NW, w, std::min(64, norb - 64 * w)});
+    SQ_CHECK(sort_by_words(words, kidx.p, m2, s));
+    gather_bits_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(K_keys_u.p, kidx.p, K_keys.p, m2);
+    SQ_LAUNCH_CHECK();
+    gather_u32_kernel<<<nblocks(m2), kThreads, 0, s>>>((const uint32_t *)K_grp_u.p, kidx.p, (uint32_t *)K_grp.p, m2);
+    SQ_LAUNCH_CHECK();
+    nm1_runs_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(str, g_off, ng, nel, K_keys.p, m2, run_lo.p, run_hi.p);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CHECK(nbr_cnt.alloc(ng + 1));
+  SQ_CHECK(nbr_off.alloc(ng + 1));
+  SQ_CUDA(cudaMemsetAsync(nbr_cnt.p, 0, (ng + 1) * sizeof(int32_t), s));
+  nbr_count_kernel<<<nblocks(ng), kThreads, 0, s>>>(run_lo.p, run_hi.p, ng, nel, nbr_cnt.p);
+  SQ_LAUNCH_CHECK();
+  SQ_CHECK(exclusive_scan_i32_to_i64(nbr_cnt.p, nbr_off.p, ng, s));
+  int64_t nbr_total = 0;
+  SQ_CUDA(cudaMemcpy(&nbr_total, nbr_off.p + ng, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SQ_CHECK(nbr.alloc(std::max<int64_t>(nbr_total, 1)));
+  nbr_fill_kernel<<<nblocks(ng), kThreads, 0, s>>>(run_lo.p, run_hi.p, K_grp.p, ng, nel, nbr_off.p, nbr.p);
+  SQ_LAUNCH_CHECK();
+  sort_rows_warp_kernel<<<nblocks(ng, 8), 256, 0, s>>>(nbr_off.p, nbr_cnt.p, ng, nbr.p);
+  SQ_LAUNCH_CHECK();
+  if ((int64_t)nel * (norb - nel) + 1 > kWarpSortMax) {  // more neighbours than the warp sort handles (large basis sets)
+    SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
+    sort_rows_block_kernel<<<(int)std::min<int64_t>(ng, 148 * 16), 256, kBlockSortMax * 4, s>>>(nbr_off.p, nbr_cnt.p, ng, nbr.p);
+    SQ_LAUNCH_CHECK();
+  }
+  SQ_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 // ------------------------------------------------------------------ the build
 template <int NW>
 static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, OldMatrix *old) {
@@ -1080,69 +1289,42 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   scatter_gid_kernel<<<nblocks(m), kThreads, 0, s>>>(eB_sorted.p, bidx.p, eB.p, m);
   SQ_LAUNCH_CHECK();
   SQ_CUDA(cudaStreamSynchronize(s));
-  EBb.release();
   eB_sorted.release();
   bidx.release();
 
-  // ---- (N-1)-electron keys of the unique alpha strings -> neighbour runs
+  // ---- sorted neighbour-group list of every alpha group (itself + the groups of the strings one excitation away)
   const int nel = T.nup;  // time_sym requires nup == ndn (chemistry.f90:186)
-  int64_t m2 = nA * nel;
-  DevBuf<uint64_t> K_keys_u, K_keys;
-  DevBuf<int32_t> K_grp_u, K_grp, kidx, run_lo, run_hi;
-  SQ_CHECK(K_keys_u.alloc(std::max<int64_t>(m2, 1) * NW));
-  SQ_CHECK(K_grp_u.alloc(std::max<int64_t>(m2, 1)));
-  SQ_CHECK(K_keys.alloc(std::max<int64_t>(m2, 1) * NW));
-  SQ_CHECK(K_grp.alloc(std::max<int64_t>(m2, 1)));
-  SQ_CHECK(kidx.alloc(std::max<int64_t>(m2, 1)));
-  SQ_CHECK(run_lo.alloc(std::max<int64_t>(m2, 1)));
-  SQ_CHECK(run_hi.alloc(std::max<int64_t>(m2, 1)));
-  if (m2 > 0) {
-    nm1_keys_kernel<NW><<<nblocks(nA), kThreads, 0, s>>>(Ea, gA_off.p, nA, nel, K_keys_u.p, K_grp_u.p);
-    SQ_LAUNCH_CHECK();
-    iota_kernel<<<nblocks(m2), kThreads, 0, s>>>(kidx.p, m2);
-    SQ_LAUNCH_CHECK();
-    std::vector<KeyWord> words;
-    for (int w = 0; w < NW; w++) words.push_back({K_keys_u.p, NW, w, std::min(64, T.norb - 64 * w)});
-    SQ_CHECK(sort_by_words(words, kidx.p, m2, s));
-    gather_bits_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(K_keys_u.p, kidx.p, K_keys.p, m2);
-    SQ_LAUNCH_CHECK();
-    gather_u32_kernel<<<nblocks(m2), kThreads, 0, s>>>((const uint32_t *)K_grp_u.p, kidx.p, (uint32_t *)K_grp.p, m2);
-    SQ_LAUNCH_CHECK();
-    nm1_runs_kernel<NW><<<nblocks(m2), kThreads, 0, s>>>(Ea, gA_off.p, nA, nel, K_keys.p, m2, run_lo.p, run_hi.p);
-    SQ_LAUNCH_CHECK();
-  }
-  SQ_CUDA(cudaStreamSynchronize(s));
-  K_keys_u.release();
-  K_grp_u.release();
-  kidx.release();
-  K_keys.release();
-
-  // sorted neighbour-group list of every alpha group
   DevBuf<int64_t> nbr_off;
-  DevBuf<int32_t> nbr, nbr_cnt;
-  SQ_CHECK(nbr_cnt.alloc(nA + 1));
-  SQ_CHECK(nbr_off.alloc(nA + 1));
-  SQ_CUDA(cudaMemsetAsync(nbr_cnt.p, 0, (nA + 1) * sizeof(int32_t), s));
-  nbr_count_kernel<<<nblocks(nA), kThreads, 0, s>>>(run_lo.p, run_hi.p, nA, nel, nbr_cnt.p);
-  SQ_LAUNCH_CHECK();
-  SQ_CHECK(exclusive_scan_i32_to_i64(nbr_cnt.p, nbr_off.p, nA, s));
-  int64_t nbr_total = 0;
-  SQ_CUDA(cudaMemcpy(&nbr_total, nbr_off.p + nA, sizeof(int64_t), cudaMemcpyDeviceToHost));
-  SQ_CHECK(nbr.alloc(std::max<int64_t>(nbr_total, 1)));
-  nbr_fill_kernel<<<nblocks(nA), kThreads, 0, s>>>(run_lo.p, run_hi.p, K_grp.p, nA, nel, nbr_off.p, nbr.p);
-  SQ_LAUNCH_CHECK();
-  sort_rows_warp_kernel<<<nblocks(nA, 8), 256, 0, s>>>(nbr_off.p, nbr_cnt.p, nA, nbr.p);
-  SQ_LAUNCH_CHECK();
-  SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
-  if ((int64_t)nel * (T.norb - nel) + 1 > kWarpSortMax) {  // more neighbours than the warp sort handles (large basis sets)
-    sort_rows_block_kernel<<<(int)std::min<int64_t>(nA, 148 * 16), 256, kBlockSortMax * 4, s>>>(nbr_off.p, nbr_cnt.p, nA, nbr.p);
-    SQ_LAUNCH_CHECK();
+  DevBuf<int32_t> nbr;
+  SQ_CHECK(neighbour_lists<NW>(Ea, gA_off.p, nA, nel, T.norb, nbr_off, nbr, s));
+  // ---- bitmap-probe structures (connect_bitmap_kernel): beta adjacency over the unique beta strings, membership bitmaps
+  // + ranks per alpha group.  Not with time-reversal expansion (entries != rows) and only while the bitmaps stay small.
+  DevBuf<int64_t> nbrB_off;
+  DevBuf<int32_t> nbrB;
+  DevBuf<uint32_t> bm, rk, bmN, rkN;
+  const int W = (int)div_up(nB, 32);
+  bool use_bmp = !ts && W <= 8192 && nA * (int64_t)W <= (1ll << 28);
+  if (const char *be = getenv("SQMC_CONNECT_BITMAP")) use_bmp = use_bmp && atoi(be) != 0;
+  if (use_bmp) {
+    SQ_CHECK(neighbour_lists<NW>(EBb.p, gB_off.p, nB, T.ndn, T.norb, nbrB_off, nbrB, s));
+    for (int pass = 0; pass < (old ? 2 : 1); pass++) {
+      DevBuf<uint32_t> &bits = pass == 0 ? bm : bmN, &rank = pass == 0 ? rk : rkN;
+      SQ_CHECK(bits.alloc(nA * W));
+      SQ_CHECK(rank.alloc(nA * W));
+      SQ_CUDA(cudaMemsetAsync(bits.p, 0, (size_t)nA * W * sizeof(uint32_t), s));
+      bitmap_set_kernel<<<nblocks(n), kThreads, 0, s>>>(eA.p, eB.p, pass == 0 ? nullptr : old_of_new.p, n, W, bits.p);
+      SQ_LAUNCH_CHECK();
+      bitmap_rank_kernel<<<nblocks(nA * 32), 256, 0, s>>>(bits.p, nA, W, rank.p);
+      SQ_LAUNCH_CHECK();
+    }
+    if (2 * W * 4 > 24 * 1024) {
+      SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * 4));
+      SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * 4));
+    }
   }
-  SQ_CUDA(cudaStreamSynchronize(s));
-  run_lo.release();
-  run_hi.release();
-  K_grp.release();
-  nbr_cnt.release();
+  EBb.release();
+  const BmpView BV{bm.p, rk.p, bmN.p, rkN.p, W, nbrB_off.p, nbrB.p};
+  const int bmp_smem = 2 * W * 4;
   // incremental build: the partitioned row / candidate view
   DevBuf<int32_t> Pidx;
   DevBuf<uint64_t> Pb;
@@ -1211,7 +1393,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     else if (!ts) connect_tile_kernel<NW, FILL, false, true><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);        \
     else connect_tile_kernel<NW, FILL, false, false><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);                \
   } while (0)
-      SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
+      if (use_bmp) connect_bitmap_kernel<NW, false><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
+      else SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
       SQ_LAUNCH_CHECK();
       SQ_CUDA(cudaStreamSynchronize(s));
     }
@@ -1402,7 +1585,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       const TileDesc *td = fill_tiles_dev.p + cp.tile_off;
       const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cp.ntiles, G.sm_count * 16));
       const bool w32 = NW == 1 && T.norb <= 32;
-      SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p, d_oon, d_olen);
+      if (use_bmp) connect_bitmap_kernel<NW, true><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, alen.p, d_oon, d_olen);
+      else SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p, d_oon, d_olen);
       SQ_LAUNCH_CHECK();
     }
     if (ts) {  // time-reversed partners in the entry list: arbitrary candidate order, duplicates -> sort the rows
@@ -1410,6 +1594,7 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       SQ_LAUNCH_CHECK();
       if (cp.ml > kWarpSortMax) {
         int smem = (int)std::min<int64_t>(cp.ml, kBlockSortMax) * 4;
+        SQ_CUDA(cudaFuncSetAttribute(sort_rows_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSortMax * 4));
         sort_rows_block_kernel<<<(int)std::min<int64_t>(nr, 148 * 16), 256, smem, s>>>(cptr.p, cand_count.p + r, nr, cand_tmp.p);
         SQ_LAUNCH_CHECK();
       }
