@@ -1519,7 +1519,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   }
   HM.mark("alloc cols/vals/rowptr");
   // ---- chunks of rows bounded by temp candidates
-  const int64_t kChunkCand = 1ll << 27;
+  // candidates per chunk of rows: 2^28 (3.2 GB of temporaries) gives the per-chunk kernels ~2000 tiles / ~300k rows -- with 2^27 the
+  // candidate-generation launches were a single partial wave of CTAs (ncu: 975 CTAs for 1184 slots); SQMC_BUILD_CHUNK_LOG2 overrides
+  int chunk_log2 = 28;
+  if (const char *ce = getenv("SQMC_BUILD_CHUNK_LOG2")) chunk_log2 = std::max(20, std::min(30, atoi(ce)));
+  const int64_t kChunkCand = 1ll << chunk_log2;
   int64_t maxlen = 0;
   double ms_fill = 0, ms_eval = 0;
   int64_t base_nnz = 0;
