@@ -63,6 +63,10 @@ def lib():
         L.orc_davidson_single.restype = i32
         L.orc_pt2.argtypes = [vp, i64, vp, vp, vp, C.c_double, C.c_double, vp]
         L.orc_pt2.restype = C.c_double
+        L.orc_pt2_sample.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, i32, dbl, dbl, dbl, vp]
+        L.orc_pt2_sample.restype = dbl
+        L.orc_pt2_alias.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, i32, vp, vp, vp]
+        L.orc_pt2_alias.restype = i32
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
         L.orc_select.restype = i64
         L.orc_select.argtypes = [vp, i64, vp, vp, vp, vp, dbl, i64, vp, vp]
@@ -216,6 +220,34 @@ class System:
         nconn = C.c_longlong()
         de = lib().orc_pt2(self.h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), C.addressof(nconn))
         return de, nconn.value
+
+    def pt2_sample(self, up, dn, s_up, s_dn, s_coeffs, s_w_over_p, n_mc, var_energy, eps_pt, eps_pt_big):
+        """one sample of second_order_pt_alias (hci.f90:1563-1654): (up, dn) = label-sorted variational list, s_* = the distinct
+        sampled determinants -> (e_2pt_this_sample, ndets_connected)"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        su = np.ascontiguousarray(s_up, dtype=np.uint64).reshape(-1, 2)
+        sd = np.ascontiguousarray(s_dn, dtype=np.uint64).reshape(-1, 2)
+        sc = np.ascontiguousarray(s_coeffs, dtype=np.float64).reshape(-1)
+        sw = np.ascontiguousarray(s_w_over_p, dtype=np.float64).reshape(-1)
+        nconn = C.c_longlong()
+        e = lib().orc_pt2_sample(self.h, len(up), _p(up), _p(dn), len(su), _p(su), _p(sd), _p(sc), _p(sw), int(n_mc), float(var_energy),
+                                 float(eps_pt), float(eps_pt_big), C.addressof(nconn))
+        return e, nconn.value
+
+    def pt2_alias(self, up, dn, wts, var_energy, eps_pt, eps_pt_big, n_mc, target_error, seed4, max_samples=1000):
+        """the sampling loop of second_order_pt_alias (one core, n_mc > 0) with the reference's rannyu stream ->
+        dict(pt_energy, std_dev, e_now[], n_distinct[])"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        w = np.ascontiguousarray(wts, dtype=np.float64).reshape(-1)
+        seed = np.ascontiguousarray(seed4, dtype=np.int32)
+        e_now = np.zeros(max_samples)
+        nd = np.zeros(max_samples, dtype=np.int32)
+        out2 = np.zeros(2)
+        ns = lib().orc_pt2_alias(self.h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), float(eps_pt_big), int(n_mc),
+                                 float(target_error), _p(seed), int(max_samples), _p(e_now), _p(nd), _p(out2))
+        return {"pt_energy": out2[0], "std_dev": out2[1], "e_now": e_now[:ns].copy(), "n_distinct": nd[:ns].copy()}
 
     def hci(self, eps_var, eps_var_sched=(), n_states=1, max_iters=50, max_dets=0):
         sched = np.zeros(30)

@@ -1609,6 +1609,153 @@ double orc_pt2(void *h, long long n, const det_t *up, const det_t *dn, const dou
   if (n_connected) *n_connected = distinct;
   return delta;
 }
+// ---- stochastic second-order PT: second_order_pt_alias (hci.f90:1314-1684) -------------------------------------------------
+// rannyu (rannyu.f90:53-74): 48-bit multiplicative congruential generator, seed and multiplier (11^13) kept as four 12-bit digits
+struct Rannyu {
+  long long m[4] = {502, 1521, 4071, 2107}, l[4] = {0, 0, 0, 1};
+  void setrn(const int *iseed) {                       // rannyu.f90:11-21
+    for (int i = 0; i < 4; i++) l[i] = iseed[i];
+    l[3] = 2 * (l[3] / 2) + 1;
+  }
+  double next() {
+    const long long itwo12 = 4096;
+    const double two12i = 2.44140625e-4;
+    long long i1 = l[0] * m[3] + l[1] * m[2] + l[2] * m[1] + l[3] * m[0];
+    long long i2 = l[1] * m[3] + l[2] * m[2] + l[3] * m[1];
+    long long i3 = l[2] * m[3] + l[3] * m[2];
+    long long i4 = l[3] * m[3];
+    l[3] = i4 % itwo12;
+    i3 = i3 + i4 / itwo12;
+    l[2] = i3 % itwo12;
+    i2 = i2 + i3 / itwo12;
+    l[1] = i2 % itwo12;
+    l[0] = (i1 + i2 / itwo12) % itwo12;
+    return two12i * ((double)l[0] + two12i * ((double)l[1] + two12i * ((double)l[2] + two12i * ((double)l[3]))));
+  }
+  int random_int(int n) { return (int)(n * next()) + 1; }   // tools.f90:130-149
+};
+// setup_alias (more_tools.f90:5603-5662); 1-based J as in the reference
+static void setup_alias(int K, const std::vector<double> &pdf, std::vector<int> &J, std::vector<double> &q) {
+  std::vector<int> smaller(K + 1, 0), larger(K + 1, 0);
+  J.assign(K + 1, 0);
+  q.assign(K + 1, 0.0);
+  int n_s = 0, n_l = 0;
+  for (int i = 1; i <= K; i++) {
+    J[i] = i;
+    q[i] = K * pdf[i - 1];
+    if (q[i] < 1.0) smaller[++n_s] = i; else larger[++n_l] = i;
+  }
+  while (n_s > 0 && n_l > 0) {
+    const int small = smaller[n_s], large = larger[n_l];
+    J[small] = large;
+    q[large] = q[large] + q[small] - 1.0;
+    if (q[large] < 1.0) { smaller[n_s] = large; n_l--; } else n_s--;
+  }
+}
+static int sample_alias(Rannyu &R, int K, const std::vector<int> &J, const std::vector<double> &q) {  // more_tools.f90:5727-5752
+  const int i = R.random_int(K);
+  return R.next() < q[i] ? i : J[i];
+}
+// One sample: find_doubly_excited with n_mc / w_over_p / eps_var_pt_big (semistoch.f90:2044-2060) followed by the k loop of
+// second_order_pt_alias (hci.f90:1616-1632):
+//   term1(k)     = sum_i H_ki c_i w_i/p_i                 term2(k)     = sum_i (H_ki c_i)^2 ((n_mc-1) w_i/p_i - (w_i/p_i)^2)
+//   term1_big(k), term2_big(k): the same sums over the elements with |H_ki| > eps_pt_big/|c_i| (chemistry.f90:6977-6983)
+//   e = sum over k outside the variational space of (term1^2 + term2 - term1_big^2 - term2_big) / (E_var - H_kk)
+// returned divided by n_mc (n_mc - 1) (hci.f90:1654).  (up, dn) = the variational list; (s_up, s_dn, s_c, s_wop) = the distinct
+// sampled determinants with their coefficients and count/probability ratios.
+double orc_pt2_sample(void *h, long long n, const det_t *up, const det_t *dn, long long m, const det_t *s_up, const det_t *s_dn, const double *s_c,
+                      const double *s_wop, int n_mc, double var_energy, double eps_pt, double eps_pt_big, long long *n_connected) {
+  System &S = *(System *)h;
+  if (S.model == 0) chem_max_double(S); else if (S.model == 1) heg_max_double(S);
+  std::vector<det_t> cu, cd, tu, td;
+  std::vector<double> t1, t2, t1b, t2b;
+  for (long long i = 0; i < m; i++) {
+    if (s_c[i] == 0.0) continue;
+    tu.clear(); td.clear();
+    std::vector<double> el;
+    const double eps = eps_pt / std::fabs(s_c[i]), eps_big = eps_pt_big / std::fabs(s_c[i]);
+    if (S.model == 0) important_connected_chem(S, s_up[i], s_dn[i], eps, 9.e99, tu, td, &el);
+    else important_connected_heg(S, s_up[i], s_dn[i], eps, tu, td);
+    const double w = s_wop[i], f = (n_mc - 1) * w - w * w;
+    for (size_t k = 0; k < tu.size(); k++) {
+      double me = 0.0;
+      if (k > 0) me = S.model == 0 ? el[k] : hamiltonian(S, s_up[i], s_dn[i], tu[k], td[k]);
+      const double big = std::fabs(me) > eps_big ? me : 0.0;
+      cu.push_back(tu[k]); cd.push_back(td[k]);
+      t1.push_back(me * s_c[i] * w);
+      t2.push_back((me * s_c[i]) * (me * s_c[i]) * f);
+      t1b.push_back(big * s_c[i] * w);
+      t2b.push_back((big * s_c[i]) * (big * s_c[i]) * f);
+    }
+  }
+  std::vector<size_t> ord(cu.size());
+  for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
+  std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cu[a] < cu[b] || (cu[a] == cu[b] && cd[a] < cd[b]); });
+  double e = 0.0;
+  long long distinct = 0;
+  size_t k = 0;
+  while (k < ord.size()) {
+    const det_t au = cu[ord[k]], ad = cd[ord[k]];
+    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+    while (k < ord.size() && cu[ord[k]] == au && cd[ord[k]] == ad) { a1 += t1[ord[k]]; a2 += t2[ord[k]]; b1 += t1b[ord[k]]; b2 += t2b[ord[k]]; k++; }
+    distinct++;
+    long long lo = 0, hi = n;                                   // binary_search in the (label-sorted) variational list
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (up[mid] < au || (up[mid] == au && dn[mid] < ad)) lo = mid + 1; else hi = mid;
+    }
+    const bool in_var = lo < n && up[lo] == au && dn[lo] == ad;
+    if (!in_var) e += 1.0 / (var_energy - hamiltonian(S, au, ad, au, ad)) * (a1 * a1 + a2 - b1 * b1 - b2);
+  }
+  if (n_connected) *n_connected = distinct;
+  return e / (n_mc * (double)(n_mc - 1));
+}
+// The sampling loop of second_order_pt_alias for one core and n_mc > 0 (hci.f90:1387-1400,1430-1452,1654-1670): probabilities
+// |c_i| / sum|c|, alias tables, n_mc draws per sample (the same rannyu stream as the reference when seeded with irand_seed(:,1)),
+// duplicates merged with counts, Welford mean / variance; stops when sample >= 10 and the variance of the mean is below
+// target_error^2, or after max_samples.  (up, dn, wts) must be sorted by label.  e_now[s], n_distinct[s]: per-sample outputs
+// (capacity max_samples).  Returns the number of samples taken; out2 = {pt_energy, std_dev}.
+int orc_pt2_alias(void *h, long long n, const det_t *up, const det_t *dn, const double *wts, double var_energy, double eps_pt, double eps_pt_big,
+                  int n_mc, double target_error, const int *iseed4, int max_samples, double *e_now, int *n_distinct, double *out2) {
+  Rannyu R;
+  R.setrn(iseed4);
+  double norm = 0.0;
+  for (long long i = 0; i < n; i++) norm += std::fabs(wts[i]);
+  std::vector<double> prob(n), q;
+  for (long long i = 0; i < n; i++) prob[i] = std::fabs(wts[i]) / norm;
+  std::vector<int> J;
+  setup_alias((int)n, prob, J, q);
+  double mean = 0.0, S_e2 = 0.0, var = 0.0;
+  int sample = 1;
+  for (; sample <= max_samples; sample++) {
+    std::vector<int> samples(n_mc);
+    for (int i = 0; i < n_mc; i++) samples[i] = sample_alias(R, (int)n, J, q);
+    std::sort(samples.begin(), samples.end());               // sort_and_merge_count_repeats (tools.f90:1574-1602)
+    std::vector<det_t> su, sd;
+    std::vector<double> sc, sw;
+    for (size_t i = 0; i < samples.size();) {
+      size_t j = i;
+      while (j < samples.size() && samples[j] == samples[i]) j++;
+      const int d = samples[i] - 1;
+      su.push_back(up[d]); sd.push_back(dn[d]); sc.push_back(wts[d]); sw.push_back((double)(j - i) / prob[d]);
+      i = j;
+    }
+    long long nconn = 0;
+    const double e = orc_pt2_sample(h, n, up, dn, (long long)su.size(), su.data(), sd.data(), sc.data(), sw.data(), n_mc, var_energy, eps_pt,
+                                    eps_pt_big, &nconn);
+    if (e_now) e_now[sample - 1] = e;
+    if (n_distinct) n_distinct[sample - 1] = (int)su.size();
+    const double oldM = mean;                                 // welford (tools.f90:1761-1778)
+    mean = mean + (e - mean) / sample;
+    S_e2 = S_e2 + (e - mean) * (e - oldM);
+    var = S_e2 / (double)(sample - 1) / sample;
+    if (sample >= 10 && var < target_error * target_error) break;
+  }
+  if (sample > max_samples) sample = max_samples;
+  out2[0] = mean;
+  out2[1] = std::sqrt(var);
+  return sample;
+}
 int orc_hci(void *h, const double *eps_var_sched30, int n_states, int max_iters, int max_dets) {
   return perform_hci(*(System *)h, eps_var_sched30, n_states, max_iters, max_dets);
 }

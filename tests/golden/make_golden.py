@@ -88,6 +88,32 @@ def heg_from_reference_log():
             if m:
                 out["pt_big"] = {"source": "src/e2e_tests/heg/o_st_ref", "pt_correction": float(m.group(1)), "eps_pt_big": float(m.group(2)),
                                  "ndets_connected": int(m.group(3)), "line": i + 1}
+        # the stochastic stage of the same log (second_order_pt_alias, hci.f90:1314): seeds, n_mc, every printed sample
+        stl = open(st).read().splitlines()
+        sto = {"source": "src/e2e_tests/heg/o_st_ref", "samples": [], "n_ref": []}
+        in_alias = False
+        for i, ln in enumerate(stl):
+            m = re.match(r"random number seeds \[mas(\d{4})(\d{4})(\d{4})(\d{4}) ", ln)
+            if m:
+                sto["irand_seed_1"] = [int(m.group(k)) for k in range(1, 5)]          # do_walk.f90:231-238 (4i4,x,4i4), first set
+            m = re.search(r"eps_var, eps_pt, eps_pt_big, target_error=\s*(\S+)\s+(\S+)\s+(\S+)\s+(\S+)", ln)
+            if m:
+                sto["target_error"] = float(m.group(4))
+            m = re.search(r"single-list stochastic method with N_MC=\s*(\d+)", ln)
+            if m:
+                sto["n_mc"] = int(m.group(1)); in_alias = True
+            m = re.match(r"n_connected_dets,n_ref=\s*\d+\s+(\d+)", ln)
+            if m and in_alias:
+                sto["n_ref"].append(int(m.group(1)))
+            m = re.match(r"Sample, E_2pt_now, E_2pt estimate, total energy=\s*(\d+)\s+(\S+)\s+(\S+)\s+(\S+) \+-\s+(\S+)", ln)
+            if m:
+                sto["samples"].append({"sample": int(m.group(1)), "e_now": float(m.group(2)), "estimate": float(m.group(3)),
+                                       "total": float(m.group(4)), "line": i + 1})
+            m = re.search(r"Second-order PT energy lowering=\s*(\S+) \+- (\S+) \(\s*(\S+)\s+(\S+)\)", ln)
+            if m:
+                sto["pt_total"], sto["std_dev"], sto["pt_diff"] = float(m.group(1)), float(m.group(2)), float(m.group(4))
+        sto["eps_pt"], sto["eps_pt_big"] = 2e-7, out["pt_big"]["eps_pt_big"]          # i_st: pt_eps; &selected_ci eps_pt_big
+        out["pt_stochastic"] = sto
     json.dump(out, open(os.path.join(HERE, "heg_o_det_ref.json"), "w"), indent=1)
     print("wrote heg_o_det_ref.json:", out["n_det"], out["nnz"])
 

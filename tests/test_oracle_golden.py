@@ -119,6 +119,32 @@ def test_heg_pt_reproduces_reference_log(oracle):
     assert nconn2 == big["ndets_connected"] == 13159 and abs(de2 - big["pt_correction"]) < 5e-10
 
 
+def _label_sorted(r):
+    """the variational wavefunction in label order (hci.f90:556-600 sorts it before the PT stage)"""
+    key = [(int(u[1]) << 64 | int(u[0]), int(d[1]) << 64 | int(d[0])) for u, d in zip(r["up"], r["dn"])]
+    o = np.array(sorted(range(len(key)), key=lambda i: key[i]))
+    return r["up"][o], r["dn"][o], r["wts"][o, 0]
+
+
+def test_heg_stochastic_pt_reproduces_reference_log(oracle):
+    """second_order_pt_alias restatement (hci.f90:1314-1684: rannyu stream, alias tables, n_mc = 200 draws per sample,
+    term1/term2 with the eps_pt_big parts removed, Welford) against the reference's own log src/e2e_tests/heg/o_st_ref:
+    all 143 printed samples (E_2pt_now to the printed 9 decimals, number of distinct sampled determinants), the stopping
+    sample, the final estimate -0.000729402 +- 0.000009966 and the total PT lowering -0.000928741 (o_st_ref:442-875)."""
+    gold = json.load(open(os.path.join(HERE, "golden", "heg_o_det_ref.json")))
+    g = gold["pt_stochastic"]
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    r = S.hci(1e-3, n_states=1)
+    up, dn, w = _label_sorted(r)
+    res = S.pt2_alias(up, dn, w, r["energy"][0], g["eps_pt"], g["eps_pt_big"], g["n_mc"], g["target_error"], g["irand_seed_1"], max_samples=400)
+    assert len(res["e_now"]) == len(g["samples"]) == 143                      # same stopping sample
+    assert res["n_distinct"].tolist() == g["n_ref"]                            # same draws
+    assert np.max(np.abs(res["e_now"] - np.array([x["e_now"] for x in g["samples"]]))) < 5.1e-10
+    assert abs(res["pt_energy"] - g["pt_diff"]) < 5.1e-10 and abs(res["std_dev"] - g["std_dev"]) < 5.1e-10
+    de_big, _ = S.pt2(up, dn, w, r["energy"][0], g["eps_pt_big"])
+    assert abs(de_big + res["pt_energy"] - g["pt_total"]) < 1.1e-9
+
+
 def test_davidson_single_against_dense(oracle, heg_space):
     """davidson_sparse_single restatement (more_tools.f90:3055-3233) on the 277-determinant matrix of the reference log:
     its printed eigenvalues coincide with davidson_sparse's golden ones (the solvers differ only in guard and restart)"""
