@@ -130,6 +130,30 @@ module sqmc_b200_iface
       real(c_double), value :: tol
       integer(c_int) :: n_matvec, n_ritz
     end function
+    integer(c_int) function sqmc_b200_pt2_alias(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, eps_pt_big, n_mc, target_error, rannyu_state, &
+        max_samples, pt_energy, pt_energy_std_dev, n_samples, e_2pt_samples, n_connected) bind(C, name="sqmc_b200_pt2_alias")
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: h, dets_up, dets_dn, e_2pt_samples   ! c_loc of the integer(ik) arrays; e_2pt_samples may be c_null_ptr
+      integer(c_int64_t), value :: n
+      real(c_double) :: wts(*)
+      real(c_double), value :: var_energy, eps_pt, eps_pt_big, target_error
+      integer(c_int), value :: n_mc, max_samples
+      integer(c_int32_t) :: rannyu_state(4)          ! savern(rannyu_state) before, setrn(rannyu_state) after
+      real(c_double) :: pt_energy, pt_energy_std_dev
+      integer(c_int) :: n_samples
+      integer(c_int64_t) :: n_connected
+    end function
+    integer(c_int) function sqmc_b200_pt2_sample(h, n, dets_up, dets_dn, n_sampled, sampled_up, sampled_dn, sampled_coeffs, w_over_p, n_mc, &
+        var_energy, eps_pt, eps_pt_big, e_2pt_this_sample, n_connected) bind(C, name="sqmc_b200_pt2_sample")
+      import :: c_int, c_int64_t, c_double, c_ptr
+      type(c_ptr), value :: h, dets_up, dets_dn, sampled_up, sampled_dn
+      integer(c_int64_t), value :: n, n_sampled
+      real(c_double) :: sampled_coeffs(*), w_over_p(*)
+      integer(c_int), value :: n_mc
+      real(c_double), value :: var_energy, eps_pt, eps_pt_big
+      real(c_double) :: e_2pt_this_sample
+      integer(c_int64_t) :: n_connected
+    end function
     integer(c_int) function sqmc_b200_register_host(ptr, bytes) bind(C, name="sqmc_b200_register_host")
       import :: c_int, c_int64_t, c_ptr
       type(c_ptr), value :: ptr

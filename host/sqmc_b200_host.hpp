@@ -175,6 +175,15 @@ inline void second_order_pt(model_system &S, int64_t ndets, const void *dets_up,
                             rk eps_pt, rk &delta_e_2pt, int64_t &ndets_connected) {
   check(sqmc_b200_pt2(S.h, ndets, dets_up, dets_dn, wts.data(), var_energy, eps_pt, &delta_e_2pt, &ndets_connected));
 }
+// second_order_pt_alias(ndets, dets_up, dets_dn, wts, diag_elems, var_energy, eps_pt, n_mc, target_error, eps_pt_big, pt_energy,
+//                       pt_energy_std_dev, ndets_connected, pt_big)   (hci.f90:1314), n_mc > 0.  irand_state = savern(): the advanced
+// state comes back for setrn, so the caller's rannyu stream continues as after the reference routine.
+inline void second_order_pt_alias(model_system &S, int64_t ndets, const void *dets_up, const void *dets_dn, const std::vector<rk> &wts, rk var_energy,
+                                  rk eps_pt, int n_mc, rk target_error, rk eps_pt_big, int32_t irand_state[4], rk &pt_energy, rk &pt_energy_std_dev,
+                                  int64_t &ndets_connected, int &n_samples, int max_samples = 1000000) {
+  check(sqmc_b200_pt2_alias(S.h, ndets, dets_up, dets_dn, wts.data(), var_energy, eps_pt, eps_pt_big, n_mc, target_error, irand_state, max_samples,
+                            &pt_energy, &pt_energy_std_dev, &n_samples, nullptr, &ndets_connected));
+}
 // ---- the reference's MPI data distribution: every rank passes / receives the slice of the determinants it owns ----
 // set once per determinant list: owner_of_row(i) = get_det_owner(dets_up(i), dets_dn(i)) (mpi_routines.f90:419); returns my_nimp
 inline int64_t set_ownership(model_system &S, const std::vector<int32_t> &owner_of_row) {

@@ -85,6 +85,29 @@ int sqmc_b200_hci_new_dets(sqmc_b200_handle *h, void *new_up /* n_new x 16 B */,
  * symmetrised determinants) and heg. */
 int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy,
                   double eps_pt, double *delta_e, int64_t *n_connected);
+/* Stochastic second-order correction, the semistochastic PT of do_pt (hci.f90:4245-4300): replaces second_order_pt_alias
+ * (hci.f90:1314-1684).
+ * sqmc_b200_pt2_sample = ONE sample, for a caller that keeps the sampling (rannyu, alias tables) on its side: replaces the call
+ *   find_doubly_excited(..., ref = the distinct sampled determinants, ref_coeffs, n_mc, w_over_p = counts/probs,
+ *   eps_var_pt = eps_pt, eps_var_pt_big = eps_pt_big, term1, term2, term1_big, term2_big) (hci.f90:1563-1566,
+ *   semistoch.f90:2044-2060) and the k loop behind it (hci.f90:1616-1632):
+ *     e = 1/(n_mc (n_mc-1)) * sum over k outside the variational list (dets_up/dn, n entries, any order) of
+ *         (term1(k)^2 + term2(k) - term1_big(k)^2 - term2_big(k)) / (var_energy - H_kk)
+ *   = the "E_2pt_now" the reference prints per sample (e2e_tests/heg/o_st_ref:442).  n_connected = ndets_connected of the call.
+ * sqmc_b200_pt2_alias = the whole routine: probabilities |c_i| / sum |c|, setup_alias / sample_alias (more_tools.f90:5603-5752),
+ *   n_mc draws per sample merged with counts (tools.f90:1574), Welford mean and variance (tools.f90:1761), stop when
+ *   sample >= 10 and the variance of the mean < target_error^2 (hci.f90:1670) or after max_samples; the variational list stays
+ *   on the device for all samples.  rannyu_state (4 x 12-bit digits, in/out) is the generator state the caller reads with savern
+ *   and writes back with setrn (rannyu.f90:11,76), so the reference's random stream continues unchanged: seeded like the
+ *   reference's HEG test the call reproduces all 143 samples of e2e_tests/heg/o_st_ref.  dets/wts must be sorted by label as in
+ *   the reference (hci.f90:1372-1378); e_2pt_samples (optional, max_samples entries) receives the per-sample values.
+ *   n_mc > 0 only (the reference's memory-based choice of n_mc, hci.f90:1570-1612, is host policy and stays with the caller). */
+int sqmc_b200_pt2_sample(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t n_sampled, const void *sampled_up,
+                         const void *sampled_dn, const double *sampled_coeffs, const double *w_over_p, int n_mc, double var_energy, double eps_pt,
+                         double eps_pt_big, double *e_2pt_this_sample, int64_t *n_connected);
+int sqmc_b200_pt2_alias(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+                        double eps_pt_big, int n_mc, double target_error, int32_t *rannyu_state, int max_samples, double *pt_energy,
+                        double *pt_energy_std_dev, int *n_samples, double *e_2pt_samples, int64_t *n_connected);
 
 /* ---- sparse H build --------------------------------------------------------
  * Replaces generate_sparse_ham_chem_upper_triangular (chemistry.f90:7639),

@@ -16,7 +16,7 @@ SYMBOLS = [
     "sqmc_b200_system_chem", "sqmc_b200_system_heg", "sqmc_b200_system_hubbardk", "sqmc_b200_free",
     "sqmc_b200_build_h", "sqmc_b200_export_upper", "sqmc_b200_import_upper", "sqmc_b200_nnz",
     "sqmc_b200_local_rows", "sqmc_b200_diagonal", "sqmc_b200_matvec", "sqmc_b200_projector",
-    "sqmc_b200_scale_values", "sqmc_b200_set_row_bundle", "sqmc_b200_lanczos", "sqmc_b200_davidson_single", "sqmc_b200_pt2", "sqmc_b200_davidson", "sqmc_b200_matvec_dev", "sqmc_b200_device_malloc",
+    "sqmc_b200_scale_values", "sqmc_b200_set_row_bundle", "sqmc_b200_lanczos", "sqmc_b200_davidson_single", "sqmc_b200_pt2", "sqmc_b200_pt2_sample", "sqmc_b200_pt2_alias", "sqmc_b200_davidson", "sqmc_b200_matvec_dev", "sqmc_b200_device_malloc",
     "sqmc_b200_device_free", "sqmc_b200_memcpy_h2d", "sqmc_b200_memcpy_d2h", "sqmc_b200_device_sync",
     "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
     "sqmc_b200_hci_new_dets", "sqmc_b200_set_hf_to_psit",
@@ -60,6 +60,8 @@ def load():
     L.sqmc_b200_scale_values.argtypes = [vp, dbl]
     L.sqmc_b200_set_row_bundle.argtypes = [vp, i32]
     L.sqmc_b200_pt2.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, vp, vp]
+    L.sqmc_b200_pt2_sample.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, i32, dbl, dbl, dbl, vp, vp]
+    L.sqmc_b200_pt2_alias.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, i32, vp, vp, vp, vp, vp]
     L.sqmc_b200_davidson_single.argtypes = [vp, vp, vp, vp, dbl, i32, vp, vp, i32, vp]
     L.sqmc_b200_lanczos.argtypes = [vp, vp, vp, vp, dbl, i32, vp, vp, i32, vp]
     L.sqmc_b200_davidson.argtypes = [vp, i32, vp, vp, vp, dbl, i32, vp, vp, i32, vp]

@@ -308,6 +308,40 @@ class SparseHamiltonian:
         check(self._L.sqmc_b200_pt2(self._h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), C.byref(de), C.byref(nc)))
         return de.value, nc.value
 
+    def second_order_pt_sample(self, dets_up, dets_dn, sampled_up, sampled_dn, sampled_coeffs, w_over_p, n_mc, var_energy, eps_pt, eps_pt_big):
+        """One sample of second_order_pt_alias (hci.f90:1563-1654): the find_doubly_excited call with n_mc / w_over_p / eps_var_pt_big
+        and the k loop behind it -> (e_2pt_this_sample, ndets_connected)."""
+        up = np.ascontiguousarray(dets_up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dets_dn, dtype=np.uint64).reshape(-1, 2)
+        su = np.ascontiguousarray(sampled_up, dtype=np.uint64).reshape(-1, 2)
+        sd = np.ascontiguousarray(sampled_dn, dtype=np.uint64).reshape(-1, 2)
+        sc = np.ascontiguousarray(sampled_coeffs, dtype=np.float64).reshape(-1)
+        sw = np.ascontiguousarray(w_over_p, dtype=np.float64).reshape(-1)
+        if len(dn) != len(up) or not (len(su) == len(sd) == len(sc) == len(sw)):
+            raise ValueError("second_order_pt_sample: inconsistent array lengths")
+        e, nc = C.c_double(), C.c_int64()
+        check(self._L.sqmc_b200_pt2_sample(self._h, len(up), _p(up), _p(dn), len(su), _p(su), _p(sd), _p(sc), _p(sw), int(n_mc), float(var_energy),
+                                           float(eps_pt), float(eps_pt_big), C.byref(e), C.byref(nc)))
+        return e.value, nc.value
+
+    def second_order_pt_alias(self, dets_up, dets_dn, wts, var_energy, eps_pt, eps_pt_big, n_mc, target_error, rannyu_state, max_samples=1000000):
+        """second_order_pt_alias (hci.f90:1314-1684) for n_mc > 0: the label-sorted variational wavefunction, the reference's rannyu
+        state (4 twelve-bit digits; the advanced state is returned) -> dict(pt_energy, pt_energy_std_dev, n_samples, e_2pt_samples,
+        ndets_connected, rannyu_state)."""
+        up = np.ascontiguousarray(dets_up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dets_dn, dtype=np.uint64).reshape(-1, 2)
+        w = np.ascontiguousarray(wts, dtype=np.float64).reshape(-1)
+        if len(dn) != len(up) or len(w) != len(up):
+            raise ValueError("second_order_pt_alias: dets_up, dets_dn and wts must have the same length")
+        st = np.array(rannyu_state, dtype=np.int32).reshape(4).copy()
+        cap = int(min(max_samples, 1000000))
+        es = np.zeros(cap)
+        pe, sd, ns, nc = C.c_double(), C.c_double(), C.c_int(), C.c_int64()
+        check(self._L.sqmc_b200_pt2_alias(self._h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), float(eps_pt_big), int(n_mc),
+                                          float(target_error), _p(st), cap, C.byref(pe), C.byref(sd), C.byref(ns), _p(es), C.byref(nc)))
+        return dict(pt_energy=pe.value, pt_energy_std_dev=sd.value, n_samples=ns.value, e_2pt_samples=es[:ns.value].copy(),
+                    ndets_connected=nc.value, rannyu_state=st)
+
     def davidson_sparse_single(self, initial_vector=None, tol=1.0e-10, max_iter=50):
         """davidson_sparse_single (more_tools.f90:3055-3233) on the resident matrix ->
         dict(lowest_eigenvalue, highest_eigenvalue, lowest_eigenvector, ritz, n_iter)."""

@@ -443,6 +443,30 @@ int sqmc_b200_pt2(sqmc_b200_handle *h, int64_t n, const void *dets_up, const voi
   return pt2(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, delta_e, n_connected);
 }
 
+int sqmc_b200_pt2_sample(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, int64_t n_sampled, const void *sampled_up,
+                         const void *sampled_dn, const double *sampled_coeffs, const double *w_over_p, int n_mc, double var_energy, double eps_pt,
+                         double eps_pt_big, double *e_2pt_this_sample, int64_t *n_connected) {
+  SQ_CHECK(require_init());
+  if (!h || !dets_up || !dets_dn || !sampled_up || !sampled_dn || !sampled_coeffs || !w_over_p || !e_2pt_this_sample || !n_connected) {
+    set_error("pt2_sample: null argument");
+    return 2;
+  }
+  return pt2_sample(h, n, dets_up, dets_dn, n_sampled, sampled_up, sampled_dn, sampled_coeffs, w_over_p, n_mc, var_energy, eps_pt, eps_pt_big,
+                    e_2pt_this_sample, n_connected);
+}
+
+int sqmc_b200_pt2_alias(sqmc_b200_handle *h, int64_t n, const void *dets_up, const void *dets_dn, const double *wts, double var_energy, double eps_pt,
+                        double eps_pt_big, int n_mc, double target_error, int32_t *rannyu_state, int max_samples, double *pt_energy,
+                        double *pt_energy_std_dev, int *n_samples, double *e_2pt_samples, int64_t *n_connected) {
+  SQ_CHECK(require_init());
+  if (!h || !dets_up || !dets_dn || !wts || !rannyu_state || !pt_energy || !pt_energy_std_dev || !n_samples || !n_connected) {
+    set_error("pt2_alias: null argument");
+    return 2;
+  }
+  return pt2_alias(h, n, dets_up, dets_dn, wts, var_energy, eps_pt, eps_pt_big, n_mc, target_error, rannyu_state, max_samples, pt_energy,
+                   pt_energy_std_dev, n_samples, e_2pt_samples, n_connected);
+}
+
 int sqmc_b200_davidson_single(sqmc_b200_handle *h, const double *v0, double *evec, double *eig2, double tol, int max_iter, int *n_iter_out,
                               double *ritz_log, int ritz_log_cap, int *n_ritz_logged) {
   SQ_CHECK(require_init());

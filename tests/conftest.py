@@ -60,3 +60,14 @@ def c2_hci_full(oracle):
     s = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=True, z=1, hf_symmetry=1)
     r = s.hci(1e-3, eps_var_sched=[2e-3, 2e-3], n_states=1)
     return s, r
+
+
+def label_sorted(r):
+    """the variational wavefunction of an oracle HCI result in label order (signed 128-bit compare on up, then dn; the order
+    perform_hci establishes before the PT stage, hci.f90:556-600) -> (up, dn, wts of state 1)"""
+    def sgn(x):
+        v = int(x[1]) << 64 | int(x[0])
+        return v - (1 << 128) if v >> 127 else v
+    key = [(sgn(u), sgn(d)) for u, d in zip(r["up"], r["dn"])]
+    o = np.array(sorted(range(len(key)), key=lambda i: key[i]))
+    return r["up"][o], r["dn"][o], r["wts"][o, 0]

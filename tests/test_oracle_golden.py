@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+from conftest import label_sorted
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "heg_o_det_ref.json")))
 
@@ -119,13 +121,6 @@ def test_heg_pt_reproduces_reference_log(oracle):
     assert nconn2 == big["ndets_connected"] == 13159 and abs(de2 - big["pt_correction"]) < 5e-10
 
 
-def _label_sorted(r):
-    """the variational wavefunction in label order (hci.f90:556-600 sorts it before the PT stage)"""
-    key = [(int(u[1]) << 64 | int(u[0]), int(d[1]) << 64 | int(d[0])) for u, d in zip(r["up"], r["dn"])]
-    o = np.array(sorted(range(len(key)), key=lambda i: key[i]))
-    return r["up"][o], r["dn"][o], r["wts"][o, 0]
-
-
 def test_heg_stochastic_pt_reproduces_reference_log(oracle):
     """second_order_pt_alias restatement (hci.f90:1314-1684: rannyu stream, alias tables, n_mc = 200 draws per sample,
     term1/term2 with the eps_pt_big parts removed, Welford) against the reference's own log src/e2e_tests/heg/o_st_ref:
@@ -135,7 +130,7 @@ def test_heg_stochastic_pt_reproduces_reference_log(oracle):
     g = gold["pt_stochastic"]
     S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
     r = S.hci(1e-3, n_states=1)
-    up, dn, w = _label_sorted(r)
+    up, dn, w = label_sorted(r)
     res = S.pt2_alias(up, dn, w, r["energy"][0], g["eps_pt"], g["eps_pt_big"], g["n_mc"], g["target_error"], g["irand_seed_1"], max_samples=400)
     assert len(res["e_now"]) == len(g["samples"]) == 143                      # same stopping sample
     assert res["n_distinct"].tolist() == g["n_ref"]                            # same draws
