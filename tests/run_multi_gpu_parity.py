@@ -124,6 +124,18 @@ def main():
     assert nconn == 501881 and abs(de - (-0.000939196)) < 5e-10, (nconn, de)     # src/e2e_tests/heg/o_det_ref:431
     if rank == 0:
         print("multi-gpu PT ok: world=%d ndets_connected=%d delta_e=%.9f" % (world, nconn, de))
+    # stochastic PT (second_order_pt_alias): every rank draws the same samples, the sampled determinants are dealt round-robin,
+    # the partial sums all-reduced -> the first 12 samples of the reference's own log src/e2e_tests/heg/o_st_ref:442-475
+    import json
+    from conftest import label_sorted
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heg_o_det_ref.json")))["pt_stochastic"]
+    su, sd, sw = label_sorted(rh)
+    seed = list(g["irand_seed_1"]); seed[3] = 2 * (seed[3] // 2) + 1
+    res = Hh.second_order_pt_alias(su, sd, sw, rh["energy"][0], g["eps_pt"], g["eps_pt_big"], g["n_mc"], g["target_error"], seed, max_samples=12)
+    gold = np.array([x["e_now"] for x in g["samples"][:12]])
+    assert res["n_samples"] == 12 and np.max(np.abs(res["e_2pt_samples"] - gold)) < 5.1e-10, res["e_2pt_samples"]
+    if rank == 0:
+        print("multi-gpu stochastic PT ok: world=%d, 12 samples of o_st_ref reproduced, running estimate %.9f" % (world, res["pt_energy"]))
     Hh.close()
     dist.barrier()
     dist.destroy_process_group()
