@@ -376,6 +376,113 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
   }
 }
 
+// ------------------------------------------------------------------ the adopted single-vector kernel
+// Same storage format, arithmetic and per-row order as bundle_hv_kernel<R, 1, 1, 4, ., true> (bit-identical results) with the start of a
+// bundle ordered for latency.  ncu's stall samples and the shared-bundle / several-bundles-per-warp experiments (profiles/
+// r02_bundle_kernel_ab.txt) showed that the per-bundle prologue -- row pointers -> head / tail entries (up to five scalar load ->
+// gather -> add rounds, one after the other) -> first block -> first gathers -- is a chain of serial memory latencies during which
+// the warp has nothing else in flight.  Here the first block's three 128-bit stream loads are issued FIRST, and the (up to five)
+// scalar load pairs of the head / tail entries are all issued before their gathers, so these latencies overlap: 2 % on the
+// 26-block bundles of the bench matrix, 6 % on 9-block bundles.
+template <int R, int MINB, bool SCAT>
+__global__ void __launch_bounds__(256, MINB) bundle_hvk_kernel(const int64_t *__restrict__ rowptr, int64_t nloc, int64_t nb, const int32_t *__restrict__ cols,
+                                                               const double *__restrict__ vals, double *__restrict__ y, OwnerScatter O,
+                                                               cudaTextureObject_t xtex) {
+  const Policies P;
+  auto gx = [&](int32_t col) -> double {
+    const int2 t = tex1Dfetch<int2>(xtex, col);
+    return __hiloint2double(t.y, t.x);
+  };
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (b < nb) {
+    const int64_t e0 = rowptr[b * R], e1 = rowptr[min(b * R + R, nloc)];
+    const Sigma S(e0, e1 - e0);
+    const int64_t nblk = S.nblk, o0 = e0 + S.h;
+    Blk A, B;
+    double xa[4], acc[R];
+    if (nblk > 0) blk_load(A, cols, vals, o0, lane, P);
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+    {
+      // head entry of this lane (slot 0) and its tail entries (slots 1..4); absent entries get column word 0 / value 0.0: a product
+      // 0.0 * x[0] that is routed nowhere (the one-hot bits of the word are 0)
+      const int64_t t0 = o0 + (nblk << 7) + lane;
+      int32_t cw[5];
+      double vv[5], xx[5];
+      cw[0] = 0; vv[0] = 0.0;
+      if (lane < S.h) { cw[0] = ld_col(cols + e0 + lane, P); vv[0] = ld_val(vals + e0 + lane, P); }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        cw[q + 1] = 0; vv[q + 1] = 0.0;
+        if (t0 + 32 * q < e1) { cw[q + 1] = ld_col(cols + t0 + 32 * q, P); vv[q + 1] = ld_val(vals + t0 + 32 * q, P); }
+      }
+#pragma unroll
+      for (int q = 0; q < 5; q++) xx[q] = gx(cw[q] >> kBShift);
+#pragma unroll
+      for (int q = 0; q < 5; q++) badd<R, 1>(acc, cw[q], vv[q] * xx[q]);
+    }
+    auto gather = [&](const Blk &K) {
+      xa[0] = gx(K.c.x >> kBShift);
+      xa[1] = gx(K.c.y >> kBShift);
+      xa[2] = gx(K.c.z >> kBShift);
+      xa[3] = gx(K.c.w >> kBShift);
+    };
+    auto work = [&](const Blk &K) {
+      badd<R, 1>(acc, K.c.x, K.v01.x * xa[0]);
+      badd<R, 1>(acc, K.c.y, K.v01.y * xa[1]);
+      badd<R, 1>(acc, K.c.z, K.v23.x * xa[2]);
+      badd<R, 1>(acc, K.c.w, K.v23.y * xa[3]);
+    };
+    // software pipeline over the full blocks with two named register sets: gathers of the current block, then the next block's
+    // 128-bit stream loads, then the current block's arithmetic (the loads are asm volatile: their order is kept)
+    int64_t j = 0;
+    for (; j + 2 <= nblk; j += 2) {
+      gather(A);
+      blk_load(B, cols, vals, o0 + ((j + 1) << 7), lane, P);
+      work(A);
+      gather(B);
+      if (j + 2 < nblk) blk_load(A, cols, vals, o0 + ((j + 2) << 7), lane, P);
+      work(B);
+    }
+    if (j < nblk) {
+      gather(A);
+      work(A);
+    }
+    double m0 = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      double a0 = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      if (lane == r) m0 = a0;
+    }
+    const int64_t row = b * R + lane;
+    if (lane < R && row < nloc) {
+      if (SCAT) {
+        double v = m0;
+        if (O.w) v = v + O.c * O.w[row];
+        O.dst[O.owner[row]][O.pos[row]] = v;
+      } else {
+        y[row] = m0;
+      }
+    }
+  }
+  if (SCAT) {  // all rows of this CTA are on their way: the last CTA publishes the epoch to every peer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long prev = atomicAdd(O.counter, 1ull);
+      if (prev == gridDim.x - 1) {
+        *O.counter = 0ull;
+        __threadfence_system();
+        for (int p = 0; p < O.nranks; p++)
+          if (O.flag[p]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(O.flag[p]), "l"(O.epoch) : "memory");
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 // default: bundles of 4 rows (measured best on B200, profiles/r01_bundle_experiment.txt); SQMC_BUNDLE=0|2|4 overrides.
 // Read per call (a getenv is ~100 ns) so that one process can A/B layouts on one resident matrix.
@@ -384,13 +491,14 @@ static int bundle_want() {
   const int v = e ? atoi(e) : 4;
   return (v == 2 || v == 4) ? v : 0;
 }
-// kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 3 = 0/1-multiplier routing + gathers through the texture path,
-// 1 = the same with LSU gathers, 0 = predicated adds; MINB = CTAs/SM the register allocation is bounded for).  Default 34
-// (falls back to 14 when the vector is not 512-byte aligned).  A/B results in profiles/r02_bundle_kernel_ab.txt.
+// kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 4 = the adopted kernel: 0/1-multiplier routing, gathers through the
+// texture path, latency-ordered bundle prologue; 3 = the same without the prologue ordering, 1 = 3 with LSU gathers, 0 = predicated
+// adds; MINB = CTAs/SM the register allocation is bounded for).  Default 44 (falls back to 14 when the vector is not 512-byte
+// aligned; two interleaved vectors use 34).  A/B results in profiles/r02_bundle_kernel_ab.txt.
 static int bundle_variant() {
   const char *e = getenv("SQMC_BUNDLE_KERNEL");
-  const int v = e ? atoi(e) : 34;
-  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 34 || v == 35) ? v : 34;
+  const int v = e ? atoi(e) : 44;
+  return (v == 4 || v == 5 || v == 14 || v == 15 || v == 34 || v == 35 || v == 44) ? v : 44;
 }
 
 template <int R>
@@ -521,8 +629,11 @@ static int launch_hv(sqmc_b200_handle *h, const double *x, double *y, cudaStream
     cudaTextureObject_t tex = 0;
     SQ_CHECK(x_texture(h, x, NV, &tex));
 #define SQ_BT(RR, MINB) bundle_hv_kernel<RR, 1, NV, MINB, false, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, y, none, tex)
-    if (R == 4) { if (var == 34) SQ_BT(4, 4); else SQ_BT(4, 5); }
-    else { if (var == 34) SQ_BT(2, 4); else SQ_BT(2, 5); }
+    if (NV == 1 && var == 44) {
+      if (R == 4) bundle_hvk_kernel<4, 4, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, y, none, tex);
+      else bundle_hvk_kernel<2, 4, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, y, none, tex);
+    } else if (R == 4) { if (var == 35) SQ_BT(4, 5); else SQ_BT(4, 4); }
+    else { if (var == 35) SQ_BT(2, 5); else SQ_BT(2, 4); }
 #undef SQ_BT
     SQ_LAUNCH_CHECK();
     return 0;
@@ -550,8 +661,8 @@ int bundle_spmv_scatter(sqmc_b200_handle *h, const double *x, const OwnerScatter
   if (bundle_variant() >= 30 && ((uintptr_t)x & 511) == 0) {
     cudaTextureObject_t tex = 0;
     SQ_CHECK(x_texture(h, x, 1, &tex));
-    if (R == 4) bundle_hv_kernel<4, 1, 1, 4, true, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, tex);
-    else bundle_hv_kernel<2, 1, 1, 4, true, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, tex);
+    if (R == 4) bundle_hvk_kernel<4, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, nullptr, O, tex);
+    else bundle_hvk_kernel<2, 4, true><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, nullptr, O, tex);
   } else if (R == 4) {
     bundle_hv_kernel<4, 1, 1, 4, true, false><<<grid, 256, 0, s>>>(h->d_rowptr, nloc, nb, h->d_cols, h->d_vals, x, nullptr, O, 0);
   } else {
