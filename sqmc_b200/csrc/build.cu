@@ -442,11 +442,14 @@ __global__ void __launch_bounds__(256) bitmap_rank_kernel(const uint32_t *bm, in
   }
 }
 
-template <int NW, bool FILL>
+// STG: every thread's probe list (the ids of {beta} U singles(beta), <= lmax of them, ids < 65536) is staged ONCE per tile in shared
+// memory, transposed ([k][thread]: conflict-free), instead of being re-read from global memory for each of the ~89 neighbour groups --
+// those reads are uncoalesced (one cache line per lane: 32 L1 wavefronts per warp instruction) and made the probe loop L1-bound.
+template <int NW, bool FILL, bool STG>
 __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, BmpView B, const TileDesc *tiles, int64_t ntiles, int64_t row_begin,
                                                                    int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen,
                                                                    const int32_t *old_of_new, const int32_t *olen) {
-  extern __shared__ uint32_t s_words[];  // bitmap row [W], rank row [W]
+  extern __shared__ uint32_t s_words[];  // bitmap row [W], rank row [W], (STG) probe lists [lmax][kConnTile] as 16-bit ids
   __shared__ uint64_t sEb[kConnStage * NW];
   __shared__ uint32_t sErep[FILL ? kConnStage : 1];
   __shared__ int32_t s_cnt[kConnTile];
@@ -470,6 +473,10 @@ __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, B
       const int32_t bid = V.eB[p];
       nb0 = B.nbrB_off[bid];
       nb1 = B.nbrB_off[bid + 1];
+    }
+    uint16_t *s_ids = reinterpret_cast<uint16_t *>(s_words + 2 * B.W);
+    if (STG) {  // every thread fills and reads only its own column: no barrier needed
+      for (int64_t k = nb0; k < nb1; k++) s_ids[(k - nb0) * kConnTile + threadIdx.x] = (uint16_t)__ldg(B.nbrB + k);
     }
     const int g = T.g;
     for (int64_t q = V.nbr_off[g]; q < V.nbr_off[g + 1]; q++) {
@@ -509,7 +516,7 @@ __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, B
         __syncthreads();
         const int64_t pos0 = only_new ? V.gNew_off[g2] : V.gA_off[g2];
         for (int64_t k = nb0; k < nb1; k++) {
-          const int32_t id = __ldg(B.nbrB + k);
+          const int32_t id = STG ? (int32_t)s_ids[(k - nb0) * kConnTile + threadIdx.x] : __ldg(B.nbrB + k);
           const uint32_t w = s_bm[id >> 5];
           const int bit = id & 31;
           if ((w >> bit) & 1u) {
@@ -1317,14 +1324,20 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       bitmap_rank_kernel<<<nblocks(nA * 32), 256, 0, s>>>(bits.p, nA, W, rank.p);
       SQ_LAUNCH_CHECK();
     }
-    if (2 * W * 4 > 24 * 1024) {
-      SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * 4));
-      SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * W * 4));
-    }
+  }
+  // probe lists staged in shared memory when they are short enough (lmax = ndn (norb - ndn) + 1 ids per string) and the ids fit 16 bits
+  const int probe_lmax = T.ndn * (T.norb - T.ndn) + 1;
+  bool stage_ids = use_bmp && nB <= 65535 && 2 * W * 4 + probe_lmax * kConnTile * 2 <= 160 * 1024;
+  if (const char *se = getenv("SQMC_CONNECT_STAGE")) stage_ids = stage_ids && atoi(se) != 0;
+  const int bmp_smem = 2 * W * 4 + (stage_ids ? probe_lmax * kConnTile * 2 : 0);
+  if (use_bmp && bmp_smem > 24 * 1024) {
+    SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bmp_smem));
+    SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bmp_smem));
+    SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bmp_smem));
+    SQ_CUDA(cudaFuncSetAttribute(connect_bitmap_kernel<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bmp_smem));
   }
   EBb.release();
   const BmpView BV{bm.p, rk.p, bmN.p, rkN.p, W, nbrB_off.p, nbrB.p};
-  const int bmp_smem = 2 * W * 4;
   // incremental build: the partitioned row / candidate view
   DevBuf<int32_t> Pidx;
   DevBuf<uint64_t> Pb;
@@ -1393,7 +1406,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
     else if (!ts) connect_tile_kernel<NW, FILL, false, true><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);        \
     else connect_tile_kernel<NW, FILL, false, false><<<cgrid, kConnTile, 0, s>>>(__VA_ARGS__);                \
   } while (0)
-      if (use_bmp) connect_bitmap_kernel<NW, false><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
+      if (use_bmp && stage_ids) connect_bitmap_kernel<NW, false, true><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
+      else if (use_bmp) connect_bitmap_kernel<NW, false, false><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
       else SQ_CONN(false, V, dt.p, (int64_t)tiles.size(), c0, cand_count.p + c0, nullptr, nullptr, nullptr, d_oon, nullptr);
       SQ_LAUNCH_CHECK();
       SQ_CUDA(cudaStreamSynchronize(s));
@@ -1589,7 +1603,8 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
       const TileDesc *td = fill_tiles_dev.p + cp.tile_off;
       const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cp.ntiles, G.sm_count * 16));
       const bool w32 = NW == 1 && T.norb <= 32;
-      if (use_bmp) connect_bitmap_kernel<NW, true><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, alen.p, d_oon, d_olen);
+      if (use_bmp && stage_ids) connect_bitmap_kernel<NW, true, true><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, alen.p, d_oon, d_olen);
+      else if (use_bmp) connect_bitmap_kernel<NW, true, false><<<cgrid, kConnTile, bmp_smem, s>>>(V, BV, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, alen.p, d_oon, d_olen);
       else SQ_CONN(true, V, td, cp.ntiles, r, nullptr, cptr.p, cand_tmp.p, ts ? nullptr : alen.p, d_oon, d_olen);
       SQ_LAUNCH_CHECK();
     }
