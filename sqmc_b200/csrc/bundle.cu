@@ -276,19 +276,6 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
 #pragma unroll
   for (int r = 0; r < (NV == 2 ? R : 1); r++) acc2[r] = 0.0;
 
-  auto one = [&](int32_t cw, double v) {
-    if (NV == 1) {
-      badd<R, MODE>(acc, cw, v * gx(cw >> kBShift));
-    } else {
-      const double2 xv = gx2(cw >> kBShift);
-      badd<R, MODE>(acc, cw, v * xv.x);
-      badd<(NV == 2 ? R : 1), MODE>(acc2, cw, v * xv.y);
-    }
-  };
-  // entries in front of the first aligned block (<= 3) and behind the last full block (<= 127): merged order, scalar loads
-  if (lane < S.h) one(ld_col(cols + e0 + lane, P), ld_val(vals + e0 + lane, P));
-  for (int64_t k = e0 + S.h + (S.nblk << 7) + lane; k < e1; k += 32) one(ld_col(cols + k, P), ld_val(vals + k, P));
-
   const int64_t o0 = e0 + S.h;
   auto work = [&](const Blk &B, double (&xa)[4], double (&xb)[4]) {
     badd<R, MODE>(acc, B.c.x, B.v01.x * xa[0]);
@@ -322,6 +309,34 @@ __global__ void __launch_bounds__(256, MINB) bundle_hv_kernel(const int64_t *__r
   double xa[4], xb[4];
   const int64_t nblk = S.nblk;
   if (nblk > 0) blk_load(A, cols, vals, o0, lane, P);
+  // entries in front of the first aligned block (<= 3) and behind the last full block (<= 127), merged order, scalar loads -- after the
+  // first block's stream loads are on their way (see bundle_hvk_kernel)
+  if constexpr (NV == 1) {
+    // all load pairs first (slot 0: head, slots 1..4: tail), then all gathers, then the products; absent entries get column word 0 /
+    // value 0.0: a product 0.0 * x[0] that is routed nowhere
+    const int64_t t0 = o0 + (nblk << 7) + lane;
+    int32_t cw[5];
+    double vv[5], xx[5];
+    cw[0] = 0; vv[0] = 0.0;
+    if (lane < S.h) { cw[0] = ld_col(cols + e0 + lane, P); vv[0] = ld_val(vals + e0 + lane, P); }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      cw[q + 1] = 0; vv[q + 1] = 0.0;
+      if (t0 + 32 * q < e1) { cw[q + 1] = ld_col(cols + t0 + 32 * q, P); vv[q + 1] = ld_val(vals + t0 + 32 * q, P); }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; q++) xx[q] = gx(cw[q] >> kBShift);
+#pragma unroll
+    for (int q = 0; q < 5; q++) badd<R, MODE>(acc, cw[q], vv[q] * xx[q]);
+  } else {  // two vectors: 2 R row sums are live, the entries are taken one round at a time
+    auto one = [&](int32_t cw, double v) {
+      const double2 xv = gx2(cw >> kBShift);
+      badd<R, MODE>(acc, cw, v * xv.x);
+      badd<(NV == 2 ? R : 1), MODE>(acc2, cw, v * xv.y);
+    };
+    if (lane < S.h) one(ld_col(cols + e0 + lane, P), ld_val(vals + e0 + lane, P));
+    for (int64_t k = o0 + (nblk << 7) + lane; k < e1; k += 32) one(ld_col(cols + k, P), ld_val(vals + k, P));
+  }
   int64_t j = 0;
   for (; j + 2 <= nblk; j += 2) {
     gather(A, xa, xb);
@@ -492,9 +507,9 @@ static int bundle_want() {
   return (v == 2 || v == 4) ? v : 0;
 }
 // kernel variant: SQMC_BUNDLE_KERNEL = 10*MODE + MINB (MODE 4 = the adopted kernel: 0/1-multiplier routing, gathers through the
-// texture path, latency-ordered bundle prologue; 3 = the same without the prologue ordering, 1 = 3 with LSU gathers, 0 = predicated
+// texture path; 3 = the same body as a member of the general template (two vectors, A/B), 1 = 3 with LSU gathers, 0 = predicated
 // adds; MINB = CTAs/SM the register allocation is bounded for).  Default 44 (falls back to 14 when the vector is not 512-byte
-// aligned; two interleaved vectors use 34).  A/B results in profiles/r02_bundle_kernel_ab.txt.
+// aligned; two interleaved vectors use 34).  All variants start a bundle with the latency-ordered prologue.  A/B results in profiles/r02_bundle_kernel_ab.txt.
 static int bundle_variant() {
   const char *e = getenv("SQMC_BUNDLE_KERNEL");
   const int v = e ? atoi(e) : 44;
