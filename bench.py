@@ -420,7 +420,8 @@ def emit(c, args, H, system_factory, up, dn, workload, config_extra, t_build, t_
                 "call": e2e_call},
         "gpu_launches": launches,
         "clocks": clocks,
-        "build": {"seconds_wall": t_build, "nnz_upper_per_s": nnz_upper / t_build, "phases_ms": bt, "space_seconds": t_space},
+        "build": {"seconds_wall": t_build, "nnz_upper_per_s": nnz_upper / t_build, "phases_ms": bt, "alloc_stall_ms": LAST_BUILD_STALL_MS,
+                  "space_seconds": t_space},
         "step_ms_min_max": [min(per), max(per)],
         "nnz_per_rank_max_over_mean": nnz_max / (nnz_full / c.world),
     }
@@ -435,10 +436,19 @@ def emit(c, args, H, system_factory, up, dn, workload, config_extra, t_build, t_
         raise SystemExit("bench.py: parity check failed: %s" % json.dumps(par))
 
 
+LAST_BUILD_STALL_MS = 0.0
+
+
 def timed_build(c, H, up, dn, **kw):
+    """wall time of one build (max over ranks); the host time this rank spent blocked inside allocator / memory-mapping calls during it
+    goes to LAST_BUILD_STALL_MS (printed as build.alloc_stall_ms: erratic on virtualised hosts, profiles/r02_alloc_trace.txt)"""
+    global LAST_BUILD_STALL_MS
+    from sqmc_b200 import _lib
     barrier(c)
+    _lib.load().sqmc_b200_alloc_stall_ms(1)
     t0 = time.perf_counter()
     H.generate_sparse_ham_upper_triangular(up, dn, **kw)
+    LAST_BUILD_STALL_MS = float(_lib.load().sqmc_b200_alloc_stall_ms(1))
     barrier(c)
     return max_over_ranks(c, time.perf_counter() - t0)
 

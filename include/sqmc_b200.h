@@ -241,6 +241,10 @@ int sqmc_b200_build_times(sqmc_b200_handle *h, double *stats8);
 int sqmc_b200_partition_rows(const int64_t *work_prefix, int64_t n, int nranks, int64_t *row_starts);
 /* number of kernels launched by the library since init (for gpu_launches accounting) */
 int64_t sqmc_b200_launch_count(void);
+/* Host milliseconds this process has spent inside device allocator / memory-mapping calls since start (or since the last call with
+ * reset != 0).  On virtualised GPU hosts these driver calls block for 0.01-1.2 s at random; the bench prints the number next to every
+ * build so that its wall time can be read (profiles/r02_alloc_trace.txt). */
+double sqmc_b200_alloc_stall_ms(int reset);
 
 #ifdef __cplusplus
 }

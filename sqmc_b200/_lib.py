@@ -21,7 +21,7 @@ SYMBOLS = [
     "sqmc_b200_get_perm", "sqmc_b200_build_times", "sqmc_b200_launch_count", "sqmc_b200_partition_rows", "sqmc_b200_get_row", "sqmc_b200_system_orbital_symmetries", "sqmc_b200_hci_select",
     "sqmc_b200_hci_new_dets", "sqmc_b200_set_hf_to_psit",
     "sqmc_b200_set_ownership", "sqmc_b200_matvec_local", "sqmc_b200_projector_local", "sqmc_b200_davidson_local",
-    "sqmc_b200_last_build_incremental", "sqmc_b200_register_host", "sqmc_b200_unregister_host", "sqmc_b200_exchange_mode",
+    "sqmc_b200_last_build_incremental", "sqmc_b200_alloc_stall_ms", "sqmc_b200_register_host", "sqmc_b200_unregister_host", "sqmc_b200_exchange_mode",
 ]
 
 
@@ -43,6 +43,8 @@ def load():
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
     L.sqmc_b200_last_error.restype = C.c_char_p
     L.sqmc_b200_launch_count.restype = i64
+    L.sqmc_b200_alloc_stall_ms.restype = dbl
+    L.sqmc_b200_alloc_stall_ms.argtypes = [i32]
     L.sqmc_b200_get_unique_id.argtypes = [vp]
     L.sqmc_b200_init.argtypes = [i32, i32, i32, vp]
     L.sqmc_b200_system_chem.argtypes = [vp, i32, i32, i32, vp, i64, vp, i32, i32]

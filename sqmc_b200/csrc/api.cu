@@ -39,7 +39,10 @@ namespace sqmc {
 // costs ~40 ms per GB).  Memory is returned explicitly when some allocation fails (devbuf_alloc, big_malloc, grow_ensure).
 static const uint64_t kPoolKeepBytes = ~0ull;
 static bool g_use_pool = true;
-// SQMC_ALLOC_TRACE=1: report every allocator call that blocks the host for more than 10 ms
+// Host time spent inside allocator / mapping calls is accumulated (g_alloc_stall_ms, sqmc_b200_alloc_stall_ms): on the measurement
+// boxes these calls block for 0.01-1.2 s at random, and a build's wall time is only readable next to this number.
+// SQMC_ALLOC_TRACE=1 additionally reports every call that blocks the host for more than 10 ms.
+double g_alloc_stall_ms = 0.0;
 struct AllocTrace {
   const char *what;
   size_t bytes;
@@ -49,11 +52,11 @@ struct AllocTrace {
     if (v < 0) { const char *e = getenv("SQMC_ALLOC_TRACE"); v = (e && atoi(e) > 0) ? 1 : 0; }
     return v == 1;
   }
-  AllocTrace(const char *w, size_t b) : what(w), bytes(b) { if (on()) t0 = std::chrono::steady_clock::now(); }
+  AllocTrace(const char *w, size_t b) : what(w), bytes(b) { t0 = std::chrono::steady_clock::now(); }
   ~AllocTrace() {
-    if (!on()) return;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (ms > 10.0) fprintf(stderr, "[sqmc alloc] %s of %.3f GB blocked the host for %.1f ms\n", what, bytes / 1e9, ms);
+    g_alloc_stall_ms += ms;
+    if (on() && ms > 10.0) fprintf(stderr, "[sqmc alloc] %s of %.3f GB blocked the host for %.1f ms\n", what, bytes / 1e9, ms);
   }
 };
 int devbuf_alloc(void **p, size_t bytes) {
@@ -114,6 +117,11 @@ extern "C" {
 
 const char *sqmc_b200_last_error(void) { return g_last_error.c_str(); }
 int64_t sqmc_b200_launch_count(void) { return g_launch_count; }
+double sqmc_b200_alloc_stall_ms(int reset) {
+  const double v = sqmc::g_alloc_stall_ms;
+  if (reset) sqmc::g_alloc_stall_ms = 0.0;
+  return v;
+}
 
 int sqmc_b200_get_unique_id(void *id128) {
   ncclUniqueId id;

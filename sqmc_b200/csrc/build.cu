@@ -538,6 +538,17 @@ __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, B
             const int32_t id = probe_id(k);
             cnt += (int)((s_bm[id >> 5] >> (id & 31)) & 1u);
           }
+        } else if (!STG) {  // ids come from global memory: one pass, test and emit together
+          for (int64_t k = nb0; k < nb1; k++) {
+            const int32_t id = __ldg(B.nbrB + k);
+            const uint32_t w = s_bm[id >> 5];
+            const int bit = id & 31;
+            if ((w >> bit) & 1u) {
+              const int64_t pos = pos0 + s_rk[id >> 5] + __popc(w & ((1u << bit) - 1u));
+              cand[base + cnt] = only_new ? V.Pidx[pos] : (int32_t)pos;
+              cnt++;
+            }
+          }
         } else {
           // ~9 % of the probes hit, so almost every probe has SOME lane of the warp on the hit path: the tests of 32 probes are
           // collected in a mask first (branch-free) and only the set bits are walked -- ~7 instead of ~30 divergent hit-path

@@ -12,6 +12,7 @@ namespace sqmc {
 
 extern std::string g_last_error;
 extern int64_t g_launch_count;
+extern double g_alloc_stall_ms;  // host milliseconds spent inside allocator / memory-mapping calls (api.cu)
 void set_error(const char *fmt, ...);
 
 #define SQ_CUDA(call)                                                                              \

@@ -86,9 +86,10 @@ int grow_ensure(GrowBuf &b, size_t bytes) {
     const size_t before;
     GrowBuf &b;
     ~Report() {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      g_alloc_stall_ms += ms;
       const char *e = getenv("SQMC_ALLOC_TRACE");
       if (!(e && atoi(e) > 0)) return;
-      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (ms > 10.0) fprintf(stderr, "[sqmc alloc] mapping %.3f GB of a growable array blocked the host for %.1f ms\n", (b.mapped - before) / 1e9, ms);
     }
   } report{t_begin, mapped_before, b};
@@ -109,15 +110,17 @@ int grow_ensure(GrowBuf &b, size_t bytes) {
     }
     if (r != CUDA_SUCCESS) { set_error("growbuf: out of device memory mapping %zu bytes (have %zu)", bytes, b.mapped); return 1; }
     r = D.MemMap((CUdeviceptr)(b.base + b.mapped), b.chunk, 0, hd, 0);
-    if (r == CUDA_SUCCESS) r = D.MemSetAccess((CUdeviceptr)(b.base + b.mapped), b.chunk, &acc, 1);
     if (r != CUDA_SUCCESS) {
       D.MemRelease(hd);
-      set_error("growbuf: cuMemMap / cuMemSetAccess failed (%d)", (int)r);
+      set_error("growbuf: cuMemMap failed (%d)", (int)r);
       return 1;
     }
     b.handles.push_back((unsigned long long)hd);
     b.mapped += b.chunk;
   }
+  // access rights for the whole new range in ONE call (per-chunk calls were the larger part of the mapping time)
+  CUresult r = D.MemSetAccess((CUdeviceptr)(b.base + mapped_before), b.mapped - mapped_before, &acc, 1);
+  if (r != CUDA_SUCCESS) { set_error("growbuf: cuMemSetAccess failed (%d)", (int)r); return 1; }
   return 0;
 }
 

@@ -109,8 +109,11 @@ def hci_space(H, system, n_dets, eps_schedule=(1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 5e-
         up, dn = np.concatenate([up, nu]), np.concatenate([dn, nd])
         min_h = np.concatenate([min_h, np.full(len(nu), 9e99)])
         t0 = time.perf_counter()
+        from . import _lib
+        _lib.load().sqmc_b200_alloc_stall_ms(1)
         nnz = H.generate_sparse_ham_upper_triangular(up, dn, ndet_old=n_old)
         t_build = time.perf_counter() - t0
+        stall_build = float(_lib.load().sqmc_b200_alloc_stall_ms(1))
         v0 = np.zeros((len(up), 1))
         v0[:n_old, 0] = wts[:, 0]
         t0 = time.perf_counter()
@@ -119,7 +122,8 @@ def hci_space(H, system, n_dets, eps_schedule=(1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 5e-
         wts, energy = d["evecs"], float(d["evals"][0])
         if log is not None:
             log.append({"iter": it, "eps_var": eps, "n_dets": len(up), "nnz_upper": int(nnz), "energy": energy, "select_s": t_sel, "build_s": t_build,
-                        "build_device_ms": H.build_times()["total_ms"], "build_incremental": bool(H.last_build_incremental()),
+                        "build_device_ms": H.build_times()["total_ms"], "build_alloc_stall_ms": stall_build,
+                        "build_incremental": bool(H.last_build_incremental()),
                         "davidson_s": t_dav, "n_matvec": int(d["n_matvec"])})
         if len(up) >= n_dets:
             break
