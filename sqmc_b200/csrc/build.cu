@@ -749,6 +749,11 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
   int kb = 0;
   while (true) {
     int job = -1;
+    // a light job found by the scan trip keeps its candidate (row index, strings, orientation) in registers; a queued single is
+    // loaded at the job site
+    int32_t j = -1;
+    Bits<NW> ku = b_zero<NW>(), kd = b_zero<NW>();
+    bool fwd = true, loaded = false;
     if (MODEL == MODEL_CHEM && (qn >= 32 || (kb >= L && qn > 0))) {
       const int take = min(qn, 32);
       if (lane < take) job = s_q[w][lane];
@@ -760,13 +765,16 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
     } else if (kb < L) {
       const int k = kb + lane;
       const bool in = k < L;
-      const int32_t j = in ? cand[base + k] : -1;
+      j = in ? cand[base + k] : -1;
       const int32_t jprev = (TS && in && k > 0) ? cand[base + k - 1] : -2;
       const bool todo = in && j != (int32_t)p && j != jprev;
       bool heavy = false;
-      if (MODEL == MODEL_CHEM && todo) {
-        const Bits<NW> ju = b_load<NW>(up, j), jd = b_load<NW>(dn, j);
-        heavy = cp < perm[j] ? chem_is_heavy<NW, TS>(pu, pd, ju, jd) : chem_is_heavy<NW, TS>(ju, jd, pu, pd);
+      if (todo) {
+        ku = b_load<NW>(up, j);
+        kd = b_load<NW>(dn, j);
+        fwd = cp < perm[j];  // the reference stores H(i,j) for caller index i<j with det_i as bra: evaluate in that orientation
+        loaded = true;
+        if (MODEL == MODEL_CHEM) heavy = fwd ? chem_is_heavy<NW, TS>(pu, pd, ku, kd) : chem_is_heavy<NW, TS>(ku, kd, pu, pd);
       }
       if (todo && !heavy) job = k;
       if (MODEL == MODEL_CHEM) {
@@ -780,9 +788,14 @@ __global__ void __launch_bounds__(256) eval_kernel(ModelTables T, const uint64_t
       break;
     }
     if (job >= 0) {
-      const int32_t j = cand[base + job];
-      Bits<NW> bu = pu, bd = pd, ku = b_load<NW>(up, j), kd = b_load<NW>(dn, j);
-      if (!(cp < perm[j])) {  // the reference stores H(i,j) for caller index i<j with det_i as bra: evaluate in that orientation
+      if (!loaded) {
+        j = cand[base + job];
+        ku = b_load<NW>(up, j);
+        kd = b_load<NW>(dn, j);
+        fwd = cp < perm[j];
+      }
+      Bits<NW> bu = pu, bd = pd;
+      if (!fwd) {
         Bits<NW> t = bu; bu = ku; ku = t;
         t = bd; bd = kd; kd = t;
       }

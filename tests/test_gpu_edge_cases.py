@@ -112,3 +112,19 @@ def test_error_behaviour():
     hub = sq.HubbardKSystem(4, 4, 1.0, 4.0, 3, 3)
     with pytest.raises(sq.SqmcError):                                   # selection exists for chem / heg only (hci.f90:1073)
         sq.SparseHamiltonian(hub).get_next_det_list(hf, hf, [1.0], [9e99], 1e-3)
+
+
+def test_alloc_stall_counter():
+    """sqmc_b200_alloc_stall_ms: host time inside allocator / mapping calls is accumulated and can be reset"""
+    import sqmc_b200 as sq
+    from sqmc_b200 import _lib, spaces
+    L = _lib.load()
+    L.sqmc_b200_alloc_stall_ms(1)
+    chem = sq.ChemSystem(C2_FCIDUMP)
+    up, dn, _ = spaces.c2_lowest_energy_space(chem, 2000)
+    H = sq.SparseHamiltonian(chem)
+    H.generate_sparse_ham_upper_triangular(up, dn)
+    v = L.sqmc_b200_alloc_stall_ms(1)
+    assert v > 0.0 and v < 60000.0          # a build allocates
+    assert L.sqmc_b200_alloc_stall_ms(0) == 0.0
+    H.close()
