@@ -81,3 +81,37 @@ def test_cpp_caller_hubbard_hf_to_psit(oracle, tmp_path):
     assert H.generate_sparse_ham_upper_triangular(up, dn, hf_to_psit=True) == len(ref[1])
     got = H.export_upper()
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def test_cpp_caller_semistochastic_pt(oracle, tmp_path):
+    """host/pt_demo.cpp = the semistochastic branch of do_pt (hci.f90:4245-4300) as a compiled caller: second_order_pt with
+    eps_pt_big, then second_order_pt_alias with the caller's rannyu state, on the reference's HEG end-to-end case
+    (src/e2e_tests/heg/o_st_ref:432,873): -0.000199339, -0.000729402 +- 0.000009966 after 143 samples, total lowering -0.000928741"""
+    import json
+    import sqmc_b200 as sq
+    from conftest import label_sorted
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "heg_o_det_ref.json")))
+    st, big = g["pt_stochastic"], g["pt_big"]
+    S = oracle.System.heg(3, 0.5, 14, 7, 1.49)
+    r = S.hci(1e-3, n_states=1)
+    up, dn, w = label_sorted(r)
+    hs = sq.HegSystem(3, 0.5, 14, 7, 1.49)
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    seed = list(st["irand_seed_1"]); seed[3] = 2 * (seed[3] // 2) + 1          # setrn (rannyu.f90:19)
+    hdr = [hs.norb, hs.n_dim, hs.nup, hs.ndn, len(up), st["n_mc"], 1000] + seed + [0]
+    par = np.array([hs.length_cell, r["energy"][0], st["eps_pt"], st["eps_pt_big"], st["target_error"]])
+    inp, outp = str(tmp_path / "pt_in.bin"), str(tmp_path / "pt_out.bin")
+    with open(inp, "wb") as f:
+        f.write(np.asarray(hdr, dtype=np.int64).tobytes())
+        for b in (par, hs.k_vectors, up, dn, w):
+            f.write(np.ascontiguousarray(b).tobytes())
+    p = subprocess.run([os.path.join(HOST, "pt_demo"), inp, outp], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = np.fromfile(outp, dtype=np.float64)
+    pt_big, nconn_big, pt_diff, sd, n_samples = out[0], int(out[1]), out[2], out[3], int(out[4])
+    assert nconn_big == big["ndets_connected"] and abs(pt_big - big["pt_correction"]) < 5.1e-10
+    assert n_samples == len(st["samples"]) == 143
+    assert abs(pt_diff - st["pt_diff"]) < 5.1e-10 and abs(sd - st["std_dev"]) < 5.1e-10
+    assert abs(pt_big + pt_diff - st["pt_total"]) < 1.1e-9
+    assert int(out[6]) % 2 == 1                                                # the advanced rannyu state stays odd
+    assert "Second-order PT energy lowering=" in p.stdout
