@@ -288,6 +288,8 @@ struct TileDesc {
 };
 static const int kConnTile = 256;
 static const int kConnStage = 1024;  // beta strings staged per step
+static const int kBmpStage = 256;    // the same in connect_bitmap_kernel (own group only): with the probe lists in shared memory a small
+                                     // stage lets four CTAs share an SM (54 KB each for C2) instead of three
 
 // W32: norb <= 32 -> strings are compared as 32-bit words (POPC is a quarter-rate instruction: one instead of two per test)
 // SORTED (no time-reversal expansion: entries == rows): the candidate groups are visited in ascending order and the row
@@ -450,8 +452,8 @@ __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, B
                                                                    int32_t *counts, const int64_t *cand_ptr, int32_t *cand, int32_t *alen,
                                                                    const int32_t *old_of_new, const int32_t *olen) {
   extern __shared__ uint32_t s_words[];  // bitmap row [W], rank row [W], (STG) probe lists [lmax][kConnTile] as 16-bit ids
-  __shared__ uint64_t sEb[kConnStage * NW];
-  __shared__ uint32_t sErep[FILL ? kConnStage : 1];
+  __shared__ uint64_t sEb[kBmpStage * NW];
+  __shared__ uint32_t sErep[FILL ? kBmpStage : 1];
   __shared__ int32_t s_cnt[kConnTile];
   __shared__ int32_t s_row[kConnTile];
   uint32_t *s_bm = s_words, *s_rk = s_words + B.W;
@@ -485,8 +487,8 @@ __global__ void __launch_bounds__(kConnTile) connect_bitmap_kernel(ConnView V, B
         // own group: beta singles and doubles (and the row itself) -> scan the staged strings
         const int64_t lo = only_new ? V.gNew_off[g2] : V.gA_off[g2], hi = V.gA_off[g2 + 1];
         const uint64_t *cEb = only_new ? V.Pb : V.Eb;
-        for (int64_t s0 = lo; s0 < hi; s0 += kConnStage) {
-          const int ns = (int)min((int64_t)kConnStage, hi - s0);
+        for (int64_t s0 = lo; s0 < hi; s0 += kBmpStage) {
+          const int ns = (int)min((int64_t)kBmpStage, hi - s0);
           __syncthreads();
           for (int i = threadIdx.x; i < ns; i += blockDim.x) {
 #pragma unroll
