@@ -1370,7 +1370,11 @@ static int build_impl(sqmc_b200_handle *h, int64_t n, const void *dets_up, const
   DevBuf<int32_t> nbrB;
   DevBuf<uint32_t> bm, rk, bmN, rkN;
   const int W = (int)div_up(nB, 32);
-  bool use_bmp = !ts && W <= 8192 && nA * (int64_t)W <= (1ll << 28);
+  // Probing pays when the alpha groups are large: the scanning join costs a row ~n/nA tests per neighbour group, a probe pass ~lmax
+  // probes plus the staging of 2 W words per (tile, group).  HEG spaces have ~10 determinants per alpha string (137 220 / 15 024,
+  // 10^6 / 73 111): there the scan is 3-4x faster (build of the 10^6-determinant HEG space: 0.10 s vs 0.47 s), so probes need
+  // n >= 64 nA (C2 10^7: 669 per group, C2 10^6 lowest-energy: 96, Hubbard full sector: 804).
+  bool use_bmp = !ts && W <= 8192 && nA * (int64_t)W <= (1ll << 28) && n >= 64 * nA;
   if (const char *be = getenv("SQMC_CONNECT_BITMAP")) use_bmp = use_bmp && atoi(be) != 0;
   if (use_bmp) {
     SQ_CHECK(neighbour_lists<NW>(EBb.p, gB_off.p, nB, T.ndn, T.norb, nbrB_off, nbrB, s));
