@@ -169,3 +169,79 @@ def test_pt2_numerators_equal_full_matrix_elements(oracle, time_sym):
     haa = S.elements(au, ad, au, ad)
     ref = float(np.sum(num ** 2 / (e - haa)))
     assert abs(de - ref) < 1e-12 and de < -1e-2
+
+
+def _all_excitations(u, d, norb):
+    occu = [o for o in range(norb) if u >> o & 1]; viru = [o for o in range(norb) if not u >> o & 1]
+    occd = [o for o in range(norb) if d >> o & 1]; vird = [o for o in range(norb) if not d >> o & 1]
+    out = set()
+    for p in occu:
+        for q in viru:
+            out.add((u ^ (1 << p) | (1 << q), d))
+    for p in occd:
+        for q in vird:
+            out.add((u, d ^ (1 << p) | (1 << q)))
+    for p, q in itertools.combinations(occu, 2):
+        for a, b in itertools.combinations(viru, 2):
+            out.add((u ^ (1 << p) ^ (1 << q) | (1 << a) | (1 << b), d))
+    for p, q in itertools.combinations(occd, 2):
+        for a, b in itertools.combinations(vird, 2):
+            out.add((u, d ^ (1 << p) ^ (1 << q) | (1 << a) | (1 << b)))
+    for p in occu:
+        for a in viru:
+            nu = u ^ (1 << p) | (1 << a)
+            for q in occd:
+                for b in vird:
+                    out.add((nu, d ^ (1 << q) | (1 << b)))
+    return out
+
+
+def test_stochastic_pt_sample_equals_direct_formula(oracle):
+    """Independent check of the stochastic-PT sample restatement on C2 (parity-unpinned by the reference): with eps_pt -> 0 and no
+    'big' part (eps_pt_big huge) one sample must equal, term by term, the estimator of hci.f90:1616-1632 written directly with full
+    matrix elements: sum_k [ (sum_i H_ki c_i w_i)^2 + sum_i (H_ki c_i)^2 ((n_mc-1) w_i - w_i^2) ] / (E - H_kk) / (n_mc (n_mc-1)),
+    k over everything outside the variational list that the sampled determinants connect to."""
+    S = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=False, z=1, hf_symmetry=1)
+    r = S.hci(5e-2, n_states=1, max_iters=1)
+    up, dn, w, e = r["up"], r["dn"], r["wts"][:, 0], r["energy"][0]
+    key = [(int(u[0]), int(d[0])) for u, d in zip(up, dn)]
+    o = np.array(sorted(range(len(key)), key=lambda i: key[i]))
+    up, dn, w = up[o], dn[o], w[o]
+    n, n_mc = len(up), 7
+    V = {(int(u[0]), int(d[0])) for u, d in zip(up, dn)}
+    rng = np.random.default_rng(11)
+    prob = np.abs(w) / np.abs(w).sum()
+    idx, counts = np.unique(rng.choice(n, size=n_mc, p=prob), return_counts=True)
+    wop = counts / prob[idx]
+    est, nconn = S.pt2_sample(up, dn, up[idx], dn[idx], w[idx], wop, n_mc, e, 1e-13, 1e9)
+    ext = sorted({x for i in idx for x in _all_excitations(int(up[i][0]), int(dn[i][0]), 26)} - V)
+    m = len(ext)
+    au = oracle.dets_to_u64([a for a, b in ext]); ad = oracle.dets_to_u64([b for a, b in ext])
+    t1, t2 = np.zeros(m), np.zeros(m)
+    for q, i in enumerate(idx):
+        hc = S.elements(au, ad, np.repeat(up[i:i + 1], m, axis=0), np.repeat(dn[i:i + 1], m, axis=0)) * w[i]
+        t1 += hc * wop[q]
+        t2 += hc ** 2 * ((n_mc - 1) * wop[q] - wop[q] ** 2)
+    haa = S.elements(au, ad, au, ad)
+    ref = float(np.sum((t1 ** 2 + t2) / (e - haa))) / (n_mc * (n_mc - 1))
+    assert abs(est - ref) < 1e-12 * max(1.0, abs(ref)) and est != 0.0
+
+
+def test_stochastic_pt_is_unbiased(oracle):
+    """Size-independent property of second_order_pt_alias: the mean of the per-sample energies estimates the DIFFERENCE between the
+    deterministic corrections at eps_pt and eps_pt_big (hci.f90:1428: 'This is the difference between the PT correction for eps_pt
+    and eps_pt_big').  600 samples of 40 determinants on a small C2 wavefunction: the mean must agree with pt2(eps_pt) - pt2(eps_pt_big)
+    within 4 standard errors, and the standard error the loop reports must match the scatter of the samples."""
+    S = oracle.System.chem(C2_FCIDUMP, 26, 8, 4, C2_ORBSYM, time_sym=False, z=1, hf_symmetry=1)
+    r = S.hci(2e-2, n_states=1, max_iters=1)
+    up, dn, w, e = r["up"], r["dn"], r["wts"][:, 0], r["energy"][0]
+    key = [(int(u[0]), int(d[0])) for u, d in zip(up, dn)]
+    o = np.array(sorted(range(len(key)), key=lambda i: key[i]))
+    up, dn, w = up[o], dn[o], w[o]
+    eps_pt, eps_big = 1e-4, 2e-3
+    exact = S.pt2(up, dn, w, e, eps_pt)[0] - S.pt2(up, dn, w, e, eps_big)[0]
+    res = S.pt2_alias(up, dn, w, e, eps_pt, eps_big, 40, 0.0, [12, 34, 56, 79], max_samples=600)
+    assert len(res["e_now"]) == 600                       # target_error = 0: runs to max_samples
+    mean, sem = res["e_now"].mean(), res["e_now"].std(ddof=1) / np.sqrt(600)
+    assert abs(res["pt_energy"] - mean) < 1e-15 and abs(res["std_dev"] - sem) < 1e-12 * max(1.0, sem)
+    assert exact < 0 and abs(mean - exact) < 4 * sem, (mean, exact, sem)
