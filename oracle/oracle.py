@@ -65,6 +65,10 @@ def lib():
         L.orc_pt2.restype = C.c_double
         L.orc_pt2_sample.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, i32, dbl, dbl, dbl, vp]
         L.orc_pt2_sample.restype = dbl
+        L.orc_pt2_sample_terms.argtypes = [vp, i64, vp, vp, vp, vp, i32, dbl, dbl, i64, vp, vp, vp]
+        L.orc_pt2_sample_terms.restype = i64
+        L.orc_pt2_sample_energy.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, i32, dbl]
+        L.orc_pt2_sample_energy.restype = dbl
         L.orc_pt2_alias.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, i32, vp, vp, vp]
         L.orc_pt2_alias.restype = i32
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
@@ -234,6 +238,30 @@ class System:
         e = lib().orc_pt2_sample(self.h, len(up), _p(up), _p(dn), len(su), _p(su), _p(sd), _p(sc), _p(sw), int(n_mc), float(var_energy),
                                  float(eps_pt), float(eps_pt_big), C.addressof(nconn))
         return e, nconn.value
+
+    def pt2_sample_terms(self, s_up, s_dn, s_coeffs, s_w_over_p, n_mc, eps_pt, eps_pt_big):
+        """merged output of find_doubly_excited for (a share of) one sample (semistoch.f90:2044-2117): the distinct connected
+        determinants in label order with their sums term1, term2, term1_big, term2_big -> (up, dn, terms[nd, 4])"""
+        su = np.ascontiguousarray(s_up, dtype=np.uint64).reshape(-1, 2)
+        sd = np.ascontiguousarray(s_dn, dtype=np.uint64).reshape(-1, 2)
+        sc = np.ascontiguousarray(s_coeffs, dtype=np.float64).reshape(-1)
+        sw = np.ascontiguousarray(s_w_over_p, dtype=np.float64).reshape(-1)
+        args = (self.h, len(su), _p(su), _p(sd), _p(sc), _p(sw), int(n_mc), float(eps_pt), float(eps_pt_big))
+        nd = lib().orc_pt2_sample_terms(*args, 0, None, None, None)
+        ou = np.zeros((nd, 2), dtype=np.uint64)
+        od = np.zeros((nd, 2), dtype=np.uint64)
+        t = np.zeros((nd, 4))
+        lib().orc_pt2_sample_terms(*args, nd, _p(ou), _p(od), _p(t))
+        return ou, od, t
+
+    def pt2_sample_energy(self, up, dn, c_up, c_dn, terms, n_mc, var_energy):
+        """the k loop of second_order_pt_alias (hci.f90:1616-1654) over merged per-determinant sums (label-sorted variational list)"""
+        up = np.ascontiguousarray(up, dtype=np.uint64).reshape(-1, 2)
+        dn = np.ascontiguousarray(dn, dtype=np.uint64).reshape(-1, 2)
+        cu = np.ascontiguousarray(c_up, dtype=np.uint64).reshape(-1, 2)
+        cd = np.ascontiguousarray(c_dn, dtype=np.uint64).reshape(-1, 2)
+        t = np.ascontiguousarray(terms, dtype=np.float64).reshape(-1, 4)
+        return lib().orc_pt2_sample_energy(self.h, len(up), _p(up), _p(dn), len(cu), _p(cu), _p(cd), _p(t), int(n_mc), float(var_energy))
 
     def pt2_alias(self, up, dn, wts, var_energy, eps_pt, eps_pt_big, n_mc, target_error, seed4, max_samples=1000):
         """the sampling loop of second_order_pt_alias (one core, n_mc > 0) with the reference's rannyu stream ->

@@ -1663,9 +1663,11 @@ static int sample_alias(Rannyu &R, int K, const std::vector<int> &J, const std::
 //   e = sum over k outside the variational space of (term1^2 + term2 - term1_big^2 - term2_big) / (E_var - H_kk)
 // returned divided by n_mc (n_mc - 1) (hci.f90:1654).  (up, dn) = the variational list; (s_up, s_dn, s_c, s_wop) = the distinct
 // sampled determinants with their coefficients and count/probability ratios.
-double orc_pt2_sample(void *h, long long n, const det_t *up, const det_t *dn, long long m, const det_t *s_up, const det_t *s_dn, const double *s_c,
-                      const double *s_wop, int n_mc, double var_energy, double eps_pt, double eps_pt_big, long long *n_connected) {
-  System &S = *(System *)h;
+// per-determinant sums of one sample: the merged output of find_doubly_excited (semistoch.f90:2088-2117), sorted by label.
+// Returns the number of distinct connected determinants; when out_up != nullptr (capacity cap) also writes them with their four sums
+// terms[4*k + 0..3] = term1, term2, term1_big, term2_big.  A rank of a multi-core run calls this with ITS share of the sample.
+static long long pt2_sample_terms(System &S, long long m, const det_t *s_up, const det_t *s_dn, const double *s_c, const double *s_wop, int n_mc, double eps_pt,
+                                  double eps_pt_big, std::vector<det_t> &ou, std::vector<det_t> &od, std::vector<double> &terms) {
   if (S.model == 0) chem_max_double(S); else if (S.model == 1) heg_max_double(S);
   std::vector<det_t> cu, cd, tu, td;
   std::vector<double> t1, t2, t1b, t2b;
@@ -1691,24 +1693,53 @@ double orc_pt2_sample(void *h, long long n, const det_t *up, const det_t *dn, lo
   std::vector<size_t> ord(cu.size());
   for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
   std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cu[a] < cu[b] || (cu[a] == cu[b] && cd[a] < cd[b]); });
-  double e = 0.0;
-  long long distinct = 0;
+  ou.clear(); od.clear(); terms.clear();
   size_t k = 0;
   while (k < ord.size()) {
     const det_t au = cu[ord[k]], ad = cd[ord[k]];
     double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
     while (k < ord.size() && cu[ord[k]] == au && cd[ord[k]] == ad) { a1 += t1[ord[k]]; a2 += t2[ord[k]]; b1 += t1b[ord[k]]; b2 += t2b[ord[k]]; k++; }
-    distinct++;
+    ou.push_back(au); od.push_back(ad);
+    terms.push_back(a1); terms.push_back(a2); terms.push_back(b1); terms.push_back(b2);
+  }
+  return (long long)ou.size();
+}
+long long orc_pt2_sample_terms(void *h, long long m, const det_t *s_up, const det_t *s_dn, const double *s_c, const double *s_wop, int n_mc, double eps_pt,
+                               double eps_pt_big, long long cap, det_t *out_up, det_t *out_dn, double *out_terms) {
+  std::vector<det_t> ou, od;
+  std::vector<double> terms;
+  const long long nd = pt2_sample_terms(*(System *)h, m, s_up, s_dn, s_c, s_wop, n_mc, eps_pt, eps_pt_big, ou, od, terms);
+  if (out_up && nd <= cap) {
+    memcpy(out_up, ou.data(), nd * sizeof(det_t));
+    memcpy(out_dn, od.data(), nd * sizeof(det_t));
+    memcpy(out_terms, terms.data(), 4 * nd * sizeof(double));
+  }
+  return nd;
+}
+// the k loop of second_order_pt_alias (hci.f90:1616-1632) over merged per-determinant sums, divided by n_mc (n_mc - 1) (:1654)
+double orc_pt2_sample_energy(void *h, long long n, const det_t *up, const det_t *dn, long long nd, const det_t *cu, const det_t *cd, const double *terms, int n_mc,
+                             double var_energy) {
+  System &S = *(System *)h;
+  double e = 0.0;
+  for (long long k = 0; k < nd; k++) {
     long long lo = 0, hi = n;                                   // binary_search in the (label-sorted) variational list
     while (lo < hi) {
       const long long mid = (lo + hi) >> 1;
-      if (up[mid] < au || (up[mid] == au && dn[mid] < ad)) lo = mid + 1; else hi = mid;
+      if (up[mid] < cu[k] || (up[mid] == cu[k] && dn[mid] < cd[k])) lo = mid + 1; else hi = mid;
     }
-    const bool in_var = lo < n && up[lo] == au && dn[lo] == ad;
-    if (!in_var) e += 1.0 / (var_energy - hamiltonian(S, au, ad, au, ad)) * (a1 * a1 + a2 - b1 * b1 - b2);
+    const bool in_var = lo < n && up[lo] == cu[k] && dn[lo] == cd[k];
+    const double a1 = terms[4 * k], a2 = terms[4 * k + 1], b1 = terms[4 * k + 2], b2 = terms[4 * k + 3];
+    if (!in_var) e += 1.0 / (var_energy - hamiltonian(S, cu[k], cd[k], cu[k], cd[k])) * (a1 * a1 + a2 - b1 * b1 - b2);
   }
-  if (n_connected) *n_connected = distinct;
   return e / (n_mc * (double)(n_mc - 1));
+}
+double orc_pt2_sample(void *h, long long n, const det_t *up, const det_t *dn, long long m, const det_t *s_up, const det_t *s_dn, const double *s_c,
+                      const double *s_wop, int n_mc, double var_energy, double eps_pt, double eps_pt_big, long long *n_connected) {
+  std::vector<det_t> ou, od;
+  std::vector<double> terms;
+  const long long nd = pt2_sample_terms(*(System *)h, m, s_up, s_dn, s_c, s_wop, n_mc, eps_pt, eps_pt_big, ou, od, terms);
+  if (n_connected) *n_connected = nd;
+  return orc_pt2_sample_energy(h, n, up, dn, nd, ou.data(), od.data(), terms.data(), n_mc, var_energy);
 }
 // The sampling loop of second_order_pt_alias for one core and n_mc > 0 (hci.f90:1387-1400,1430-1452,1654-1670): probabilities
 // |c_i| / sum|c|, alias tables, n_mc draws per sample (the same rannyu stream as the reference when seeded with irand_seed(:,1)),

@@ -200,3 +200,67 @@ def test_distributed_slice_data_flow_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert sum(m for _, _, m in res) == 277
+
+
+def _worker_stochastic_pt(rank, world, port, q):
+    """the N > 1 data flow of one stochastic-PT sample (csrc/select.cu: pt2_core with 4 channels): every rank holds the SAME sample
+    (same rannyu stream), takes the sampled determinants rank, rank + world, ..., builds its per-determinant sums term1 / term2 /
+    term1_big / term2_big, the lists are merged by a padded all-gather + a sum per determinant, and every rank evaluates the k loop
+    on the merged sums -- emulated with the oracle per rank over gloo; must equal the single-rank sample"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import oracle as O
+    from conftest import label_sorted
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = O.System.heg(3, 0.5, 14, 7, 1.49)
+    r = S.hci(1e-3, n_states=1, max_iters=1)           # 277 determinants
+    up, dn, w = label_sorted(r)
+    e = r["energy"][0]
+    n, n_mc, eps_pt, eps_big = len(up), 60, 2e-6, 5e-4
+    rng = np.random.default_rng(7)                       # the same draws on every rank
+    prob = np.abs(w) / np.abs(w).sum()
+    idx, counts = np.unique(rng.choice(n, size=n_mc, p=prob), return_counts=True)
+    wop = counts / prob[idx]
+    mine = np.arange(rank, len(idx), world)
+    lu, ld, lt = S.pt2_sample_terms(up[idx][mine], dn[idx][mine], w[idx][mine], wop[mine], n_mc, eps_pt, eps_big)
+    # padded all-gather of (determinant, 4 sums)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(lu)], dtype=torch.int64))
+    mx = int(max(s.item() for s in sizes))
+    pd_ = torch.zeros((mx, 4), dtype=torch.int64)
+    pd_[:len(lu)] = torch.from_numpy(np.concatenate([lu, ld], axis=1).astype(np.int64))
+    pt_ = torch.zeros((mx, 4), dtype=torch.float64)
+    pt_[:len(lu)] = torch.from_numpy(lt)
+    alld = [torch.zeros((mx, 4), dtype=torch.int64) for _ in range(world)]
+    allt = [torch.zeros((mx, 4), dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(alld, pd_)
+    dist.all_gather(allt, pt_)
+    merged = {}
+    for k in range(world):                                # rank order: the same sums on every rank
+        m = int(sizes[k].item())
+        for d4, t4 in zip(alld[k][:m].numpy().astype(np.uint64), allt[k][:m].numpy()):
+            key = (int(d4[1]) << 64 | int(d4[0]), int(d4[3]) << 64 | int(d4[2]))
+            merged[key] = merged.get(key, 0.0) + t4
+    keys = sorted(merged)
+    cu = O.dets_to_u64([a for a, b in keys]); cd = O.dets_to_u64([b for a, b in keys])
+    e_merged = S.pt2_sample_energy(up, dn, cu, cd, np.array([merged[k] for k in keys]), n_mc, e)
+    e_single, nconn = S.pt2_sample(up, dn, up[idx], dn[idx], w[idx], wop, n_mc, e, eps_pt, eps_big)
+    q.put((rank, float(e_merged), float(e_single), len(keys), int(nconn)))
+    dist.destroy_process_group()
+
+
+def test_stochastic_pt_sample_merge_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_stochastic_pt, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1]                                      # identical on both ranks
+    for _, em, es, nk, nc in res:
+        assert nk == nc and es != 0.0 and abs(em - es) <= 1e-13 * abs(es), res
