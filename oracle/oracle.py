@@ -69,7 +69,7 @@ def lib():
         L.orc_pt2_sample_terms.restype = i64
         L.orc_pt2_sample_energy.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, i32, dbl]
         L.orc_pt2_sample_energy.restype = dbl
-        L.orc_pt2_alias.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, i32, vp, vp, vp]
+        L.orc_pt2_alias.argtypes = [vp, i64, vp, vp, vp, dbl, dbl, dbl, i32, dbl, vp, i32, vp, vp, vp, vp]
         L.orc_pt2_alias.restype = i32
         L.orc_projector_step.argtypes = [i64, vp, vp, vp, dbl, dbl, vp, vp]
         L.orc_select.restype = i64
@@ -273,9 +273,10 @@ class System:
         e_now = np.zeros(max_samples)
         nd = np.zeros(max_samples, dtype=np.int32)
         out2 = np.zeros(2)
+        nc = np.zeros(max_samples, dtype=np.int64)
         ns = lib().orc_pt2_alias(self.h, len(up), _p(up), _p(dn), _p(w), float(var_energy), float(eps_pt), float(eps_pt_big), int(n_mc),
-                                 float(target_error), _p(seed), int(max_samples), _p(e_now), _p(nd), _p(out2))
-        return {"pt_energy": out2[0], "std_dev": out2[1], "e_now": e_now[:ns].copy(), "n_distinct": nd[:ns].copy()}
+                                 float(target_error), _p(seed), int(max_samples), _p(e_now), _p(nd), _p(out2), _p(nc))
+        return {"pt_energy": out2[0], "std_dev": out2[1], "e_now": e_now[:ns].copy(), "n_distinct": nd[:ns].copy(), "n_connected": nc[:ns].copy()}
 
     def hci(self, eps_var, eps_var_sched=(), n_states=1, max_iters=50, max_dets=0):
         sched = np.zeros(30)

@@ -1745,9 +1745,10 @@ double orc_pt2_sample(void *h, long long n, const det_t *up, const det_t *dn, lo
 // |c_i| / sum|c|, alias tables, n_mc draws per sample (the same rannyu stream as the reference when seeded with irand_seed(:,1)),
 // duplicates merged with counts, Welford mean / variance; stops when sample >= 10 and the variance of the mean is below
 // target_error^2, or after max_samples.  (up, dn, wts) must be sorted by label.  e_now[s], n_distinct[s]: per-sample outputs
-// (capacity max_samples).  Returns the number of samples taken; out2 = {pt_energy, std_dev}.
+// (capacity max_samples), n_conn[s] (optional) = connected determinants of the sample.  Returns the number of samples taken;
+// out2 = {pt_energy, std_dev}.
 int orc_pt2_alias(void *h, long long n, const det_t *up, const det_t *dn, const double *wts, double var_energy, double eps_pt, double eps_pt_big,
-                  int n_mc, double target_error, const int *iseed4, int max_samples, double *e_now, int *n_distinct, double *out2) {
+                  int n_mc, double target_error, const int *iseed4, int max_samples, double *e_now, int *n_distinct, double *out2, long long *n_conn) {
   Rannyu R;
   R.setrn(iseed4);
   double norm = 0.0;
@@ -1776,6 +1777,7 @@ int orc_pt2_alias(void *h, long long n, const det_t *up, const det_t *dn, const 
                                     eps_pt_big, &nconn);
     if (e_now) e_now[sample - 1] = e;
     if (n_distinct) n_distinct[sample - 1] = (int)su.size();
+    if (n_conn) n_conn[sample - 1] = nconn;               // ndets_connected of this sample's find_doubly_excited call
     const double oldM = mean;                                 // welford (tools.f90:1761-1778)
     mean = mean + (e - mean) / sample;
     S_e2 = S_e2 + (e - mean) * (e - oldM);

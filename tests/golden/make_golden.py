@@ -112,6 +112,9 @@ def heg_from_reference_log():
             m = re.search(r"Second-order PT energy lowering=\s*(\S+) \+- (\S+) \(\s*(\S+)\s+(\S+)\)", ln)
             if m:
                 sto["pt_total"], sto["std_dev"], sto["pt_diff"] = float(m.group(1)), float(m.group(2)), float(m.group(4))
+            m = re.search(r"ndets, ndets_connected\(total\), Variational, PT, Total Energies=\s*(\d+)\s+(\d+)", ln)
+            if m:
+                sto["ndets_connected_last_sample"] = int(m.group(2))                  # ndets_connected left by the last find_doubly_excited call
         sto["eps_pt"], sto["eps_pt_big"] = 2e-7, out["pt_big"]["eps_pt_big"]          # i_st: pt_eps; &selected_ci eps_pt_big
         out["pt_stochastic"] = sto
     json.dump(out, open(os.path.join(HERE, "heg_o_det_ref.json"), "w"), indent=1)

@@ -134,6 +134,7 @@ def test_heg_stochastic_pt_reproduces_reference_log(oracle):
     res = S.pt2_alias(up, dn, w, r["energy"][0], g["eps_pt"], g["eps_pt_big"], g["n_mc"], g["target_error"], g["irand_seed_1"], max_samples=400)
     assert len(res["e_now"]) == len(g["samples"]) == 143                      # same stopping sample
     assert res["n_distinct"].tolist() == g["n_ref"]                            # same draws
+    assert int(res["n_connected"][-1]) == g["ndets_connected_last_sample"] == 23726   # o_st_ref:882 "ndets_connected(total)"
     assert np.max(np.abs(res["e_now"] - np.array([x["e_now"] for x in g["samples"]]))) < 5.1e-10
     assert abs(res["pt_energy"] - g["pt_diff"]) < 5.1e-10 and abs(res["std_dev"] - g["std_dev"]) < 5.1e-10
     de_big, _ = S.pt2(up, dn, w, r["energy"][0], g["eps_pt_big"])
